@@ -1,0 +1,360 @@
+// CPU ORACLE -- TEST INFRASTRUCTURE ONLY.  Exports the kzgb200.h C ABI on top of the scalar
+// multithreaded CPU implementation, so that tests can diff the CUDA library against it stage by
+// stage, and bench.py can time it as the reported CPU baseline ("cpu_baseline", kind "port").
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs load it.
+// Upstream reference is LICENSE-only (/root/reference/LICENSE:1-201); spec = BASELINE.json:5.
+#include <array>
+#include <chrono>
+#include <new>
+
+#include "kzg.hpp"
+#include "../include/kzgb200.h"
+
+using namespace orc;
+
+struct kzgb_ctx {
+    Setup setup;
+    int threads;
+    std::vector<Shard> shards;
+    Artifacts art;
+    float stage_ms[KZGB_N_STAGES] = {0};
+    float msm_ms[4] = {0};
+};
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" {
+
+const char* kzgb_version(void) { return "kzgb-oracle-cpu 0.1"; }
+
+kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const uint8_t* g2m, size_t n2, const int*,
+                         int n_devices, size_t) {
+    if (!out || !g1m || !g2m || n1 < 1 || n2 < 2) return KZGB_BADARGS;
+    kzgb_ctx* c = new (std::nothrow) kzgb_ctx();
+    if (!c) return KZGB_MALLOC;
+    if (g1_decompress(c->setup.g1, g1m) != ST_OK || c->setup.g1.inf || !g2_decompress(c->setup.g2_0, g2m) ||
+        !g2_decompress(c->setup.g2_1, g2m + 96)) {
+        delete c;
+        return KZGB_BADARGS;
+    }
+    c->threads = (int)std::thread::hardware_concurrency();
+    if (c->threads < 1) c->threads = 1;
+    c->shards.resize(n_devices > 0 ? n_devices : 1);
+    *out = c;
+    return KZGB_OK;
+}
+void kzgb_ctx_free(kzgb_ctx* c) { delete c; }
+
+int kzgb_set_threads(kzgb_ctx* c, int n) {
+    if (c && n > 0) c->threads = n;
+    return c ? c->threads : 0;
+}
+
+static void partial_to_bytes(uint8_t* out, const Partial& p) {
+    G1J s12 = p.s1.add(p.s2);
+    auto put = [](uint8_t* o, const G1J& j) {
+        if (j.is_inf()) { memset(o, 0, 144); return; }
+        j.X.to_bytes_be(o); j.Y.to_bytes_be(o + 48); j.Z.to_bytes_be(o + 96);
+    };
+    put(out, s12);
+    put(out + 144, p.s3);
+    p.sum_ry.to_bytes_be(out + 288);
+}
+
+static kzgb_ret verify_impl(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
+                            kzgb_ctx* c, bool single) {
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!c || !C || !z || !y || !pi || n == 0) return KZGB_BADARGS;
+    double t0 = now_ms();
+    Shard& sh = c->shards[0];
+    size_t nch = (n + CHUNK - 1) / CHUNK;
+    std::vector<u8> dig(32 * nch);
+    shard_phase1(sh, C, z, y, pi, n, c->threads, dig.data());
+    double t1 = now_ms();
+    c->art = Artifacts();
+    c->art.n = n;
+    c->art.n_bad_points = sh.bad_points;
+    c->art.n_bad_scalars = sh.bad_scalars;
+    if (sh.bad_points || sh.bad_scalars) return KZGB_BADARGS;
+    if (single) memset(c->art.root, 0, 32); else fs_root(c->art.root, dig.data(), nch, n);
+    Partial p = shard_phase2(sh, c->art.root, 0, c->threads, single);
+    double t2 = now_ms();
+    *ok = combine_verify(c->art, c->setup, &p, 1);
+    double t3 = now_ms();
+    memset(c->stage_ms, 0, sizeof c->stage_ms);
+    c->stage_ms[1] = (float)(t1 - t0);
+    c->stage_ms[6] = (float)(t2 - t1);
+    c->stage_ms[8] = (float)(t3 - t2);
+    c->stage_ms[9] = (float)(t3 - t0);
+    return KZGB_OK;
+}
+
+kzgb_ret verify_kzg_proof(bool* ok, const uint8_t C[48], const uint8_t z[32], const uint8_t y[32], const uint8_t pi[48],
+                          kzgb_ctx* c) {
+    return verify_impl(ok, C, z, y, pi, 1, c, true);
+}
+kzgb_ret verify_kzg_proof_batch(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
+                                kzgb_ctx* c) {
+    return verify_impl(ok, C, z, y, pi, n, c, false);
+}
+kzgb_ret verify_kzg_proof_batch_device(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi,
+                                       size_t n, kzgb_ctx* c, void*) {
+    return verify_impl(ok, C, z, y, pi, n, c, false);
+}
+
+kzgb_ret kzgb_shard_phase1(kzgb_ctx* c, int slot, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi,
+                           size_t n, int, void*, uint8_t* dig, uint32_t* n_bad) {
+    if (!c || slot < 0 || slot >= (int)c->shards.size() || !C || !z || !y || !pi || !dig || n == 0) return KZGB_BADARGS;
+    Shard& sh = c->shards[slot];
+    shard_phase1(sh, C, z, y, pi, n, c->threads, dig);
+    if (n_bad) *n_bad = sh.bad_points + sh.bad_scalars;
+    return (sh.bad_points || sh.bad_scalars) ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret kzgb_fs_root(uint8_t root[32], const uint8_t* dig, size_t nch, uint64_t n_total) {
+    if (!root || !dig) return KZGB_BADARGS;
+    fs_root(root, dig, nch, n_total);
+    return KZGB_OK;
+}
+kzgb_ret kzgb_shard_phase2(kzgb_ctx* c, int slot, const uint8_t root[32], uint64_t off, void*, uint8_t out[KZGB_PARTIAL_BYTES]) {
+    if (!c || slot < 0 || slot >= (int)c->shards.size() || !root || !out) return KZGB_BADARGS;
+    Partial p = shard_phase2(c->shards[slot], root, off, c->threads);
+    partial_to_bytes(out, p);
+    return KZGB_OK;
+}
+kzgb_ret kzgb_combine_verify(kzgb_ctx* c, const uint8_t* parts, int np, bool* ok) {
+    if (!c || !parts || np < 1 || !ok) return KZGB_BADARGS;
+    *ok = false;
+    std::vector<Partial> ps(np);
+    for (int i = 0; i < np; ++i) {
+        const uint8_t* b = parts + (size_t)KZGB_PARTIAL_BYTES * i;
+        auto get = [](G1J& j, const uint8_t* o) {
+            return Fp::from_bytes_be(j.X, o) && Fp::from_bytes_be(j.Y, o + 48) && Fp::from_bytes_be(j.Z, o + 96);
+        };
+        ps[i].s2 = G1J::inf();
+        if (!get(ps[i].s1, b) || !get(ps[i].s3, b + 144) || !Fr::from_bytes_be(ps[i].sum_ry, b + 288)) return KZGB_BADARGS;
+    }
+    *ok = combine_verify(c->art, c->setup, ps.data(), np);
+    return KZGB_OK;
+}
+
+kzgb_ret kzgb_g1_decompress_batch(uint8_t* aff, uint8_t* st, const uint8_t* in, size_t m, kzgb_ctx* c) {
+    if (!aff || !st || !in || !c) return KZGB_BADARGS;
+    parallel_for(m, c->threads, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            G1A p;
+            st[i] = g1_decompress(p, in + 48 * i);
+            g1_affine_bytes(aff + 96 * i, p);
+        }
+    });
+    return KZGB_OK;
+}
+kzgb_ret kzgb_fs_challenges(uint8_t root[32], uint8_t* r_out, const uint8_t* C, const uint8_t* z, const uint8_t* y,
+                            const uint8_t* pi, size_t n, kzgb_ctx* c) {
+    if (!root || !r_out || !C || !z || !y || !pi || !c || n == 0) return KZGB_BADARGS;
+    size_t nch = (n + CHUNK - 1) / CHUNK;
+    std::vector<u8> dig(32 * nch);
+    fs_chunk_digests(dig.data(), C, z, y, pi, n, c->threads);
+    fs_root(root, dig.data(), nch, n);
+    parallel_for(n, c->threads, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) fs_r(r_out + 16 * i, root, i);
+    });
+    return KZGB_OK;
+}
+kzgb_ret kzgb_g1_msm(uint8_t out[96], const uint8_t* pts, const uint8_t* sc, size_t m, int nbits, kzgb_ctx* c) {
+    if (!out || !pts || !sc || !c || (nbits != 255 && nbits != 128)) return KZGB_BADARGS;
+    std::vector<G1A> p(m);
+    std::vector<std::array<u64, 4>> k(m);
+    for (size_t i = 0; i < m; ++i) {
+        Fr s;
+        if (!g1_from_affine_bytes(p[i], pts + 96 * i) || !Fr::from_bytes_be(s, sc + 32 * i)) return KZGB_BADARGS;
+        s.to_raw(k[i].data());
+        if (nbits == 128 && (k[i][2] | k[i][3])) return KZGB_BADARGS;
+    }
+    double t0 = now_ms();
+    G1J r = msm(p.data(), (const u64(*)[4])k.data(), m, nbits, c->threads);
+    c->msm_ms[3] = (float)(now_ms() - t0);
+    g1_affine_bytes(out, g1_affine(r));
+    return KZGB_OK;
+}
+kzgb_ret kzgb_g1_msm_times(float ms[4], kzgb_ctx* c) {
+    if (!ms || !c) return KZGB_BADARGS;
+    memcpy(ms, c->msm_ms, sizeof c->msm_ms);
+    return KZGB_OK;
+}
+kzgb_ret kzgb_pairing_check(bool* ok, const uint8_t A[96], const uint8_t B[96], kzgb_ctx* c) {
+    if (!ok || !A || !B || !c) return KZGB_BADARGS;
+    G1A P[2];
+    if (!g1_from_affine_bytes(P[0], A) || !g1_from_affine_bytes(P[1], B)) return KZGB_BADARGS;
+    G2A Q[2] = {c->setup.g2_0, c->setup.g2_1};
+    *ok = pairing_product_is_one(P, Q, 2);
+    return KZGB_OK;
+}
+kzgb_ret kzgb_last_artifacts(kzgb_ctx* c, kzgb_artifacts* o) {
+    if (!c || !o) return KZGB_BADARGS;
+    memset(o, 0, sizeof *o);
+    g1_affine_bytes(o->S1, c->art.S1); g1_affine_bytes(o->S2, c->art.S2); g1_affine_bytes(o->S3, c->art.S3);
+    g1_affine_bytes(o->A, c->art.A); g1_affine_bytes(o->B, c->art.B);
+    c->art.sum_ry.to_bytes_be(o->sum_ry);
+    memcpy(o->root, c->art.root, 32);
+    o->n = c->art.n;
+    o->n_bad_points = c->art.n_bad_points;
+    o->n_bad_scalars = c->art.n_bad_scalars;
+    memcpy(o->stage_ms, c->stage_ms, sizeof c->stage_ms);
+    return KZGB_OK;
+}
+
+kzgb_ret kzgb_synth_instance(kzgb_ctx* c, uint64_t seed, uint64_t off, size_t n, uint8_t* C, uint8_t* z, uint8_t* y,
+                             uint8_t* pi, int) {
+    if (!C || !z || !y || !pi) return KZGB_BADARGS;
+    synth_instance(seed, off, n, C, z, y, pi, c ? c->threads : (int)std::thread::hardware_concurrency());
+    return KZGB_OK;
+}
+kzgb_ret kzgb_synth_setup(uint8_t* g1, size_t n1, uint8_t* g2, size_t n2) {
+    if ((n1 && !g1) || (n2 && !g2)) return KZGB_BADARGS;
+    synth_setup(g1, n1, g2, n2);
+    return KZGB_OK;
+}
+// oracle-only: real-polynomial instances (config BJ:7) and planted-invalid helper
+kzgb_ret kzgb_oracle_synth_instance_poly(uint64_t seed, size_t n, size_t ncoef, uint8_t* C, uint8_t* z, uint8_t* y,
+                                         uint8_t* pi, int threads) {
+    synth_instance_poly(seed, n, ncoef, C, z, y, pi, threads > 0 ? threads : (int)std::thread::hardware_concurrency());
+    return KZGB_OK;
+}
+// pi_j <- pi_j + G1 in place (valid subgroup point, wrong opening)
+kzgb_ret kzgb_oracle_plant_invalid(uint8_t* pi, size_t j) {
+    G1A p;
+    if (g1_decompress(p, pi + 48 * j) != ST_OK) return KZGB_BADARGS;
+    g1_compress(pi + 48 * j, g1_affine(p.jac().add(g1_generator().jac())));
+    return KZGB_OK;
+}
+uint64_t kzgb_oracle_plant_index(uint64_t seed, uint64_t n) {
+    u8 b[32];
+    prng_block(b, seed, STREAM_PLANT, 0);
+    u64 v = 0;
+    for (int i = 0; i < 8; ++i) v = v << 8 | b[i];
+    return v % n;
+}
+// oracle-only: slow subgroup decision ([r]P == O) for cross-checking the fast test
+int kzgb_oracle_g1_status_slow(const uint8_t in[48]) {
+    G1A p;
+    return g1_decompress(p, in, 2);
+}
+// oracle-only: tau-shortcut verdict A + tau*B == O (pairing-free)
+int kzgb_oracle_tau_shortcut(const uint8_t A[96], const uint8_t B[96]) {
+    G1A a, b;
+    if (!g1_from_affine_bytes(a, A) || !g1_from_affine_bytes(b, B)) return -1;
+    u64 k[4];
+    test_tau().to_raw(k);
+    return a.jac().add(b.jac().mul(k, 4)).is_inf() ? 1 : 0;
+}
+
+static void fp12_from_bytes(Fp12& f, const u8* b) {
+    for (int k = 0; k < 6; ++k) {
+        Fp::from_bytes_be(f.coef(k).c0, b + 96 * k);
+        Fp::from_bytes_be(f.coef(k).c1, b + 96 * k + 48);
+    }
+}
+static void fp12_to_bytes(u8* b, const Fp12& f) {
+    for (int k = 0; k < 6; ++k) {
+        f.coef(k).c0.to_bytes_be(b + 96 * k);
+        f.coef(k).c1.to_bytes_be(b + 96 * k + 48);
+    }
+}
+
+kzgb_ret kzgb_debug_op(kzgb_ctx* c, int op, const uint8_t* in, uint8_t* out, size_t count) {
+    if (!in || !out) return KZGB_BADARGS;
+    for (size_t i = 0; i < count; ++i) {
+        switch (op) {
+            case KZGB_OP_FP_MUL: case KZGB_OP_FP_ADD: case KZGB_OP_FP_SUB: {
+                Fp a, b;
+                if (!Fp::from_bytes_be(a, in + 96 * i) || !Fp::from_bytes_be(b, in + 96 * i + 48)) return KZGB_BADARGS;
+                Fp r = op == KZGB_OP_FP_MUL ? a * b : (op == KZGB_OP_FP_ADD ? a + b : a - b);
+                r.to_bytes_be(out + 48 * i);
+                break;
+            }
+            case KZGB_OP_FP_SQR: case KZGB_OP_FP_INV: case KZGB_OP_FP_SQRT_CAND: {
+                Fp a;
+                if (!Fp::from_bytes_be(a, in + 48 * i)) return KZGB_BADARGS;
+                Fp r;
+                if (op == KZGB_OP_FP_SQR) r = a.sqr();
+                else if (op == KZGB_OP_FP_INV) r = a.inv();
+                else {
+                    u64 e[6], onev[6] = {1};
+                    add_raw<6>(e, fp_params().mod, onev);
+                    for (int k = 0; k < 6; ++k) e[k] = (e[k] >> 2) | (k < 5 ? e[k + 1] << 62 : 0);
+                    r = a.pow(e, 6);
+                }
+                r.to_bytes_be(out + 48 * i);
+                break;
+            }
+            case KZGB_OP_FR_MUL: case KZGB_OP_FR_ADD: {
+                Fr a, b;
+                if (!Fr::from_bytes_be(a, in + 64 * i) || !Fr::from_bytes_be(b, in + 64 * i + 32)) return KZGB_BADARGS;
+                (op == KZGB_OP_FR_MUL ? a * b : a + b).to_bytes_be(out + 32 * i);
+                break;
+            }
+            case KZGB_OP_G1_ADD: {
+                G1A p, q;
+                if (!g1_from_affine_bytes(p, in + 192 * i) || !g1_from_affine_bytes(q, in + 192 * i + 96)) return KZGB_BADARGS;
+                g1_affine_bytes(out + 96 * i, g1_affine(p.jac().add(q.jac())));
+                break;
+            }
+            case KZGB_OP_G1_DBL: case KZGB_OP_G1_MUL_XSQ: {
+                G1A p;
+                if (!g1_from_affine_bytes(p, in + 96 * i)) return KZGB_BADARGS;
+                u64 k[1] = {X_ABS};
+                G1J r = op == KZGB_OP_G1_DBL ? p.jac().dbl() : p.jac().mul(k, 1).mul(k, 1);
+                g1_affine_bytes(out + 96 * i, g1_affine(r));
+                break;
+            }
+            case KZGB_OP_G1_MUL: {
+                G1A p;
+                Fr s;
+                if (!g1_from_affine_bytes(p, in + 128 * i) || !Fr::from_bytes_be(s, in + 128 * i + 96)) return KZGB_BADARGS;
+                u64 k[4];
+                s.to_raw(k);
+                g1_affine_bytes(out + 96 * i, g1_affine(p.jac().mul(k, 4)));
+                break;
+            }
+            case KZGB_OP_FP12_MUL: {
+                Fp12 a, b;
+                fp12_from_bytes(a, in + 1152 * i);
+                fp12_from_bytes(b, in + 1152 * i + 576);
+                fp12_to_bytes(out + 576 * i, a * b);
+                break;
+            }
+            case KZGB_OP_FP12_FROB1: case KZGB_OP_FP12_FROB2: case KZGB_OP_FP12_INV: case KZGB_OP_FINAL_EXP: {
+                Fp12 a;
+                fp12_from_bytes(a, in + 576 * i);
+                Fp12 r = op == KZGB_OP_FP12_FROB1 ? frob1(a) : op == KZGB_OP_FP12_FROB2 ? frob2(a)
+                         : op == KZGB_OP_FP12_INV ? a.inv() : final_exp(a);
+                fp12_to_bytes(out + 576 * i, r);
+                break;
+            }
+            case KZGB_OP_MILLER_FE: {
+                if (!c) return KZGB_BADARGS;
+                G1A P[2];
+                if (!g1_from_affine_bytes(P[0], in + 192 * i) || !g1_from_affine_bytes(P[1], in + 192 * i + 96)) return KZGB_BADARGS;
+                G2A Q[2] = {c->setup.g2_0, c->setup.g2_1};
+                fp12_to_bytes(out + 576 * i, final_exp(miller_loop_multi(P, Q, 2)));
+                break;
+            }
+            case KZGB_OP_SHA256_64: {
+                Sha256 s;
+                s.update(in + 64 * i, 64);
+                s.final(out + 32 * i);
+                break;
+            }
+            default: return KZGB_BADARGS;
+        }
+    }
+    return KZGB_OK;
+}
+
+kzgb_ret kzgb_imad_peak(kzgb_ctx*, double*, double*) { return KZGB_ERROR; }
+uint64_t kzgb_launch_count(const kzgb_ctx*) { return 0; }
+
+}  // extern "C"

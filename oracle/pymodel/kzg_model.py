@@ -1,0 +1,157 @@
+"""Pure-Python model of the KZG batch-verification semantics (docs: DESIGN.md "SPEC").  TEST INFRASTRUCTURE.
+
+Follows BASELINE.json:5 and SURVEY.md Appendix B (the upstream reference is LICENSE-only,
+/root/reference/LICENSE:1-201, so there is no reference file to cite).  Small n only.
+"""
+from __future__ import annotations
+
+import hashlib
+import struct
+
+from . import bls12_381 as bls
+from .bls12_381 import P, R
+
+CHUNK = 1024
+FIELD_ELEMENTS_PER_BLOB = 4096
+
+TAG_LEAF = b"KZGB200/leaf_v1_"
+TAG_CHUNK = b"KZGB200/chunk_v1"
+TAG_ROOT = b"KZGB200/root_v1_"
+TAG_R = b"KZGB200/r_v1____"
+TAG_PRNG = b"kzgb200/prng"
+assert all(len(t) == 16 for t in (TAG_LEAF, TAG_CHUNK, TAG_ROOT, TAG_R))
+
+TAU = int.from_bytes(hashlib.sha256(b"kzgb200/insecure-test-tau").digest(), "big") % R
+
+
+def sha(b: bytes) -> bytes:
+    return hashlib.sha256(b).digest()
+
+
+# ----------------------------------------------------------------------------- PRNG
+def prng_block(seed: int, stream: int, k: int) -> bytes:
+    return sha(TAG_PRNG + struct.pack(">QQQ", seed, stream, k))
+
+
+def prng_fr(seed: int, stream: int, idx: int) -> int:
+    """idx-th Fr sample of a stream: blocks 2*idx, 2*idx+1 as a 512-bit big-endian integer mod r."""
+    return int.from_bytes(prng_block(seed, stream, 2 * idx) + prng_block(seed, stream, 2 * idx + 1), "big") % R
+
+
+STREAM_A, STREAM_Z, STREAM_Y, STREAM_PLANT, STREAM_POLY = 1, 2, 3, 99, 7
+
+
+# ----------------------------------------------------------------------------- instances
+def gen_instance_shortcut(seed: int, n: int, offset: int = 0):
+    """Scalar-shortcut instances (configs BJ:8-10): a_i stands for f_i(tau)."""
+    C, Z, Y, PI = [], [], [], []
+    for i in range(offset, offset + n):
+        a, z, y = prng_fr(seed, STREAM_A, i), prng_fr(seed, STREAM_Z, i), prng_fr(seed, STREAM_Y, i)
+        q = (a - y) * pow((TAU - z) % R, R - 2, R) % R
+        C.append(bls.g1_compress(bls.g1_mul(a, bls.G1)))
+        PI.append(bls.g1_compress(bls.g1_mul(q, bls.G1)))
+        Z.append(z.to_bytes(32, "big"))
+        Y.append(y.to_bytes(32, "big"))
+    return b"".join(C), b"".join(Z), b"".join(Y), b"".join(PI)
+
+
+def gen_instance_poly(seed: int, n: int, degree_plus_1: int = FIELD_ELEMENTS_PER_BLOB):
+    """Real-polynomial instances (config BJ:7): f_i with `degree_plus_1` random coefficients."""
+    C, Z, Y, PI = [], [], [], []
+    for i in range(n):
+        ft, fz = 0, 0
+        z = prng_fr(seed, STREAM_Z, i)
+        for j in range(degree_plus_1 - 1, -1, -1):          # Horner, highest coefficient first
+            c = prng_fr(seed, STREAM_POLY, i * degree_plus_1 + j)
+            ft = (ft * TAU + c) % R
+            fz = (fz * z + c) % R
+        q = (ft - fz) * pow((TAU - z) % R, R - 2, R) % R
+        C.append(bls.g1_compress(bls.g1_mul(ft, bls.G1)))
+        PI.append(bls.g1_compress(bls.g1_mul(q, bls.G1)))
+        Z.append(z.to_bytes(32, "big"))
+        Y.append(fz.to_bytes(32, "big"))
+    return b"".join(C), b"".join(Z), b"".join(Y), b"".join(PI)
+
+
+def plant_index(seed: int, n: int) -> int:
+    return int.from_bytes(prng_block(seed, STREAM_PLANT, 0)[:8], "big") % n
+
+
+def plant_invalid(PI: bytes, j: int) -> bytes:
+    """pi_j <- pi_j + G1: a valid subgroup point that is the wrong opening."""
+    st, pt = bls.g1_decompress(PI[48 * j:48 * j + 48])
+    assert st == 0
+    return PI[:48 * j] + bls.g1_compress(bls.g1_add(pt, bls.G1)) + PI[48 * j + 48:]
+
+
+def setup_g1(n1: int) -> bytes:
+    return b"".join(bls.g1_compress(bls.g1_mul(pow(TAU, i, R), bls.G1)) for i in range(n1))
+
+
+def setup_g2(n2: int) -> bytes:
+    return b"".join(bls.g2_compress(bls.g2_mul(pow(TAU, i, R), bls.G2)) for i in range(n2))
+
+
+# ----------------------------------------------------------------------------- Fiat-Shamir (App. B.4)
+def fs_leaves(C, Z, Y, PI, n):
+    return [sha(TAG_LEAF + C[48 * i:48 * i + 48] + Z[32 * i:32 * i + 32] + Y[32 * i:32 * i + 32] + PI[48 * i:48 * i + 48])
+            for i in range(n)]
+
+
+def fs_chunk_digests(leaves):
+    return [sha(TAG_CHUNK + b"".join(leaves[j:j + CHUNK])) for j in range(0, len(leaves), CHUNK)]
+
+
+def fs_root(digests, n):
+    return sha(TAG_ROOT + struct.pack(">QQ", FIELD_ELEMENTS_PER_BLOB, n) + b"".join(digests))
+
+
+def fs_r(root: bytes, i: int) -> int:
+    return int.from_bytes(sha(TAG_R + root + struct.pack(">Q", i))[:16], "big")
+
+
+def fs_challenges(C, Z, Y, PI, n):
+    root = fs_root(fs_chunk_digests(fs_leaves(C, Z, Y, PI, n)), n)
+    return root, [fs_r(root, i) for i in range(n)]
+
+
+# ----------------------------------------------------------------------------- verification
+KZGB_OK, KZGB_BADARGS = 0, 1
+
+
+def batch_artifacts(C, Z, Y, PI, n, single=False):
+    """Returns dict(ret, statuses, S1, S2, S3, A, B, sum_ry, root, r) with affine points / None."""
+    out = {"ret": KZGB_OK}
+    cs = [bls.g1_decompress(C[48 * i:48 * i + 48]) for i in range(n)]
+    ps = [bls.g1_decompress(PI[48 * i:48 * i + 48]) for i in range(n)]
+    zs = [int.from_bytes(Z[32 * i:32 * i + 32], "big") for i in range(n)]
+    ys = [int.from_bytes(Y[32 * i:32 * i + 32], "big") for i in range(n)]
+    out["status_c"] = [s for s, _ in cs]
+    out["status_pi"] = [s for s, _ in ps]
+    if any(s for s, _ in cs) or any(s for s, _ in ps) or any(v >= R for v in zs) or any(v >= R for v in ys):
+        out["ret"] = KZGB_BADARGS
+        return out
+    if single:
+        root, r = bytes(32), [1]
+    else:
+        root, r = fs_challenges(C, Z, Y, PI, n)
+    s1 = s2 = s3 = None
+    sum_ry = 0
+    for i in range(n):
+        s1 = bls.g1_add(s1, bls.g1_mul(r[i], cs[i][1]))
+        s2 = bls.g1_add(s2, bls.g1_mul(r[i] * zs[i] % R, ps[i][1]))
+        s3 = bls.g1_add(s3, bls.g1_mul(r[i], ps[i][1]))
+        sum_ry = (sum_ry + r[i] * ys[i]) % R
+    a = bls.g1_add(bls.g1_add(s1, s2), bls.g1_neg(bls.g1_mul(sum_ry, bls.G1)))
+    b = bls.g1_neg(s3)
+    out.update(root=root, r=r, S1=s1, S2=s2, S3=s3, A=a, B=b, sum_ry=sum_ry)
+    return out
+
+
+def verdict_tau_shortcut(art) -> bool:
+    """e(A,G2) e(B,[tau]G2) = 1  <=>  A + tau*B = O  (SURVEY 4.2); pairing-free."""
+    return bls.g1_add(art["A"], bls.g1_mul(TAU, art["B"])) is None
+
+
+def verdict_pairing(art, g2_tau) -> bool:
+    return bls.pairing_product_is_one([(art["A"], bls.G2), (art["B"], g2_tau)])
