@@ -31,7 +31,7 @@ typedef enum { KZGB_OK = 0, KZGB_BADARGS = 1, KZGB_ERROR = 2, KZGB_MALLOC = 3 } 
 enum { KZGB_ST_OK = 0, KZGB_ST_BAD_FLAGS = 1, KZGB_ST_X_GE_P = 2, KZGB_ST_NOT_ON_CURVE = 3, KZGB_ST_NOT_IN_G1 = 4 };
 
 #define KZGB_CHUNK 1024u          /* proofs per Fiat-Shamir chunk digest (App. B.4) */
-#define KZGB_PARTIAL_BYTES 320u   /* per-shard partial: S1+S2 (Jacobian 144 B) | S3 (144 B) | sum r_i y_i (32 B) */
+#define KZGB_PARTIAL_BYTES 320u   /* per-shard partial: A_shard = S1+S2-(sum r_i y_i)G1 (Jacobian X|Y|Z, 144 B) | S3 (144 B) | sum r_i y_i (32 B) */
 #define KZGB_N_STAGES 10
 
 typedef struct kzgb_ctx kzgb_ctx; /* opaque: trusted setup + per-GPU workspaces */

@@ -121,7 +121,7 @@ class Context:
     def __init__(self, klib: KzgLib, g1_monomial, g2_monomial, devices, n_max):
         self.klib, self.lib = klib, klib.lib
         if g1_monomial is None or g2_monomial is None:
-            g1_monomial, g2_monomial = klib.synth_setup(1, 2)
+            g1_monomial, g2_monomial = test_setup()
         devs = None
         nd = 0
         if devices is not None:
@@ -260,6 +260,13 @@ class Context:
 
 
 PKG_DIR = Path(__file__).resolve().parent
+
+
+def test_setup():
+    """The insecure TEST trusted setup (known tau; tools/gen_test_setup.py): ([tau^0]G1, [tau^0..1]G2)."""
+    blob = (PKG_DIR / "data" / "test_setup.bin").read_bytes()
+    return blob[:48], blob[48:240]
+
 PRODUCT_LIB = PKG_DIR / "csrc" / "libkzgb200.so"
 
 

@@ -1,0 +1,650 @@
+// Host orchestration + the C ABI of include/kzgb200.h for the CUDA product library (libkzgb200.so).
+// One DeviceSlot per GPU: own stream, workspaces sized for n_max, pinned mailboxes.  A batch is cut into
+// contiguous shards (multiples of 1024 proofs) over the slots; only chunk digests (32 B / 1024 proofs),
+// the 32-byte root and one 320-byte partial per shard cross the host (BASELINE.json:5: "combined on the
+// host, so no NCCL is needed").  There is NO CPU fallback: every arithmetic step runs in a kernel.
+#include <cstdio>
+#include <chrono>
+#include <new>
+#include <vector>
+
+#include "../../include/kzgb200.h"
+#include "kernels.h"
+
+#define CK(x)                                                                                         \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) {                                                                      \
+            fprintf(stderr, "[kzgb200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return KZGB_ERROR;                                                                        \
+        }                                                                                             \
+    } while (0)
+
+namespace {
+
+struct SortBuf {
+    uint32_t *keys = nullptr, *vals = nullptr, *keys_alt = nullptr, *vals_alt = nullptr, *bucket_start = nullptr;
+    size_t capacity = 0;
+};
+
+struct DeviceSlot {
+    int device = 0;
+    size_t n_max = 0;
+    cudaStream_t stream = nullptr;
+    // staged inputs (host-pointer API)
+    uint8_t *dC = nullptr, *dz = nullptr, *dy = nullptr, *dpi = nullptr;
+    Fp* pts = nullptr;                 // 2*n_max + 1 affine points: C | pi | G
+    uint8_t* status = nullptr;         // 2*n_max
+    uint32_t* counters = nullptr;      // [0] bad points [1] bad scalars
+    uint32_t *leaves = nullptr, *digests = nullptr, *root_words = nullptr;
+    uint32_t *r = nullptr, *rz = nullptr, *partials = nullptr, *sum_ry = nullptr;
+    SortBuf sortR, sortZ;
+    G1Xyzz *bucketsA = nullptr, *bucketsB = nullptr, *bucketsC = nullptr, *segsums = nullptr, *winsums = nullptr;
+    size_t max_bucketsR = 0, max_bucketsZ = 0, max_segs = 0;
+    void* cub_temp = nullptr;
+    size_t cub_temp_bytes = 0;
+    G1Jac* sums = nullptr;             // [0] S1 [1] S2' [2] S3 [3] A [4] B
+    uint8_t* partial_dev = nullptr;    // 320
+    uint8_t* partials_in = nullptr;    // 320 * 64
+    uint8_t* scratch = nullptr;        // misc byte buffer (debug ops, artefacts): 1 MiB
+    int* result_dev = nullptr;
+    G2Lines* lines = nullptr;
+    Fp* g1_pt = nullptr;
+    int* setup_status = nullptr;
+    Fp* comb = nullptr;
+    bool comb_built = false;
+    // pinned mailboxes
+    uint8_t* h_digests = nullptr;      // 32 * ceil(n_max/1024)
+    uint32_t* h_small = nullptr;       // 64 words: [0..1] counters, [8..15] root words, [16] result
+    uint8_t* h_partial = nullptr;      // 320 * 64
+    cudaEvent_t ev[12] = {};
+    // current shard (between phase 1 and phase 2)
+    const uint8_t *cur_C = nullptr, *cur_z = nullptr, *cur_y = nullptr, *cur_pi = nullptr;
+    size_t cur_n = 0;
+    bool have_sums = false;
+    MsmPlan planR, planZ;
+};
+
+}  // namespace
+
+struct kzgb_ctx {
+    std::vector<DeviceSlot> slots;
+    kzgb_artifacts art;
+    float msm_ms[4] = {0, 0, 0, 0};
+    uint64_t launches_at_create = 0;
+};
+
+namespace {
+
+template <class T>
+cudaError_t dmalloc(T*& p, size_t count) { return cudaMalloc((void**)&p, count * sizeof(T)); }
+
+kzgb_ret slot_alloc_sort(SortBuf& b, size_t cap, size_t buckets) {
+    b.capacity = cap;
+    CK(dmalloc(b.keys, cap)); CK(dmalloc(b.vals, cap)); CK(dmalloc(b.keys_alt, cap)); CK(dmalloc(b.vals_alt, cap));
+    CK(dmalloc(b.bucket_start, buckets + 2));
+    return KZGB_OK;
+}
+
+kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, const uint8_t* g2m) {
+    s.device = device;
+    s.n_max = n_max;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    for (auto& e : s.ev) CK(cudaEventCreate(&e));
+    CK(dmalloc(s.dC, 48 * (n_max + 1))); CK(dmalloc(s.dz, 32 * (n_max + 1))); CK(dmalloc(s.dy, 32 * (n_max + 1))); CK(dmalloc(s.dpi, 48 * (n_max + 1)));
+    CK(dmalloc(s.pts, 2 * (2 * n_max + 2)));
+    CK(dmalloc(s.status, 2 * n_max + 2));
+    CK(dmalloc(s.counters, 8));
+    size_t nch = (n_max + KZGB_CHUNK - 1) / KZGB_CHUNK;
+    CK(dmalloc(s.leaves, 8 * n_max)); CK(dmalloc(s.digests, 8 * nch)); CK(dmalloc(s.root_words, 8));
+    CK(dmalloc(s.r, 4 * n_max)); CK(dmalloc(s.rz, 8 * (n_max + 1)));
+    CK(dmalloc(s.partials, 8 * ((n_max + 127) / 128 + 1))); CK(dmalloc(s.sum_ry, 8));
+    MsmPlan pr = msm_make_plan(n_max, 128), pz = msm_make_plan(n_max + 1, 255);
+    s.max_bucketsR = pr.total_buckets;
+    s.max_bucketsZ = pz.total_buckets;
+    s.max_segs = pz.total_segs > pr.total_segs ? pz.total_segs : pr.total_segs;
+    // small n use narrower windows (more of them): keep generous floors so every n <= n_max fits
+    size_t capR = (size_t)pr.W * n_max + 4096, capZ = (size_t)pz.W * (n_max + 1) + 8192;
+    if (slot_alloc_sort(s.sortR, capR, s.max_bucketsR + 512)) return KZGB_ERROR;
+    if (slot_alloc_sort(s.sortZ, capZ, s.max_bucketsZ + 512)) return KZGB_ERROR;
+    CK(dmalloc(s.bucketsA, s.max_bucketsR + 512)); CK(dmalloc(s.bucketsB, s.max_bucketsR + 512));
+    CK(dmalloc(s.bucketsC, s.max_bucketsZ + 512));
+    CK(dmalloc(s.segsums, s.max_segs + 512)); CK(dmalloc(s.winsums, KZ_MSM_MAX_WINDOWS));
+    s.cub_temp_bytes = msm_cub_temp_bytes(capZ) + 256;
+    CK(cudaMalloc(&s.cub_temp, s.cub_temp_bytes));
+    CK(dmalloc(s.sums, 5)); CK(dmalloc(s.partial_dev, KZGB_PARTIAL_BYTES)); CK(dmalloc(s.partials_in, KZGB_PARTIAL_BYTES * 64));
+    CK(dmalloc(s.scratch, 1 << 20));
+    CK(dmalloc(s.result_dev, 4)); CK(dmalloc(s.lines, 2)); CK(dmalloc(s.g1_pt, 2)); CK(dmalloc(s.setup_status, 4));
+    CK(cudaMallocHost((void**)&s.h_digests, 32 * nch)); CK(cudaMallocHost((void**)&s.h_small, 64 * sizeof(uint32_t)));
+    CK(cudaMallocHost((void**)&s.h_partial, KZGB_PARTIAL_BYTES * 64));
+    // trusted setup: decompress + check on the device, precompute the G2 lines
+    CK(cudaMemcpyAsync(s.scratch, g2m, 192, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.scratch + 256, g1m, 48, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemsetAsync(s.setup_status, 0, 4 * sizeof(int), s.stream));
+    launch_g2_setup(s.stream, s.scratch, s.lines, s.setup_status);
+    launch_g1_setup(s.stream, s.scratch + 256, s.g1_pt, s.setup_status);
+    int st[4];
+    CK(cudaMemcpyAsync(st, s.setup_status, sizeof st, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaGetLastError());
+    if (!(st[0] && st[1] && st[2])) return KZGB_BADARGS;
+    return KZGB_OK;
+}
+
+void slot_free(DeviceSlot& s) {
+    cudaSetDevice(s.device);
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    void* dev[] = {s.dC, s.dz, s.dy, s.dpi, s.pts, s.status, s.counters, s.leaves, s.digests, s.root_words, s.r, s.rz,
+                   s.partials, s.sum_ry, s.sortR.keys, s.sortR.vals, s.sortR.keys_alt, s.sortR.vals_alt, s.sortR.bucket_start,
+                   s.sortZ.keys, s.sortZ.vals, s.sortZ.keys_alt, s.sortZ.vals_alt, s.sortZ.bucket_start, s.bucketsA,
+                   s.bucketsB, s.bucketsC, s.segsums, s.winsums, s.cub_temp, s.sums, s.partial_dev, s.partials_in,
+                   s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb};
+    for (void* p : dev) if (p) cudaFree(p);
+    if (s.h_digests) cudaFreeHost(s.h_digests);
+    if (s.h_small) cudaFreeHost(s.h_small);
+    if (s.h_partial) cudaFreeHost(s.h_partial);
+    for (auto& e : s.ev) if (e) cudaEventDestroy(e);
+    if (s.stream) cudaStreamDestroy(s.stream);
+}
+
+MsmWorkspace make_ws(DeviceSlot& s, SortBuf& b, G1Xyzz* buckets) {
+    MsmWorkspace ws;
+    ws.keys = b.keys; ws.vals = b.vals; ws.keys_alt = b.keys_alt; ws.vals_alt = b.vals_alt;
+    ws.capacity = b.capacity; ws.bucket_start = b.bucket_start; ws.buckets = buckets; ws.segsums = s.segsums;
+    ws.winsums = s.winsums; ws.cub_temp = s.cub_temp; ws.cub_temp_bytes = s.cub_temp_bytes;
+    ws.max_buckets = 0; ws.max_segs = s.max_segs;
+    return ws;
+}
+void save_ws(SortBuf& b, const MsmWorkspace& ws) {
+    b.keys = ws.keys; b.vals = ws.vals; b.keys_alt = ws.keys_alt; b.vals_alt = ws.vals_alt;
+}
+
+// words (big-endian values) <-> bytes
+void words_to_be(uint8_t* out, const uint32_t* w, size_t nw) {
+    for (size_t i = 0; i < nw; ++i) { out[4 * i] = w[i] >> 24; out[4 * i + 1] = w[i] >> 16; out[4 * i + 2] = w[i] >> 8; out[4 * i + 3] = w[i]; }
+}
+void be_to_words(uint32_t* w, const uint8_t* in, size_t nw) {
+    for (size_t i = 0; i < nw; ++i) w[i] = (uint32_t)in[4 * i] << 24 | in[4 * i + 1] << 16 | in[4 * i + 2] << 8 | in[4 * i + 3];
+}
+
+// Phase 1: [H2D] -> leaf + chunk hashes -> digests D2H -> K1 decompress (left running).
+// Returns after the digests are on the host.  `stream_override`: caller's stream or null.
+kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
+                bool on_device, uint8_t* digests_out) {
+    if (n == 0 || n > s.n_max) return KZGB_BADARGS;
+    CK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
+    CK(cudaEventRecord(s.ev[0], st));
+    if (!on_device) {
+        CK(cudaMemcpyAsync(s.dC, C, 48 * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.dz, z, 32 * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.dy, y, 32 * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.dpi, pi, 48 * n, cudaMemcpyHostToDevice, st));
+        s.cur_C = s.dC; s.cur_z = s.dz; s.cur_y = s.dy; s.cur_pi = s.dpi;
+    } else {
+        s.cur_C = C; s.cur_z = z; s.cur_y = y; s.cur_pi = pi;
+    }
+    s.cur_n = n;
+    s.have_sums = false;
+    CK(cudaEventRecord(s.ev[1], st));
+    CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), st));
+    launch_leaf_hash(st, s.cur_C, s.cur_z, s.cur_y, s.cur_pi, n, s.leaves, s.counters);
+    launch_chunk_hash(st, s.leaves, n, s.digests);
+    size_t nch = (n + KZGB_CHUNK - 1) / KZGB_CHUNK;
+    CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(s.ev[2], st));
+    launch_decompress(st, s.cur_C, s.cur_pi, n, s.pts, s.status, s.counters);
+    CK(cudaEventRecord(s.ev[3], st));
+    CK(cudaEventSynchronize(s.ev[2]));
+    words_to_be(digests_out, (const uint32_t*)s.h_digests, 8 * nch);
+    return KZGB_OK;
+}
+
+// Phase 2: challenges, the three MSMs, partial.  Leaves the partial in s.h_partial[0..320) after sync.
+kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, bool single) {
+    size_t n = s.cur_n;
+    if (!n) return KZGB_BADARGS;
+    CK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
+    be_to_words(s.h_small + 8, root, 8);
+    CK(cudaMemcpyAsync(s.root_words, s.h_small + 8, 32, cudaMemcpyHostToDevice, st));
+    launch_challenges(st, s.root_words, global_offset, s.cur_z, s.cur_y, n, single ? 1 : 0, s.r, s.rz, s.partials, s.sum_ry);
+    // the setup point G joins the 255-bit sum with scalar -(sum r_i y_i): point slot 2n
+    CK(cudaMemcpyAsync(s.pts + 2 * (2 * n), s.g1_pt, 2 * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    CK(cudaEventRecord(s.ev[4], st));
+    s.planR = msm_make_plan(n, 128);
+    s.planZ = msm_make_plan(n + 1, 255);
+    if ((size_t)s.planR.W * n > s.sortR.capacity || (size_t)s.planZ.W * (n + 1) > s.sortZ.capacity ||
+        s.planR.total_buckets > s.max_bucketsR + 512 || s.planZ.total_buckets > s.max_bucketsZ + 512 ||
+        s.planZ.total_segs > s.max_segs + 512 || s.planR.total_segs > s.max_segs + 512)
+        return KZGB_BADARGS;
+    MsmWorkspace wr = make_ws(s, s.sortR, s.bucketsA), wz = make_ws(s, s.sortZ, s.bucketsC);
+    msm_sort_stage(st, s.planR, s.r, 4, n, wr);
+    msm_sort_stage(st, s.planZ, s.rz, 8, n + 1, wz);
+    save_ws(s.sortR, wr); save_ws(s.sortZ, wz);
+    CK(cudaEventRecord(s.ev[5], st));
+    MsmWorkspace wr2 = wr;
+    wr2.buckets = s.bucketsB;
+    msm_accumulate_stage(st, s.planR, s.pts, n, wr);                 // S1 over C_i
+    msm_accumulate_stage(st, s.planR, s.pts + 2 * n, n, wr2);        // S3 over pi_i
+    msm_accumulate_stage(st, s.planZ, s.pts + 2 * n, n + 1, wz);     // S2' over pi_i and G
+    CK(cudaEventRecord(s.ev[6], st));
+    msm_reduce_stage(st, s.planR, wr, s.sums + 0);
+    msm_reduce_stage(st, s.planR, wr2, s.sums + 2);
+    msm_reduce_stage(st, s.planZ, wz, s.sums + 1);
+    launch_make_partial(st, s.sums + 0, s.sums + 1, s.sums + 2, s.sum_ry, s.partial_dev);
+    CK(cudaMemcpyAsync(s.h_partial, s.partial_dev, KZGB_PARTIAL_BYTES, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_small, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(s.ev[7], st));
+    s.have_sums = true;
+    return KZGB_OK;
+}
+
+kzgb_ret combine(DeviceSlot& s, const uint8_t* partials, int np, bool* ok) {
+    if (np < 1 || np > 64) return KZGB_BADARGS;
+    CK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
+    memcpy(s.h_partial, partials, (size_t)KZGB_PARTIAL_BYTES * np);
+    CK(cudaMemcpyAsync(s.partials_in, s.h_partial, (size_t)KZGB_PARTIAL_BYTES * np, cudaMemcpyHostToDevice, st));
+    launch_combine(st, s.partials_in, np, s.sums + 3, s.sum_ry);
+    launch_pairing(st, s.lines, s.sums + 3, s.result_dev);
+    CK(cudaMemcpyAsync(s.h_small + 16, s.result_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(s.ev[8], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    *ok = s.h_small[16] == 1;
+    return KZGB_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ms;
+}
+
+kzgb_ret verify_common(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
+                       kzgb_ctx* ctx, bool on_device, bool single) {
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!ctx || !C || !z || !y || !pi || n == 0) return KZGB_BADARGS;
+    size_t G = on_device ? 1 : ctx->slots.size();
+    // contiguous shards, multiples of the 1024-proof hash chunk
+    size_t nch = (n + KZGB_CHUNK - 1) / KZGB_CHUNK;
+    if (G > nch) G = nch;
+    std::vector<size_t> lo(G + 1);
+    for (size_t g = 0; g <= G; ++g) { size_t c = nch * g / G * KZGB_CHUNK; lo[g] = c < n ? c : n; }
+    lo[G] = n;
+    std::vector<uint8_t> digests(32 * nch);
+    for (size_t g = 0; g < G; ++g) {
+        size_t a = lo[g], m = lo[g + 1] - a;
+        kzgb_ret rc = phase1(ctx->slots[g], C + 48 * a, z + 32 * a, y + 32 * a, pi + 48 * a, m, on_device,
+                             digests.data() + 32 * (a / KZGB_CHUNK));
+        if (rc) return rc;
+    }
+    uint8_t root[32] = {0};
+    auto t0 = std::chrono::steady_clock::now();
+    if (!single) host_sha256_root(root, digests.data(), nch, n);
+    float root_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (size_t g = 0; g < G; ++g) {
+        kzgb_ret rc = phase2(ctx->slots[g], root, lo[g], single);
+        if (rc) return rc;
+    }
+    std::vector<uint8_t> parts(KZGB_PARTIAL_BYTES * G);
+    uint32_t badp = 0, bads = 0;
+    for (size_t g = 0; g < G; ++g) {
+        DeviceSlot& s = ctx->slots[g];
+        CK(cudaSetDevice(s.device));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+        memcpy(parts.data() + KZGB_PARTIAL_BYTES * g, s.h_partial, KZGB_PARTIAL_BYTES);
+        badp += s.h_small[0];
+        bads += s.h_small[1];
+    }
+    kzgb_artifacts& art = ctx->art;
+    memset(&art, 0, sizeof art);
+    art.n = n;
+    art.n_bad_points = badp;
+    art.n_bad_scalars = bads;
+    memcpy(art.root, root, 32);
+    if (badp || bads) {
+        for (auto& s : ctx->slots) s.have_sums = false;
+        return KZGB_BADARGS;
+    }
+    DeviceSlot& s0 = ctx->slots[0];
+    kzgb_ret rc = combine(s0, parts.data(), (int)G, ok);
+    if (rc) return rc;
+    if (G > 1) s0.have_sums = false;
+    art.stage_ms[0] = ev_ms(s0.ev[0], s0.ev[1]);
+    art.stage_ms[2] = ev_ms(s0.ev[1], s0.ev[2]);
+    art.stage_ms[1] = ev_ms(s0.ev[2], s0.ev[3]);
+    art.stage_ms[3] = root_ms;
+    art.stage_ms[4] = ev_ms(s0.ev[3], s0.ev[4]);
+    art.stage_ms[5] = ev_ms(s0.ev[4], s0.ev[5]);
+    art.stage_ms[6] = ev_ms(s0.ev[5], s0.ev[6]);
+    art.stage_ms[7] = ev_ms(s0.ev[6], s0.ev[7]);
+    art.stage_ms[8] = ev_ms(s0.ev[7], s0.ev[8]);
+    art.stage_ms[9] = ev_ms(s0.ev[0], s0.ev[8]);
+    return KZGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* kzgb_version(void) { return "kzgb200-cuda-sm100a 0.1"; }
+
+kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const uint8_t* g2m, size_t n2, const int* devices,
+                         int n_devices, size_t n_max) {
+    if (!out || !g1m || !g2m || n1 < 1 || n2 < 2 || n_max < 1 || n_devices < 0 || n_devices > 64) return KZGB_BADARGS;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        fprintf(stderr, "[kzgb200] no CUDA device: this library has no CPU fallback\n");
+        return KZGB_ERROR;
+    }
+    kzgb_ctx* c = new (std::nothrow) kzgb_ctx();
+    if (!c) return KZGB_MALLOC;
+    int nd = n_devices > 0 && devices ? n_devices : 1;
+    c->slots.resize(nd);
+    for (int i = 0; i < nd; ++i) {
+        int dev = (n_devices > 0 && devices) ? devices[i] : 0;
+        if (dev < 0 || dev >= ndev) { kzgb_ctx_free(c); return KZGB_BADARGS; }
+        kzgb_ret rc = slot_init(c->slots[i], dev, n_max, g1m, g2m);
+        if (rc) { kzgb_ctx_free(c); return rc; }
+    }
+    memset(&c->art, 0, sizeof c->art);
+    c->launches_at_create = g_kzgb_launches.load();
+    *out = c;
+    return KZGB_OK;
+}
+void kzgb_ctx_free(kzgb_ctx* c) {
+    if (!c) return;
+    for (auto& s : c->slots) slot_free(s);
+    delete c;
+}
+
+kzgb_ret verify_kzg_proof(bool* ok, const uint8_t C[48], const uint8_t z[32], const uint8_t y[32], const uint8_t pi[48],
+                          kzgb_ctx* ctx) {
+    return verify_common(ok, C, z, y, pi, 1, ctx, false, true);
+}
+kzgb_ret verify_kzg_proof_batch(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
+                                kzgb_ctx* ctx) {
+    return verify_common(ok, C, z, y, pi, n, ctx, false, false);
+}
+kzgb_ret verify_kzg_proof_batch_device(bool* ok, const uint8_t* dC, const uint8_t* dz, const uint8_t* dy, const uint8_t* dpi,
+                                       size_t n, kzgb_ctx* ctx, void* stream) {
+    // inputs may have been produced on the caller's stream: order our stream after it
+    if (ctx && !ctx->slots.empty()) {
+        DeviceSlot& s = ctx->slots[0];
+        CK(cudaSetDevice(s.device));
+        CK(cudaEventRecord(s.ev[11], (cudaStream_t)stream));
+        CK(cudaStreamWaitEvent(s.stream, s.ev[11], 0));
+    }
+    return verify_common(ok, dC, dz, dy, dpi, n, ctx, true, false);
+}
+
+kzgb_ret kzgb_shard_phase1(kzgb_ctx* ctx, int slot, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi,
+                           size_t n_local, int on_device, void* stream, uint8_t* digests_out, uint32_t* n_bad_out) {
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size() || !C || !z || !y || !pi || !digests_out) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[slot];
+    if (on_device) {
+        CK(cudaSetDevice(s.device));
+        CK(cudaEventRecord(s.ev[11], (cudaStream_t)stream));
+        CK(cudaStreamWaitEvent(s.stream, s.ev[11], 0));
+    }
+    kzgb_ret rc = phase1(s, C, z, y, pi, n_local, on_device != 0, digests_out);
+    if (n_bad_out) *n_bad_out = 0;      // malformed elements are reported by phase 2 (K1 is still running)
+    return rc;
+}
+kzgb_ret kzgb_fs_root(uint8_t root_out[32], const uint8_t* chunk_digests, size_t n_chunks, uint64_t n_total) {
+    if (!root_out || !chunk_digests) return KZGB_BADARGS;
+    host_sha256_root(root_out, chunk_digests, n_chunks, n_total);
+    return KZGB_OK;
+}
+kzgb_ret kzgb_shard_phase2(kzgb_ctx* ctx, int slot, const uint8_t root[32], uint64_t global_offset, void*,
+                           uint8_t partial_out[KZGB_PARTIAL_BYTES]) {
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size() || !root || !partial_out) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[slot];
+    kzgb_ret rc = phase2(s, root, global_offset, false);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaGetLastError());
+    memcpy(partial_out, s.h_partial, KZGB_PARTIAL_BYTES);
+    ctx->art.n_bad_points = s.h_small[0];
+    ctx->art.n_bad_scalars = s.h_small[1];
+    return (s.h_small[0] || s.h_small[1]) ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret kzgb_combine_verify(kzgb_ctx* ctx, const uint8_t* partials, int n_partials, bool* ok) {
+    if (!ctx || !partials || !ok) return KZGB_BADARGS;
+    *ok = false;
+    DeviceSlot& s = ctx->slots[0];
+    if (n_partials != 1) s.have_sums = false;
+    return combine(s, partials, n_partials, ok);
+}
+
+kzgb_ret kzgb_g1_decompress_batch(uint8_t* affine_out, uint8_t* status_out, const uint8_t* in, size_t m, kzgb_ctx* ctx) {
+    if (!affine_out || !status_out || !in || !ctx) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    CK(cudaSetDevice(s.device));
+    uint8_t* d_be = nullptr;
+    size_t slice = s.n_max;
+    CK(cudaMalloc((void**)&d_be, 96 * (slice + 1)));
+    for (size_t done = 0; done < m; done += slice) {
+        // K1 takes two input arrays of h points each: split the slice in two halves of one buffer
+        size_t k = m - done < slice ? m - done : slice;
+        size_t h = (k + 1) / 2;
+        CK(cudaMemsetAsync(s.dC + 48 * k, 0, 48, s.stream));             // pad slot when k is odd
+        CK(cudaMemcpyAsync(s.dC, in + 48 * done, 48 * k, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), s.stream));
+        launch_decompress(s.stream, s.dC, s.dC + 48 * h, h, s.pts, s.status, s.counters);
+        launch_points_to_be(s.stream, s.pts, k, d_be);
+        CK(cudaMemcpyAsync(affine_out + 96 * done, d_be, 96 * k, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(status_out + done, s.status, k, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    CK(cudaFree(d_be));
+    CK(cudaGetLastError());
+    s.have_sums = false;
+    return KZGB_OK;
+}
+
+kzgb_ret kzgb_fs_challenges(uint8_t root_out[32], uint8_t* r_out, const uint8_t* C, const uint8_t* z, const uint8_t* y,
+                            const uint8_t* pi, size_t n, kzgb_ctx* ctx) {
+    if (!root_out || !r_out || !C || !z || !y || !pi || !ctx || n == 0) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    if (n > s.n_max) return KZGB_BADARGS;
+    size_t nch = (n + KZGB_CHUNK - 1) / KZGB_CHUNK;
+    std::vector<uint8_t> dig(32 * nch);
+    kzgb_ret rc = phase1(s, C, z, y, pi, n, false, dig.data());
+    if (rc) return rc;
+    host_sha256_root(root_out, dig.data(), nch, n);
+    be_to_words(s.h_small + 8, root_out, 8);
+    CK(cudaMemcpyAsync(s.root_words, s.h_small + 8, 32, cudaMemcpyHostToDevice, s.stream));
+    uint8_t* d_r = nullptr;
+    CK(cudaMalloc((void**)&d_r, 16 * n));
+    launch_r_only(s.stream, s.root_words, n, d_r);
+    CK(cudaMemcpyAsync(r_out, d_r, 16 * n, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaFree(d_r));
+    CK(cudaGetLastError());
+    return KZGB_OK;
+}
+
+kzgb_ret kzgb_g1_msm(uint8_t affine_out[96], const uint8_t* points_affine, const uint8_t* scalars, size_t m, int nbits,
+                     kzgb_ctx* ctx) {
+    if (!affine_out || !points_affine || !scalars || !ctx || (nbits != 255 && nbits != 128)) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    if (m > s.n_max) return KZGB_BADARGS;
+    if (m == 0) { memset(affine_out, 0, 96); return KZGB_OK; }
+    CK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
+    uint8_t *d_pts = nullptr, *d_sc = nullptr;
+    CK(cudaMalloc((void**)&d_pts, 96 * m)); CK(cudaMalloc((void**)&d_sc, 32 * m));
+    CK(cudaMemcpyAsync(d_pts, points_affine, 96 * m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_sc, scalars, 32 * m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), st));
+    launch_points_from_be(st, d_pts, m, s.pts, s.counters);
+    launch_scalars_from_be(st, d_sc, m, s.rz, s.counters);
+    MsmPlan plan = msm_make_plan(m, nbits);
+    if ((size_t)plan.W * m > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || plan.total_segs > s.max_segs + 512) {
+        cudaFree(d_pts); cudaFree(d_sc);
+        return KZGB_BADARGS;
+    }
+    MsmWorkspace ws = make_ws(s, s.sortZ, s.bucketsC);
+    CK(cudaEventRecord(s.ev[0], st));
+    msm_sort_stage(st, plan, s.rz, 8, m, ws);
+    save_ws(s.sortZ, ws);
+    CK(cudaEventRecord(s.ev[1], st));
+    msm_accumulate_stage(st, plan, s.pts, m, ws);
+    CK(cudaEventRecord(s.ev[2], st));
+    msm_reduce_stage(st, plan, ws, s.sums + 0);
+    CK(cudaEventRecord(s.ev[3], st));
+    // affine conversion through the artefact kernel's path: reuse k_artifacts slot 0 (S1)
+    CK(cudaMemsetAsync(s.sums + 1, 0, 2 * sizeof(G1Jac), st));
+    CK(cudaMemsetAsync(s.sum_ry, 0, 8 * sizeof(uint32_t), st));
+    launch_artifacts(st, s.sums + 0, s.sums + 1, s.sums + 2, s.sum_ry, s.g1_pt, s.scratch);
+    CK(cudaMemcpyAsync(s.h_partial, s.scratch, 96, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_small, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(d_pts)); CK(cudaFree(d_sc));
+    CK(cudaGetLastError());
+    s.have_sums = false;
+    ctx->msm_ms[0] = ev_ms(s.ev[0], s.ev[1]);
+    ctx->msm_ms[1] = ev_ms(s.ev[1], s.ev[2]);
+    ctx->msm_ms[2] = ev_ms(s.ev[2], s.ev[3]);
+    ctx->msm_ms[3] = ev_ms(s.ev[0], s.ev[3]);
+    if (s.h_small[0] || s.h_small[1]) return KZGB_BADARGS;
+    if (nbits == 128) {
+        for (size_t i = 0; i < m; ++i)
+            for (int k = 0; k < 16; ++k)
+                if (scalars[32 * i + k]) return KZGB_BADARGS;
+    }
+    memcpy(affine_out, s.h_partial, 96);
+    return KZGB_OK;
+}
+kzgb_ret kzgb_g1_msm_times(float ms_out[4], kzgb_ctx* ctx) {
+    if (!ms_out || !ctx) return KZGB_BADARGS;
+    memcpy(ms_out, ctx->msm_ms, sizeof ctx->msm_ms);
+    return KZGB_OK;
+}
+
+kzgb_ret kzgb_pairing_check(bool* ok, const uint8_t A_affine[96], const uint8_t B_affine[96], kzgb_ctx* ctx) {
+    if (!ok || !A_affine || !B_affine || !ctx) return KZGB_BADARGS;
+    *ok = false;
+    DeviceSlot& s = ctx->slots[0];
+    CK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
+    memcpy(s.h_partial, A_affine, 96);
+    memcpy(s.h_partial + 96, B_affine, 96);
+    CK(cudaMemcpyAsync(s.scratch, s.h_partial, 192, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), st));
+    launch_points_from_be(st, s.scratch, 2, s.pts, s.counters);       // validates range + curve equation
+    CK(cudaMemcpyAsync(s.h_small, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    launch_points_jac_from_be(st, s.scratch, 2, s.sums + 3);
+    launch_pairing(st, s.lines, s.sums + 3, s.result_dev);
+    CK(cudaMemcpyAsync(s.h_small + 16, s.result_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    s.have_sums = false;
+    if (s.h_small[0]) return KZGB_BADARGS;
+    *ok = s.h_small[16] == 1;
+    return KZGB_OK;
+}
+
+kzgb_ret kzgb_last_artifacts(kzgb_ctx* ctx, kzgb_artifacts* out) {
+    if (!ctx || !out) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    if (s.have_sums) {
+        CK(cudaSetDevice(s.device));
+        launch_artifacts(s.stream, s.sums + 0, s.sums + 1, s.sums + 2, s.sum_ry, s.g1_pt, s.scratch);
+        CK(cudaMemcpyAsync(s.h_partial, s.scratch, 512, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+        memcpy(ctx->art.S1, s.h_partial, 96); memcpy(ctx->art.S2, s.h_partial + 96, 96);
+        memcpy(ctx->art.S3, s.h_partial + 192, 96); memcpy(ctx->art.A, s.h_partial + 288, 96);
+        memcpy(ctx->art.B, s.h_partial + 384, 96); memcpy(ctx->art.sum_ry, s.h_partial + 480, 32);
+    }
+    *out = ctx->art;
+    return KZGB_OK;
+}
+
+kzgb_ret kzgb_synth_instance(kzgb_ctx* ctx, uint64_t seed, uint64_t offset, size_t n, uint8_t* C, uint8_t* z, uint8_t* y,
+                             uint8_t* pi, int out_on_device) {
+    if (!ctx || !C || !z || !y || !pi) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    CK(cudaSetDevice(s.device));
+    if (!s.comb_built) {
+        CK(dmalloc(s.comb, 2 * 32 * 255));
+        launch_build_comb(s.stream, s.comb);
+        s.comb_built = true;
+    }
+    if (out_on_device) {
+        launch_synth(s.stream, seed, offset, n, s.comb, C, z, y, pi);
+        CK(cudaStreamSynchronize(s.stream));
+    } else {
+        size_t done = 0;
+        while (done < n) {
+            size_t k = n - done < s.n_max ? n - done : s.n_max;
+            launch_synth(s.stream, seed, offset + done, k, s.comb, s.dC, s.dz, s.dy, s.dpi);
+            CK(cudaMemcpyAsync(C + 48 * done, s.dC, 48 * k, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(z + 32 * done, s.dz, 32 * k, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(y + 32 * done, s.dy, 32 * k, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(pi + 48 * done, s.dpi, 48 * k, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaStreamSynchronize(s.stream));
+            done += k;
+        }
+    }
+    CK(cudaGetLastError());
+    return KZGB_OK;
+}
+// The insecure test setup needs [tau]G2, i.e. G2 arithmetic that the verification path never uses; the
+// product library therefore does not carry it.  Tests and bench take the setup bytes from
+// tests/golden/test_setup.bin (generated by the oracle) or from the oracle library.
+kzgb_ret kzgb_synth_setup(uint8_t*, size_t, uint8_t*, size_t) { return KZGB_ERROR; }
+
+kzgb_ret kzgb_debug_op(kzgb_ctx* ctx, int op, const uint8_t* in, uint8_t* out, size_t count) {
+    if (!ctx || !in || !out) return KZGB_BADARGS;
+    static const int isz[] = {0, 96, 48, 96, 96, 48, 48, 64, 64, 192, 96, 128, 96, 1152, 576, 576, 576, 576, 192, 64};
+    static const int osz[] = {0, 48, 48, 48, 48, 48, 48, 32, 32, 96, 96, 96, 96, 576, 576, 576, 576, 576, 576, 32};
+    if (op < 1 || op > 18) return KZGB_BADARGS;      // SHA256_64 is exercised through the FS stage exports
+    DeviceSlot& s = ctx->slots[0];
+    CK(cudaSetDevice(s.device));
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    CK(cudaMalloc((void**)&d_in, (size_t)isz[op] * count + 16)); CK(cudaMalloc((void**)&d_out, (size_t)osz[op] * count + 16));
+    CK(cudaMemcpyAsync(d_in, in, (size_t)isz[op] * count, cudaMemcpyHostToDevice, s.stream));
+    if (op <= 12) launch_debug_op(s.stream, op, d_in, d_out, count);
+    else for (size_t i = 0; i < count; ++i) launch_pairing_debug(s.stream, op, s.lines, d_in + (size_t)isz[op] * i, d_out + (size_t)osz[op] * i);
+    CK(cudaMemcpyAsync(out, d_out, (size_t)osz[op] * count, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaFree(d_in)); CK(cudaFree(d_out));
+    CK(cudaGetLastError());
+    return KZGB_OK;
+}
+
+kzgb_ret kzgb_imad_peak(kzgb_ctx* ctx, double* imad_per_sec_out, double* ms_out) {
+    if (!ctx || !imad_per_sec_out) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    CK(cudaSetDevice(s.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, s.device));
+    int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4000;
+    launch_imad_bench(s.stream, (uint32_t*)s.scratch, blocks, threads, 200);      // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(s.ev[9], s.stream));
+        launch_imad_bench(s.stream, (uint32_t*)s.scratch, blocks, threads, iters);
+        CK(cudaEventRecord(s.ev[10], s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        float ms = ev_ms(s.ev[9], s.ev[10]);
+        if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    double total = (double)blocks * threads * (double)iters * 128.0;
+    *imad_per_sec_out = total / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return KZGB_OK;
+}
+uint64_t kzgb_launch_count(const kzgb_ctx*) { return g_kzgb_launches.load(); }
+int kzgb_set_threads(kzgb_ctx*, int) { return 0; }
+
+}  // extern "C"

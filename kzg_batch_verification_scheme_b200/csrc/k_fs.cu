@@ -1,0 +1,305 @@
+// K2/K3: batched Fiat-Shamir (BASELINE.json:5 item (c)) -- SHA-256 leaf and chunk hashes, challenge
+// derivation r_i, the scalar products r_i z_i and sum r_i y_i -- plus the device-side synthetic instance
+// generator and the host root hash.
+#include "kernels.h"
+#include "sha256.cuh"
+
+__device__ __forceinline__ u32 ld_be32(u32 x) { return __byte_perm(x, 0, 0x0123); }
+
+// ---- leaf hashes: one thread per proof; also counts z_i, y_i >= r
+__global__ void __launch_bounds__(128) k_leaf_hash(const u8* __restrict__ C, const u8* __restrict__ z,
+                                                   const u8* __restrict__ y, const u8* __restrict__ pi, size_t n,
+                                                   u32* __restrict__ leaves, u32* __restrict__ counters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 cw[12], pw[12], zw[8], yw[8];
+    const uint4* c4 = reinterpret_cast<const uint4*>(C + 48 * i);
+    const uint4* p4 = reinterpret_cast<const uint4*>(pi + 48 * i);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        uint4 a = __ldg(c4 + k), b = __ldg(p4 + k);
+        cw[4 * k] = ld_be32(a.x); cw[4 * k + 1] = ld_be32(a.y); cw[4 * k + 2] = ld_be32(a.z); cw[4 * k + 3] = ld_be32(a.w);
+        pw[4 * k] = ld_be32(b.x); pw[4 * k + 1] = ld_be32(b.y); pw[4 * k + 2] = ld_be32(b.z); pw[4 * k + 3] = ld_be32(b.w);
+    }
+    const uint4* z4 = reinterpret_cast<const uint4*>(z + 32 * i);
+    const uint4* y4 = reinterpret_cast<const uint4*>(y + 32 * i);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        uint4 a = __ldg(z4 + k), b = __ldg(y4 + k);
+        zw[4 * k] = ld_be32(a.x); zw[4 * k + 1] = ld_be32(a.y); zw[4 * k + 2] = ld_be32(a.z); zw[4 * k + 3] = ld_be32(a.w);
+        yw[4 * k] = ld_be32(b.x); yw[4 * k + 1] = ld_be32(b.y); yw[4 * k + 2] = ld_be32(b.z); yw[4 * k + 3] = ld_be32(b.w);
+    }
+    Fr zr, yr;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { zr.v[k] = zw[7 - k]; yr.v[k] = yw[7 - k]; }
+    u32 bad = (fr_raw_is_canonical(zr) ? 0u : 1u) + (fr_raw_is_canonical(yr) ? 0u : 1u);
+    if (bad) atomicAdd(counters + 1, bad);
+    u32 h[8];
+    fs_leaf_words(h, cw, zw, yw, pw);
+    uint4* o4 = reinterpret_cast<uint4*>(leaves + 8 * i);
+    o4[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    o4[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+void launch_leaf_hash(cudaStream_t s, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
+                      uint32_t* leaves, uint32_t* counters) {
+    if (!n) return;
+    k_leaf_hash<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(C, z, y, pi, n, leaves, counters);
+    KZ_COUNT_LAUNCH();
+}
+
+// ---- chunk digests: one thread per chunk of 1024 leaves (serial SHA-256 over <= 32 KiB)
+__global__ void k_chunk_hash(const u32* __restrict__ leaves, size_t n, u32* __restrict__ digests) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t nch = (n + 1023) / 1024;
+    if (j >= nch) return;
+    size_t lo = j * 1024;
+    u32 cnt = (u32)((n - lo) < 1024 ? (n - lo) : 1024);
+    u32 h[8];
+    fs_chunk_words(h, leaves + 8 * lo, cnt);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) digests[8 * j + k] = h[k];
+}
+void launch_chunk_hash(cudaStream_t s, const uint32_t* leaves, size_t n, uint32_t* digests_words) {
+    if (!n) return;
+    size_t nch = (n + 1023) / 1024;
+    k_chunk_hash<<<(unsigned)((nch + 31) / 32), 32, 0, s>>>(leaves, n, digests_words);
+    KZ_COUNT_LAUNCH();
+}
+
+// ---- challenges and scalar products
+#define KZ_CH_THREADS 128
+__global__ void __launch_bounds__(KZ_CH_THREADS) k_challenges(const u32* __restrict__ root_words, u64 global_offset,
+                                                              const u8* __restrict__ z, const u8* __restrict__ y, size_t n,
+                                                              int single, u32* __restrict__ r_out, u32* __restrict__ rz_out,
+                                                              u32* __restrict__ partials) {
+    __shared__ Fr red[KZ_CH_THREADS];
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Fr ry = fr_zero();
+    if (i < n) {
+        u32 root[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) root[k] = root_words[k];
+        Fr r = fr_zero();
+        if (single) r.v[0] = 1; else fs_r_limbs(r.v, root, global_offset + i);
+        Fr zr, yr;
+        const uint4* z4 = reinterpret_cast<const uint4*>(z + 32 * i);
+        const uint4* y4 = reinterpret_cast<const uint4*>(y + 32 * i);
+        uint4 a0 = __ldg(z4), a1 = __ldg(z4 + 1), b0 = __ldg(y4), b1 = __ldg(y4 + 1);
+        u32 zw[8] = {ld_be32(a0.x), ld_be32(a0.y), ld_be32(a0.z), ld_be32(a0.w), ld_be32(a1.x), ld_be32(a1.y), ld_be32(a1.z), ld_be32(a1.w)};
+        u32 yw[8] = {ld_be32(b0.x), ld_be32(b0.y), ld_be32(b0.z), ld_be32(b0.w), ld_be32(b1.x), ld_be32(b1.y), ld_be32(b1.z), ld_be32(b1.w)};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { zr.v[k] = zw[7 - k]; yr.v[k] = yw[7 - k]; }
+        // raw * Montgomery -> canonical product
+        Fr rz = fr_mul(r, fr_to_mont(zr));
+        ry = fr_mul(r, fr_to_mont(yr));
+        uint4* ro = reinterpret_cast<uint4*>(r_out + 4 * i);
+        ro[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+        uint4* zo = reinterpret_cast<uint4*>(rz_out + 8 * i);
+        zo[0] = make_uint4(rz.v[0], rz.v[1], rz.v[2], rz.v[3]);
+        zo[1] = make_uint4(rz.v[4], rz.v[5], rz.v[6], rz.v[7]);
+    }
+    red[threadIdx.x] = ry;
+    __syncthreads();
+    for (int s = KZ_CH_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] = fr_add(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) partials[8 * blockIdx.x + k] = red[0].v[k];
+    }
+}
+// single block: sum the per-block partials; write sum (canonical) and -sum into scalar slot n of rz
+__global__ void __launch_bounds__(KZ_CH_THREADS) k_sum_ry(const u32* __restrict__ partials, size_t nparts, size_t n,
+                                                          u32* __restrict__ rz_out, u32* __restrict__ sum_out) {
+    __shared__ Fr red[KZ_CH_THREADS];
+    Fr acc = fr_zero();
+    for (size_t j = threadIdx.x; j < nparts; j += KZ_CH_THREADS) {
+        Fr v;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v.v[k] = partials[8 * j + k];
+        acc = fr_add(acc, v);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = KZ_CH_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] = fr_add(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        Fr neg = fr_neg(red[0]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sum_out[k] = red[0].v[k]; rz_out[8 * n + k] = neg.v[k]; }
+    }
+}
+void launch_challenges(cudaStream_t s, const uint32_t* root_words, uint64_t global_offset, const uint8_t* z,
+                       const uint8_t* y, size_t n, int single, uint32_t* r_out, uint32_t* rz_out, uint32_t* partials,
+                       uint32_t* sum_ry_out) {
+    if (!n) return;
+    size_t nb = (n + KZ_CH_THREADS - 1) / KZ_CH_THREADS;
+    k_challenges<<<(unsigned)nb, KZ_CH_THREADS, 0, s>>>(root_words, global_offset, z, y, n, single, r_out, rz_out, partials);
+    KZ_COUNT_LAUNCH();
+    k_sum_ry<<<1, KZ_CH_THREADS, 0, s>>>(partials, nb, n, rz_out, sum_ry_out);
+    KZ_COUNT_LAUNCH();
+}
+// r_i only, as 16 big-endian bytes (stage export kzgb_fs_challenges)
+__global__ void k_r_only(const u32* __restrict__ root_words, size_t n, u8* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 root[8], r[4];
+    for (int k = 0; k < 8; ++k) root[k] = root_words[k];
+    fs_r_limbs(r, root, i);
+    for (int k = 0; k < 4; ++k) {
+        u32 v = r[3 - k];
+        out[16 * i + 4 * k] = v >> 24; out[16 * i + 4 * k + 1] = v >> 16; out[16 * i + 4 * k + 2] = v >> 8; out[16 * i + 4 * k + 3] = v;
+    }
+}
+void launch_r_only(cudaStream_t s, const uint32_t* root_words, size_t n, uint8_t* r_be16) {
+    if (!n) return;
+    k_r_only<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(root_words, n, r_be16);
+    KZ_COUNT_LAUNCH();
+}
+// 32-byte big-endian scalars -> 8 little-endian limbs (kzgb_g1_msm); counts values >= r
+__global__ void k_scalars_from_be(const u8* __restrict__ in, size_t m, u32* __restrict__ out, u32* counters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    Fr v;
+    fr_raw_from_be(v, in + 32 * i);
+    if (!fr_raw_is_canonical(v)) atomicAdd(counters + 1, 1u);
+    for (int k = 0; k < 8; ++k) out[8 * i + k] = v.v[k];
+}
+void launch_scalars_from_be(cudaStream_t s, const uint8_t* be32, size_t m, uint32_t* limbs8, uint32_t* counters) {
+    if (!m) return;
+    k_scalars_from_be<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(be32, m, limbs8, counters);
+    KZ_COUNT_LAUNCH();
+}
+
+// ---- synthetic instances on the device (scalar shortcut); not part of the timed path.
+// comb table: tab[w*255 + j-1] = j * 2^(8w) * G1 (affine, Montgomery), w < 32, j = 1..255.
+__global__ void k_build_comb(Fp* tab) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= 32) return;
+    G1Aff g = {fp_const(G1_GEN_X), fp_const(G1_GEN_Y)};
+    G1Jac base = jac_from_aff(g);
+    for (int k = 0; k < 8 * w; ++k) base = jac_dbl(base);
+    G1Jac acc = base;
+    for (int j = 0; j < 255; ++j) {
+        G1Aff a = jac_to_aff(acc);
+        tab[2 * (w * 255 + j)] = a.x;
+        tab[2 * (w * 255 + j) + 1] = a.y;
+        acc = jac_add(acc, base);
+    }
+}
+void launch_build_comb(cudaStream_t s, Fp* comb_table) {
+    k_build_comb<<<1, 32, 0, s>>>(comb_table);
+    KZ_COUNT_LAUNCH();
+}
+__device__ __noinline__ G1Aff comb_mul(const Fp* tab, const Fr& k_mont) {
+    Fr k = fr_from_mont(k_mont);
+    G1Jac acc = jac_inf();
+    for (int w = 0; w < 32; ++w) {
+        u32 d = (k.v[w >> 2] >> (8 * (w & 3))) & 0xFF;
+        if (d) {
+            G1Aff t = {tab[2 * (w * 255 + d - 1)], tab[2 * (w * 255 + d - 1) + 1]};
+            acc = jac_madd(acc, t);
+        }
+    }
+    return jac_to_aff(acc);
+}
+__device__ __forceinline__ void store_be_words(u8* dst, const u32* w, int nw) {
+    u32* d = reinterpret_cast<u32*>(dst);
+    for (int k = 0; k < nw; ++k) d[k] = __byte_perm(w[k], 0, 0x0123);
+}
+__global__ void __launch_bounds__(64) k_synth(u64 seed, u64 offset, size_t n, const Fp* __restrict__ tab, u8* C, u8* z,
+                                              u8* y, u8* pi) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 idx = offset + i;
+    Fr a = prng_fr(seed, 1, idx), zz = prng_fr(seed, 2, idx), yy = prng_fr(seed, 3, idx);
+    Fr den = fr_sub(fr_const(FR_TEST_TAU), zz);
+    Fr q = fr_mul(fr_sub(a, yy), fr_inv(den));
+    G1Aff cp = comb_mul(tab, a), pp = comb_mul(tab, q);
+    u32 w[12];
+    g1_compress_words(w, cp);
+    store_be_words(C + 48 * i, w, 12);
+    g1_compress_words(w, pp);
+    store_be_words(pi + 48 * i, w, 12);
+    Fr zc = fr_from_mont(zz), yc = fr_from_mont(yy);
+    u32 t[8];
+    for (int k = 0; k < 8; ++k) t[k] = zc.v[7 - k];
+    store_be_words(z + 32 * i, t, 8);
+    for (int k = 0; k < 8; ++k) t[k] = yc.v[7 - k];
+    store_be_words(y + 32 * i, t, 8);
+}
+void launch_synth(cudaStream_t s, uint64_t seed, uint64_t offset, size_t n, const Fp* comb_table, uint8_t* C, uint8_t* z,
+                  uint8_t* y, uint8_t* pi) {
+    if (!n) return;
+    k_synth<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(seed, offset, n, comb_table, C, z, y, pi);
+    KZ_COUNT_LAUNCH();
+}
+
+// ---- host SHA-256 for the root (<= 32 KiB at n = 2^20; the one cross-shard step)
+namespace {
+struct HostSha {
+    uint32_t h[8];
+    uint8_t buf[64];
+    uint64_t len = 0;
+    HostSha() {
+        static const uint32_t iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+        memcpy(h, iv, sizeof h);
+    }
+    static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+    void block(const uint8_t* p) {
+        static const uint32_t K[64] = {
+            0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+            0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+            0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+            0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+            0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+            0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+            0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+            0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+        uint32_t w[64];
+        for (int i = 0; i < 16; ++i) w[i] = (uint32_t)p[4 * i] << 24 | p[4 * i + 1] << 16 | p[4 * i + 2] << 8 | p[4 * i + 3];
+        for (int i = 16; i < 64; ++i) {
+            uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+            uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+        for (int i = 0; i < 64; ++i) {
+            uint32_t t1 = hh + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+            uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+    void update(const uint8_t* p, size_t n) {
+        for (size_t i = 0; i < n; ++i) {
+            buf[len++ % 64] = p[i];
+            if (len % 64 == 0) block(buf);
+        }
+    }
+    void final(uint8_t out[32]) {
+        uint64_t bits = len * 8;
+        uint8_t pad = 0x80;
+        update(&pad, 1);
+        pad = 0;
+        while (len % 64 != 56) update(&pad, 1);
+        uint8_t lb[8];
+        for (int i = 0; i < 8; ++i) lb[i] = (uint8_t)(bits >> (56 - 8 * i));
+        update(lb, 8);
+        for (int i = 0; i < 8; ++i) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }
+    }
+};
+}  // namespace
+void host_sha256_root(uint8_t out[32], const uint8_t* digests, size_t n_chunks, uint64_t n_total) {
+    HostSha s;
+    s.update((const uint8_t*)"KZGB200/root_v1_", 16);
+    uint8_t be[16];
+    uint64_t deg = 4096;
+    for (int i = 0; i < 8; ++i) { be[i] = (uint8_t)(deg >> (56 - 8 * i)); be[8 + i] = (uint8_t)(n_total >> (56 - 8 * i)); }
+    s.update(be, 16);
+    s.update(digests, 32 * n_chunks);
+    s.final(out);
+}

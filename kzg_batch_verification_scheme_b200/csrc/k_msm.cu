@@ -1,0 +1,107 @@
+// K4-K7: Pippenger MSM kernels (BASELINE.json:5 item (d)).
+//   K4 digits     one thread per scalar: signed-window recoding -> (bucket key, point|sign) pairs
+//   K5 sort       radix sort of the pairs by bucket key (CUB DeviceRadixSort, first cut -- SURVEY 2.2 S5)
+//                 + bucket boundary detection
+//   K6 accumulate bucket sums in XYZZ (mixed additions with the affine points)
+//   K7 reduce     per-segment running sums, per-window block reduction, Horner combine over windows
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.h"
+
+__global__ void __launch_bounds__(128) k_msm_digits(const u32* __restrict__ scalars, int nl, size_t m,
+                                                    u32* __restrict__ keys, u32* __restrict__ vals,
+                                                    const __grid_constant__ MsmPlan plan) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    u32 sc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sc[k] = k < nl ? scalars[(size_t)nl * i + k] : 0u;
+    msm_digits_body(keys, vals, sc, i, m, plan);
+}
+
+// start[b] = first sorted position with key >= b, for b in [0, total_buckets+1]
+__global__ void k_bucket_bounds(const u32* __restrict__ keys, size_t N, u32 total_buckets, u32* __restrict__ start) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    u32 k = keys[i];
+    u32 kp = i ? keys[i - 1] : 0xFFFFFFFFu;      // treat "before the first" as key -1
+    if (i == 0) { for (u32 b = 0; b <= k; ++b) start[b] = 0; }
+    else if (k != kp) { for (u32 b = kp + 1; b <= k; ++b) start[b] = (u32)i; }
+    if (i == N - 1) { for (u32 b = k + 1; b <= total_buckets + 1; ++b) start[b] = (u32)N; }
+}
+
+__global__ void __launch_bounds__(128) k_msm_accumulate(const Fp* __restrict__ pts, const u32* __restrict__ vals,
+                                                        const u32* __restrict__ start, u32 total_buckets,
+                                                        G1Xyzz* __restrict__ buckets) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total_buckets) return;
+    buckets[b] = msm_bucket_body(pts, vals, start[b], start[b + 1]);
+}
+
+__global__ void __launch_bounds__(128) k_msm_segments(const G1Xyzz* __restrict__ buckets, G1Xyzz* __restrict__ segsums,
+                                                      const __grid_constant__ MsmPlan plan) {
+    u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= plan.total_segs) return;
+    int w = 0;
+    while (s >= plan.seg_off[w + 1]) ++w;
+    segsums[s] = msm_segment_body(buckets + plan.bucket_off[w], plan.nb[w], s - plan.seg_off[w]);
+}
+
+// one block per window: sum of its segment sums
+#define KZ_WIN_THREADS 128
+__global__ void __launch_bounds__(KZ_WIN_THREADS) k_msm_window_sum(const G1Xyzz* __restrict__ segsums,
+                                                                   G1Xyzz* __restrict__ winsums,
+                                                                   const __grid_constant__ MsmPlan plan) {
+    __shared__ G1Xyzz red[KZ_WIN_THREADS];
+    int w = blockIdx.x;
+    u32 lo = plan.seg_off[w], hi = plan.seg_off[w + 1];
+    G1Xyzz acc = xyzz_inf();
+    for (u32 s = lo + threadIdx.x; s < hi; s += KZ_WIN_THREADS) acc = xyzz_add(acc, segsums[s]);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = KZ_WIN_THREADS / 2; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) red[threadIdx.x] = xyzz_add(red[threadIdx.x], red[threadIdx.x + st]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) winsums[w] = red[0];
+}
+__global__ void k_msm_combine(const G1Xyzz* __restrict__ winsums, int W, int c, G1Jac* out) {
+    if (threadIdx.x || blockIdx.x) return;
+    *out = xyzz_to_jac(msm_combine_body(winsums, W, c));
+}
+
+size_t msm_cub_temp_bytes(size_t entries) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<u32> k(nullptr, nullptr), v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int)entries, 0, 32, (cudaStream_t)0);
+    return bytes;
+}
+
+void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars, int nl, size_t m, MsmWorkspace& ws) {
+    size_t N = m * (size_t)plan.W;
+    k_msm_digits<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(scalars, nl, m, ws.keys, ws.vals, plan);
+    KZ_COUNT_LAUNCH();
+    int end_bit = 1;
+    while ((1u << end_bit) <= plan.total_buckets) ++end_bit;
+    cub::DoubleBuffer<u32> k(ws.keys, ws.keys_alt), v(ws.vals, ws.vals_alt);
+    size_t bytes = ws.cub_temp_bytes;
+    cub::DeviceRadixSort::SortPairs(ws.cub_temp, bytes, k, v, (int)N, 0, end_bit, s);
+    KZ_COUNT_LAUNCH();
+    if (k.Current() != ws.keys) { std::swap(ws.keys, ws.keys_alt); std::swap(ws.vals, ws.vals_alt); }
+    k_bucket_bounds<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(ws.keys, N, plan.total_buckets, ws.bucket_start);
+    KZ_COUNT_LAUNCH();
+}
+void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, size_t m, MsmWorkspace& ws) {
+    (void)m;
+    k_msm_accumulate<<<(plan.total_buckets + 127) / 128, 128, 0, s>>>(pts, ws.vals, ws.bucket_start, plan.total_buckets,
+                                                                      ws.buckets);
+    KZ_COUNT_LAUNCH();
+}
+void msm_reduce_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, G1Jac* out) {
+    k_msm_segments<<<(plan.total_segs + 127) / 128, 128, 0, s>>>(ws.buckets, ws.segsums, plan);
+    KZ_COUNT_LAUNCH();
+    k_msm_window_sum<<<plan.W, KZ_WIN_THREADS, 0, s>>>(ws.segsums, ws.winsums, plan);
+    KZ_COUNT_LAUNCH();
+    k_msm_combine<<<1, 32, 0, s>>>(ws.winsums, plan.W, plan.c, out);
+    KZ_COUNT_LAUNCH();
+}

@@ -1,0 +1,73 @@
+// Launcher prototypes shared by the translation units of libkzgb200.so (host side only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstddef>
+#include <cstdint>
+
+#include "msm.cuh"
+#include "pairing.cuh"
+
+extern std::atomic<uint64_t> g_kzgb_launches;      // counts every kernel launch of this library
+#define KZ_COUNT_LAUNCH() (g_kzgb_launches.fetch_add(1, std::memory_order_relaxed))
+
+// ---- k_decompress.cu
+// points [0,n): from inC, [n,2n): from inPi (48 B compressed each).  out_pts: 2 Fp per point (Montgomery
+// affine, (0,0) = infinity/invalid).  counters[0] += number of points with status != 0.
+void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, Fp* out_pts, uint8_t* status,
+                       uint32_t* counters);
+void launch_points_to_be(cudaStream_t s, const Fp* pts, size_t m, uint8_t* out96);           // canonical x||y
+void launch_points_from_be(cudaStream_t s, const uint8_t* in96, size_t m, Fp* pts, uint32_t* counters);
+void launch_debug_op(cudaStream_t s, int op, const uint8_t* in, uint8_t* out, size_t count);
+void launch_imad_bench(cudaStream_t s, uint32_t* sink, int blocks, int threads, int iters);
+
+// ---- k_fs.cu
+void launch_leaf_hash(cudaStream_t s, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
+                      uint32_t* leaves, uint32_t* counters /* [1] += scalars >= r */);
+void launch_chunk_hash(cudaStream_t s, const uint32_t* leaves, size_t n, uint32_t* digests_words);
+// r_i (4 limbs), rz_i = r_i z_i (8 limbs), block partials of sum r_i y_i; then sum + slot n of rz = -sum
+void launch_challenges(cudaStream_t s, const uint32_t* root_words, uint64_t global_offset, const uint8_t* z,
+                       const uint8_t* y, size_t n, int single, uint32_t* r_out, uint32_t* rz_out, uint32_t* partials,
+                       uint32_t* sum_ry_out /*8 limbs canonical*/);
+void launch_r_only(cudaStream_t s, const uint32_t* root_words, size_t n, uint8_t* r_be16);
+void launch_synth(cudaStream_t s, uint64_t seed, uint64_t offset, size_t n, const Fp* comb_table, uint8_t* C, uint8_t* z,
+                  uint8_t* y, uint8_t* pi);
+void launch_build_comb(cudaStream_t s, Fp* comb_table /* 32*255 affine points */);
+void launch_scalars_from_be(cudaStream_t s, const uint8_t* be32, size_t m, uint32_t* limbs8, uint32_t* counters);
+void host_sha256_root(uint8_t out[32], const uint8_t* digests, size_t n_chunks, uint64_t n_total);
+
+// ---- k_msm.cu
+struct MsmWorkspace {
+    uint32_t *keys, *vals, *keys_alt, *vals_alt;   // capacity entries each
+    size_t capacity;
+    uint32_t* bucket_start;                        // total_buckets + 2
+    G1Xyzz* buckets;                               // max total buckets
+    G1Xyzz* segsums;                               // max total segs
+    G1Xyzz* winsums;                               // KZ_MSM_MAX_WINDOWS
+    void* cub_temp;
+    size_t cub_temp_bytes;
+    size_t max_buckets, max_segs;
+};
+size_t msm_cub_temp_bytes(size_t entries);
+// digits + sort + bucket boundaries for `m` scalars of `nl` limbs each
+void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars, int nl, size_t m, MsmWorkspace& ws);
+// accumulate + reduce + combine over points `pts` (2 Fp each, m points) using the sorted entries in ws
+void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, size_t m, MsmWorkspace& ws);
+void msm_reduce_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, G1Jac* out);
+
+// ---- k_pairing.cu
+// setup: decompress the two G2 points, subgroup-check, precompute lines.  status[0] = 1 on success.
+void launch_g2_setup(cudaStream_t s, const uint8_t* g2_bytes /*192*/, G2Lines* lines /*2*/, int* status);
+void launch_g1_setup(cudaStream_t s, const uint8_t* g1_bytes /*48*/, Fp* g1_pt /*2 Fp*/, int* status);
+// partial = (S1 + S2') | S3 | sum_ry as canonical big-endian bytes (320 B)
+void launch_make_partial(cudaStream_t s, const G1Jac* s1, const G1Jac* s2, const G1Jac* s3, const uint32_t* sum_ry,
+                         uint8_t* partial_out);
+// combine G partials (device copy of 320*G bytes) -> A, B (Jacobian) and run the pairing check
+void launch_combine(cudaStream_t s, const uint8_t* partials, int n_partials, G1Jac* AB /*2*/, uint32_t* sum_ry_total);
+void launch_pairing(cudaStream_t s, const G2Lines* lines, const G1Jac* AB, int* result);
+void launch_points_jac_from_be(cudaStream_t s, const uint8_t* in96, int m, G1Jac* out);
+// artefacts: S1,S2,S3,A,B affine canonical from the Jacobian sums (S2 = S2' + sum_ry * G)
+void launch_artifacts(cudaStream_t s, const G1Jac* s1, const G1Jac* s2p, const G1Jac* s3, const uint32_t* sum_ry,
+                      const Fp* g1_pt, uint8_t* out /*5*96 + 32*/);
+void launch_pairing_debug(cudaStream_t s, int op, const G2Lines* lines, const uint8_t* in, uint8_t* out);

@@ -1,0 +1,341 @@
+// Two-pairing product check  e(A,G2) * e(B,[tau]G2) == 1  as ONE small cooperative device kernel
+// (BASELINE.json:5: "The final two-pairing Miller loop and final exponentiation run as one small device
+// kernel, since they are latency- rather than throughput-bound").
+//
+// Latency design: Fp12 = Fp2[w]/(w^6 - xi) is kept in shared memory in the flat basis w^0..w^5; one
+// Fp12 product is spread over 72 threads (36 Fp2 partial products x {real, imaginary}) followed by a
+// 12-thread fold with w^6 = xi = 1+u.  Control flow is uniform over the block.  The G2 arguments are
+// fixed per context, so their 68 line-function coefficient pairs each are precomputed once at context
+// creation (affine twist arithmetic) and only evaluated at A/B here.  A and B are taken in Jacobian
+// form and the lines are scaled by Z^3 (an Fp factor the final exponentiation kills), so no inversion
+// is needed to normalise the MSM outputs.
+//
+// Line through twist points, scaled by w^3:  l = (lam*xT - yT) + (-lam*xP) w^2 + yP w^3
+// (derivation: DESIGN.md "Pairing"; the CPU oracle uses the same placement but computes lam on the fly).
+#pragma once
+#include "g1.cuh"
+
+struct Fp2 { Fp c0, c1; };
+struct Fp12 { Fp2 c[6]; };
+
+#if defined(KZGB_EMU)
+#define COOP_FOR(t, n) for (int t = 0; t < (n); ++t)
+#define COOP_SYNC() ((void)0)
+#else
+#define COOP_FOR(t, n) for (int t = threadIdx.x; t < (n); t += blockDim.x)
+#define COOP_SYNC() __syncthreads()
+#endif
+
+// ------------------------------------------------------------------ serial Fp2 (setup kernel, cold)
+KZ_HD Fp2 fp2_zero() { return {fp_zero(), fp_zero()}; }
+KZ_HD Fp2 fp2_one() { return {fp_one(), fp_zero()}; }
+KZ_HD Fp2 fp2_add(const Fp2& a, const Fp2& b) { return {fp_add(a.c0, b.c0), fp_add(a.c1, b.c1)}; }
+KZ_HD Fp2 fp2_sub(const Fp2& a, const Fp2& b) { return {fp_sub(a.c0, b.c0), fp_sub(a.c1, b.c1)}; }
+KZ_HD Fp2 fp2_neg(const Fp2& a) { return {fp_neg(a.c0), fp_neg(a.c1)}; }
+KZ_HD Fp2 fp2_dbl(const Fp2& a) { return {fp_dbl(a.c0), fp_dbl(a.c1)}; }
+KZ_HD Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
+    Fp t0 = fp_mul(a.c0, b.c0), t1 = fp_mul(a.c1, b.c1);
+    Fp t2 = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+    return {fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
+}
+KZ_HD Fp2 fp2_sqr(const Fp2& a) {
+    Fp t = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
+    return {t, fp_dbl(fp_mul(a.c0, a.c1))};
+}
+KZ_HD bool fp2_is_zero(const Fp2& a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
+KZ_HD bool fp2_eq(const Fp2& a, const Fp2& b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
+KZ_COLD Fp2 fp2_inv(const Fp2& a) {
+    Fp n = fp_inv(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
+    return {fp_mul(a.c0, n), fp_neg(fp_mul(a.c1, n))};
+}
+KZ_COLD Fp2 fp2_pow_const(const Fp2& a, const u32* e, int nbits) {
+    Fp2 r = a;
+    for (int i = nbits - 2; i >= 0; --i) {
+        r = fp2_sqr(r);
+        if ((e[i >> 5] >> (i & 31)) & 1) r = fp2_mul(r, a);
+    }
+    return r;
+}
+// sqrt in Fp2 for p = 3 mod 4; false if a is a non-residue
+KZ_COLD bool fp2_sqrt(Fp2& out, const Fp2& a) {
+    if (fp2_is_zero(a)) { out = a; return true; }
+    Fp2 a1 = fp2_pow_const(a, EXP_PM3D4, 379);
+    Fp2 alpha = fp2_mul(fp2_sqr(a1), a);
+    Fp2 x0 = fp2_mul(a1, a);
+    Fp2 x;
+    if (fp2_eq(alpha, fp2_neg(fp2_one()))) {
+        x = {fp_neg(x0.c1), x0.c0};                          // u * x0
+    } else {
+        Fp2 b = fp2_pow_const(fp2_add(fp2_one(), alpha), EXP_PM1D2, 380);
+        x = fp2_mul(b, x0);
+    }
+    out = x;
+    return fp2_eq(fp2_sqr(x), a);
+}
+KZ_HD bool fp2_is_lex_largest(const Fp2& a) { return fp_is_zero(a.c1) ? fp_is_lex_largest(a.c0) : fp_is_lex_largest(a.c1); }
+
+// ------------------------------------------------------------------ G2 setup: decompress, subgroup, lines
+struct G2Aff { Fp2 x, y; };
+#define KZ_N_LINES 68                      // 63 doublings + 5 additions for |x|
+struct G2Lines { Fp2 a[KZ_N_LINES], b[KZ_N_LINES]; };   // l = a + (b * xP) w^2 + yP w^3
+
+KZ_COLD bool g2_decompress(G2Aff& q, const u8* in) {
+    u8 b0 = in[0];
+    if (!(b0 & 0x80) || (b0 & 0x40)) return false;
+    u8 tmp[48];
+    for (int i = 0; i < 48; ++i) tmp[i] = in[i];
+    tmp[0] &= 0x1F;
+    if (!fp_from_be(q.x.c1, tmp) || !fp_from_be(q.x.c0, in + 48)) return false;
+    Fp2 b4 = {fp_const(FP_B), fp_const(FP_B)};                // 4(1+u)
+    Fp2 rhs = fp2_add(fp2_mul(fp2_sqr(q.x), q.x), b4);
+    if (!fp2_sqrt(q.y, rhs)) return false;
+    if (fp2_is_lex_largest(q.y) != ((b0 & 0x20) != 0)) q.y = fp2_neg(q.y);
+    return true;
+}
+// affine twist step helpers; return false on a vanishing denominator (degenerate input)
+KZ_COLD bool g2_dbl_step(G2Aff& t, Fp2& la, Fp2& lb) {
+    if (fp2_is_zero(t.y)) return false;
+    Fp2 x2 = fp2_sqr(t.x);
+    Fp2 lam = fp2_mul(fp2_add(fp2_dbl(x2), x2), fp2_inv(fp2_dbl(t.y)));
+    la = fp2_sub(fp2_mul(lam, t.x), t.y);
+    lb = fp2_neg(lam);
+    Fp2 x3 = fp2_sub(fp2_sqr(lam), fp2_dbl(t.x));
+    t.y = fp2_sub(fp2_mul(lam, fp2_sub(t.x, x3)), t.y);
+    t.x = x3;
+    return true;
+}
+KZ_COLD bool g2_add_step(G2Aff& t, const G2Aff& q, Fp2& la, Fp2& lb) {
+    Fp2 dx = fp2_sub(t.x, q.x);
+    if (fp2_is_zero(dx)) return false;
+    Fp2 lam = fp2_mul(fp2_sub(t.y, q.y), fp2_inv(dx));
+    la = fp2_sub(fp2_mul(lam, q.x), q.y);
+    lb = fp2_neg(lam);
+    Fp2 x3 = fp2_sub(fp2_sub(fp2_sqr(lam), t.x), q.x);
+    t.y = fp2_sub(fp2_mul(lam, fp2_sub(t.x, x3)), t.y);
+    t.x = x3;
+    return true;
+}
+// [|x|]Q with the line coefficients of every step (lines may be null)
+KZ_COLD bool g2_mul_xabs(G2Aff& out, const G2Aff& q, G2Lines* lines) {
+    G2Aff t = q;
+    const u64 k = ((u64)X_ABS_HI << 32) | X_ABS_LO;
+    int s = 0;
+    Fp2 la, lb;
+    for (int i = 62; i >= 0; --i) {
+        if (!g2_dbl_step(t, la, lb)) return false;
+        if (lines) { lines->a[s] = la; lines->b[s] = lb; }
+        ++s;
+        if ((k >> i) & 1) {
+            if (!g2_add_step(t, q, la, lb)) return false;
+            if (lines) { lines->a[s] = la; lines->b[s] = lb; }
+            ++s;
+        }
+    }
+    out = t;
+    return true;
+}
+// full setup of one G2 point: decompress, r-torsion check ([x^4]Q + Q == [x^2]Q, r = x^4 - x^2 + 1), lines
+KZ_COLD bool g2_setup_point(G2Lines& lines, const u8* in96) {
+    G2Aff q, q1, q2, q3, q4;
+    if (!g2_decompress(q, in96)) return false;
+    if (!g2_mul_xabs(q1, q, &lines)) return false;
+    if (!g2_mul_xabs(q2, q1, nullptr)) return false;
+    if (!g2_mul_xabs(q3, q2, nullptr)) return false;
+    if (!g2_mul_xabs(q4, q3, nullptr)) return false;
+    Fp2 la, lb;
+    if (!g2_add_step(q4, q, la, lb)) return false;           // q4 <- [x^4]Q + Q
+    return fp2_eq(q4.x, q2.x) && fp2_eq(q4.y, q2.y);
+}
+
+// ------------------------------------------------------------------ cooperative Fp12 (shared memory)
+struct PairScratch {
+    Fp12 f, a, b, c, t;          // working values
+    Fp12 l0, l1;                 // sparse line values (entries 0, 2, 3 only)
+    Fp2 prod[36];
+    Fp pz3[2], pxz[2], py[2];    // per-pair  Z^3, X*Z, Y
+    int pinf[2];
+    int result;
+};
+
+KZ_COLD void coop_mul(PairScratch& S, Fp12& dst, const Fp12& x, const Fp12& y) {
+    COOP_FOR(t, 72) {
+        int q = t >> 1, i = q / 6, j = q % 6;
+        Fp a0 = x.c[i].c0, a1 = x.c[i].c1, b0 = y.c[j].c0, b1 = y.c[j].c1;
+        if ((t & 1) == 0) S.prod[q].c0 = fp_sub(fp_mul(a0, b0), fp_mul(a1, b1));
+        else S.prod[q].c1 = fp_add(fp_mul(a0, b1), fp_mul(a1, b0));
+    }
+    COOP_SYNC();
+    COOP_FOR(t, 12) {
+        int k = t >> 1, h = t & 1;
+        Fp lo = fp_zero(), h0 = fp_zero(), h1 = fp_zero();
+        for (int i = 0; i < 6; ++i) {
+            int j = k - i;
+            if (j >= 0 && j < 6) lo = fp_add(lo, h ? S.prod[i * 6 + j].c1 : S.prod[i * 6 + j].c0);
+            j = k + 6 - i;
+            if (j >= 0 && j < 6) { h0 = fp_add(h0, S.prod[i * 6 + j].c0); h1 = fp_add(h1, S.prod[i * 6 + j].c1); }
+        }
+        // xi * (h0 + h1 u) = (h0 - h1) + (h0 + h1) u
+        Fp r = h ? fp_add(lo, fp_add(h0, h1)) : fp_add(lo, fp_sub(h0, h1));
+        if (h) dst.c[k].c1 = r; else dst.c[k].c0 = r;
+    }
+    COOP_SYNC();
+}
+KZ_COLD void coop_copy(Fp12& dst, const Fp12& src) {
+    COOP_FOR(t, 12) { if (t & 1) dst.c[t >> 1].c1 = src.c[t >> 1].c1; else dst.c[t >> 1].c0 = src.c[t >> 1].c0; }
+    COOP_SYNC();
+}
+KZ_COLD void coop_set_one(Fp12& dst) {
+    COOP_FOR(t, 12) {
+        Fp v = t == 0 ? fp_one() : fp_zero();
+        if (t & 1) dst.c[t >> 1].c1 = v; else dst.c[t >> 1].c0 = v;
+    }
+    COOP_SYNC();
+}
+KZ_COLD void coop_conj(Fp12& dst, const Fp12& src) {          // w -> -w
+    COOP_FOR(t, 12) {
+        int k = t >> 1;
+        Fp v = (t & 1) ? src.c[k].c1 : src.c[k].c0;
+        if (k & 1) v = fp_neg(v);
+        if (t & 1) dst.c[k].c1 = v; else dst.c[k].c0 = v;
+    }
+    COOP_SYNC();
+}
+KZ_COLD void coop_frob1(Fp12& dst, const Fp12& src) {         // c_k = conj(a_k) * gamma1_k ; dst must NOT alias src
+    COOP_FOR(t, 12) {
+        int k = t >> 1;
+        Fp a0 = src.c[k].c0, a1 = src.c[k].c1;
+        Fp g0 = fp_const(FROB1_GAMMA + 24 * k), g1 = fp_const(FROB1_GAMMA + 24 * k + 12);
+        Fp v = (t & 1) ? fp_sub(fp_mul(a0, g1), fp_mul(a1, g0)) : fp_add(fp_mul(a0, g0), fp_mul(a1, g1));
+        if (t & 1) dst.c[k].c1 = v; else dst.c[k].c0 = v;
+    }
+    COOP_SYNC();
+}
+KZ_COLD void coop_frob2(Fp12& dst, const Fp12& src) {         // c_k = a_k * gamma2_k, gamma2 in Fp
+    COOP_FOR(t, 12) {
+        int k = t >> 1;
+        Fp v = fp_mul((t & 1) ? src.c[k].c1 : src.c[k].c0, fp_const(FROB2_GAMMA + 12 * k));
+        if (t & 1) dst.c[k].c1 = v; else dst.c[k].c0 = v;
+    }
+    COOP_SYNC();
+}
+// dst = x^|x| (square-and-multiply, 63 squarings + 5 products), then conjugated: x^x for x<0 in the
+// cyclotomic subgroup.  dst must not alias x; uses S.t.
+KZ_COLD void coop_pow_x(PairScratch& S, Fp12& dst, const Fp12& x) {
+    const u64 k = ((u64)X_ABS_HI << 32) | X_ABS_LO;
+    coop_copy(S.t, x);
+    for (int i = 62; i >= 0; --i) {
+        coop_mul(S, S.t, S.t, S.t);
+        if ((k >> i) & 1) coop_mul(S, S.t, S.t, x);
+    }
+    coop_conj(dst, S.t);
+}
+// dst = x^-1.  Norm chain through Frobenius: n6 = x*conj(x) in Fp6, n2 = n6 * n6^(p^2) * n6^(p^4) in Fp2.
+// Uses S.a, S.b, S.c, S.t; dst must be S.f or distinct from those.
+KZ_COLD void coop_inv(PairScratch& S, Fp12& dst, const Fp12& x) {
+    coop_conj(S.a, x);                       // a = conj(x)
+    coop_mul(S, S.b, x, S.a);                // b = n6
+    coop_frob2(S.c, S.b);                    // c = n6^(p^2)
+    coop_frob2(S.t, S.c);                    // t = n6^(p^4)
+    coop_mul(S, S.c, S.c, S.t);              // c = n6^(p^2+p^4)
+    coop_mul(S, S.b, S.b, S.c);              // b = n2 (in Fp2: only coefficient 0)
+    COOP_FOR(t, 1) { S.b.c[0] = fp2_inv(S.b.c[0]); }
+    COOP_SYNC();
+    coop_mul(S, S.a, S.a, S.c);              // a = conj(x) * n6^(p^2+p^4)
+    COOP_FOR(t, 12) {                        // dst = a * n2^-1
+        int k = t >> 1;
+        Fp s0 = S.b.c[0].c0, s1 = S.b.c[0].c1, a0 = S.a.c[k].c0, a1 = S.a.c[k].c1;
+        Fp v = (t & 1) ? fp_add(fp_mul(a0, s1), fp_mul(a1, s0)) : fp_sub(fp_mul(a0, s0), fp_mul(a1, s1));
+        if (t & 1) dst.c[k].c1 = v; else dst.c[k].c0 = v;
+    }
+    COOP_SYNC();
+}
+
+// f <- f^(3 (p^12-1)/r): easy part, then the hard part 3(p^4-p^2+1)/r = (x-1)^2 (x+p)(x^2+p^2-1) + 3.
+// In/out: S.f.
+KZ_COLD void coop_final_exp(PairScratch& S) {
+    coop_inv(S, S.l0, S.f);                  // l0 = f^-1   (l0/l1 are free after the Miller loop)
+    coop_conj(S.a, S.f);
+    coop_mul(S, S.f, S.a, S.l0);             // f = f^(p^6-1)
+    coop_frob2(S.a, S.f);
+    coop_mul(S, S.f, S.a, S.f);              // f = f^((p^6-1)(p^2+1))  -- cyclotomic from here on
+    // a = f^(x-1)
+    coop_pow_x(S, S.a, S.f);
+    coop_conj(S.b, S.f);
+    coop_mul(S, S.a, S.a, S.b);
+    // a = a^(x-1)
+    coop_pow_x(S, S.b, S.a);
+    coop_conj(S.c, S.a);
+    coop_mul(S, S.a, S.b, S.c);
+    // b = a^(x+p)
+    coop_pow_x(S, S.b, S.a);
+    coop_frob1(S.c, S.a);
+    coop_mul(S, S.b, S.b, S.c);
+    // c = b^(x^2+p^2-1)
+    coop_pow_x(S, S.c, S.b);
+    coop_pow_x(S, S.a, S.c);                 // a = b^(x^2)
+    coop_frob2(S.c, S.b);
+    coop_mul(S, S.a, S.a, S.c);
+    coop_conj(S.c, S.b);
+    coop_mul(S, S.a, S.a, S.c);              // a = b^(x^2+p^2-1)
+    // result = a * f^3
+    coop_mul(S, S.b, S.f, S.f);
+    coop_mul(S, S.b, S.b, S.f);
+    coop_mul(S, S.f, S.a, S.b);
+}
+
+// Evaluate the step-s lines of both fixed G2 points at the two G1 arguments into S.l0, S.l1.
+KZ_COLD void coop_eval_lines(PairScratch& S, const G2Lines* lines, int s) {
+    COOP_FOR(t, 8) {
+        int pr = t >> 2, which = t & 3;
+        Fp12& L = pr ? S.l1 : S.l0;
+        const Fp2& src = (which < 2) ? lines[pr].a[s] : lines[pr].b[s];
+        Fp m = (which < 2) ? S.pz3[pr] : S.pxz[pr];
+        Fp v = fp_mul((which & 1) ? src.c1 : src.c0, m);
+        Fp2& d = (which < 2) ? L.c[0] : L.c[2];
+        if (which & 1) d.c1 = v; else d.c0 = v;
+    }
+    COOP_SYNC();
+}
+// Miller loop product for (P0, Q0), (P1, Q1) with precomputed lines; P_k Jacobian.  Result in S.f.
+KZ_COLD void coop_miller(PairScratch& S, const G2Lines* lines, const G1Jac* P) {
+    COOP_FOR(t, 2) {
+        G1Jac p = P[t];
+        S.pinf[t] = jac_is_inf(p) ? 1 : 0;
+        Fp zz = fp_sqr(p.Z);
+        S.pz3[t] = fp_mul(zz, p.Z);
+        S.pxz[t] = fp_mul(p.X, p.Z);
+        S.py[t] = p.Y;
+    }
+    COOP_SYNC();
+    COOP_FOR(t, 24) {                                       // zero both sparse line holders, then place Y at w^3
+        Fp12& L = (t >= 12) ? S.l1 : S.l0;
+        int u = t % 12, k = u >> 1;
+        Fp v = (k == 3 && (u & 1) == 0) ? S.py[t >= 12 ? 1 : 0] : fp_zero();
+        if (u & 1) L.c[k].c1 = v; else L.c[k].c0 = v;
+    }
+    COOP_SYNC();
+    coop_set_one(S.f);
+    const u64 k = ((u64)X_ABS_HI << 32) | X_ABS_LO;
+    int s = 0;
+    for (int i = 62; i >= 0; --i) {
+        coop_mul(S, S.f, S.f, S.f);
+        for (int rep = 0; rep < 1 + (int)((k >> i) & 1); ++rep) {
+            coop_eval_lines(S, lines, s);
+            if (!S.pinf[0]) coop_mul(S, S.f, S.f, S.l0);
+            if (!S.pinf[1]) coop_mul(S, S.f, S.f, S.l1);
+            ++s;
+        }
+    }
+    coop_conj(S.f, S.f);
+}
+// whole check; result (1 = product is one) in S.result
+KZ_COLD void coop_pairing_check(PairScratch& S, const G2Lines* lines, const G1Jac* P) {
+    coop_miller(S, lines, P);
+    coop_final_exp(S);
+    COOP_FOR(t, 1) {
+        bool one = fp_eq(S.f.c[0].c0, fp_one()) && fp_is_zero(S.f.c[0].c1);
+        for (int k = 1; k < 6; ++k) one = one && fp2_is_zero(S.f.c[k]);
+        S.result = one ? 1 : 0;
+    }
+    COOP_SYNC();
+}

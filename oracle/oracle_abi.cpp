@@ -52,13 +52,16 @@ int kzgb_set_threads(kzgb_ctx* c, int n) {
     return c ? c->threads : 0;
 }
 
-static void partial_to_bytes(uint8_t* out, const Partial& p) {
-    G1J s12 = p.s1.add(p.s2);
+// partial = A_shard | S3_shard | sum_ry_shard with A_shard = S1 + S2 - sum_ry_shard * G1 (Jacobian, canonical BE)
+static void partial_to_bytes(uint8_t* out, const Partial& p, const Setup& st) {
+    u64 k[4];
+    p.sum_ry.to_raw(k);
+    G1J a = p.s1.add(p.s2).add(st.g1.jac().mul(k, 4).neg());
     auto put = [](uint8_t* o, const G1J& j) {
         if (j.is_inf()) { memset(o, 0, 144); return; }
         j.X.to_bytes_be(o); j.Y.to_bytes_be(o + 48); j.Z.to_bytes_be(o + 96);
     };
-    put(out, s12);
+    put(out, a);
     put(out + 144, p.s3);
     p.sum_ry.to_bytes_be(out + 288);
 }
@@ -121,22 +124,32 @@ kzgb_ret kzgb_fs_root(uint8_t root[32], const uint8_t* dig, size_t nch, uint64_t
 kzgb_ret kzgb_shard_phase2(kzgb_ctx* c, int slot, const uint8_t root[32], uint64_t off, void*, uint8_t out[KZGB_PARTIAL_BYTES]) {
     if (!c || slot < 0 || slot >= (int)c->shards.size() || !root || !out) return KZGB_BADARGS;
     Partial p = shard_phase2(c->shards[slot], root, off, c->threads);
-    partial_to_bytes(out, p);
+    partial_to_bytes(out, p, c->setup);
     return KZGB_OK;
 }
 kzgb_ret kzgb_combine_verify(kzgb_ctx* c, const uint8_t* parts, int np, bool* ok) {
     if (!c || !parts || np < 1 || !ok) return KZGB_BADARGS;
     *ok = false;
-    std::vector<Partial> ps(np);
+    G1J a = G1J::inf(), s3 = G1J::inf();
+    Fr sry = Fr::zero();
     for (int i = 0; i < np; ++i) {
         const uint8_t* b = parts + (size_t)KZGB_PARTIAL_BYTES * i;
         auto get = [](G1J& j, const uint8_t* o) {
             return Fp::from_bytes_be(j.X, o) && Fp::from_bytes_be(j.Y, o + 48) && Fp::from_bytes_be(j.Z, o + 96);
         };
-        ps[i].s2 = G1J::inf();
-        if (!get(ps[i].s1, b) || !get(ps[i].s3, b + 144) || !Fr::from_bytes_be(ps[i].sum_ry, b + 288)) return KZGB_BADARGS;
+        G1J pa, p3;
+        Fr v;
+        if (!get(pa, b) || !get(p3, b + 144) || !Fr::from_bytes_be(v, b + 288)) return KZGB_BADARGS;
+        a = a.add(pa); s3 = s3.add(p3); sry = sry + v;
     }
-    *ok = combine_verify(c->art, c->setup, ps.data(), np);
+    c->art = Artifacts();
+    c->art.S1 = c->art.S2 = c->art.S3 = G1A::infinity();     // per-sum artefacts are not carried by partials
+    c->art.A = g1_affine(a);
+    c->art.B = g1_affine(s3.neg());
+    c->art.sum_ry = sry;
+    G1A P[2] = {c->art.A, c->art.B};
+    G2A Q[2] = {c->setup.g2_0, c->setup.g2_1};
+    *ok = pairing_product_is_one(P, Q, 2);
     return KZGB_OK;
 }
 

@@ -1,0 +1,353 @@
+// TEST INFRASTRUCTURE ONLY -- host emulation of the CUDA kernels' per-thread bodies.
+// The device math headers of kzg_batch_verification_scheme_b200/csrc are compiled here by g++ with
+// -DKZGB_EMU (portable limb loops instead of the inline-PTX blocks, `for` loops instead of thread
+// indices) so the no-GPU CI can exercise the SAME decompression / subgroup / SHA / MSM / pairing logic
+// that runs on the B200 and diff it against the oracle.  Nothing in the product library links this.
+#include <algorithm>
+#include <vector>
+
+#include "../../include/kzgb200.h"
+#include "../../kzg_batch_verification_scheme_b200/csrc/msm.cuh"
+#include "../../kzg_batch_verification_scheme_b200/csrc/pairing.cuh"
+#include "../../kzg_batch_verification_scheme_b200/csrc/sha256.cuh"
+
+struct kzgb_ctx {
+    G2Lines lines[2];
+    G1Aff g1;
+    kzgb_artifacts art;
+    G1Jac sums[3];
+    Fr sum_ry;
+    bool have_sums = false;
+};
+
+static void words_from_be(u32* w, const u8* in, int nw) {
+    for (int i = 0; i < nw; ++i) w[i] = (u32)in[4 * i] << 24 | in[4 * i + 1] << 16 | in[4 * i + 2] << 8 | in[4 * i + 3];
+}
+static void words_to_be(u8* out, const u32* w, int nw) {
+    for (int i = 0; i < nw; ++i) { out[4 * i] = w[i] >> 24; out[4 * i + 1] = w[i] >> 16; out[4 * i + 2] = w[i] >> 8; out[4 * i + 3] = w[i]; }
+}
+
+// emulated MSM pipeline: digits -> sort -> bounds -> accumulate -> segments -> window sums -> combine
+static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nbits) {
+    MsmPlan plan = msm_make_plan(m, nbits);
+    size_t N = m * (size_t)plan.W;
+    std::vector<u32> keys(N), vals(N);
+    for (size_t i = 0; i < m; ++i) {
+        u32 sc[8];
+        for (int k = 0; k < 8; ++k) sc[k] = k < nl ? scalars[nl * i + k] : 0;
+        msm_digits_body(keys.data(), vals.data(), sc, i, m, plan);
+    }
+    std::vector<size_t> order(N);
+    for (size_t i = 0; i < N; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+    std::vector<u32> sk(N), sv(N);
+    for (size_t i = 0; i < N; ++i) { sk[i] = keys[order[i]]; sv[i] = vals[order[i]]; }
+    std::vector<u32> start(plan.total_buckets + 2);
+    for (u32 b = 0; b <= plan.total_buckets + 1; ++b) start[b] = (u32)(std::lower_bound(sk.begin(), sk.end(), b) - sk.begin());
+    std::vector<G1Xyzz> buckets(plan.total_buckets), segs(plan.total_segs), wins(plan.W);
+    for (u32 b = 0; b < plan.total_buckets; ++b) buckets[b] = msm_bucket_body(pts, sv.data(), start[b], start[b + 1]);
+    for (u32 s = 0; s < plan.total_segs; ++s) {
+        int w = 0;
+        while (s >= plan.seg_off[w + 1]) ++w;
+        segs[s] = msm_segment_body(buckets.data() + plan.bucket_off[w], plan.nb[w], s - plan.seg_off[w]);
+    }
+    for (int w = 0; w < plan.W; ++w) {
+        G1Xyzz acc = xyzz_inf();
+        for (u32 s = plan.seg_off[w]; s < plan.seg_off[w + 1]; ++s) acc = xyzz_add(acc, segs[s]);
+        wins[w] = acc;
+    }
+    return xyzz_to_jac(msm_combine_body(wins.data(), plan.W, plan.c));
+}
+
+extern "C" {
+
+const char* kzgb_version(void) { return "kzgb200-emu (tests only)"; }
+
+kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const uint8_t* g2m, size_t n2, const int*, int, size_t) {
+    if (!out || !g1m || !g2m || n1 < 1 || n2 < 2) return KZGB_BADARGS;
+    kzgb_ctx* c = new kzgb_ctx();
+    u32 w[12];
+    words_from_be(w, g1m, 12);
+    bool ok = g1_decompress_validate(c->g1, w) == ST_OK && !aff_is_inf(c->g1);
+    ok = ok && g2_setup_point(c->lines[0], g2m) && g2_setup_point(c->lines[1], g2m + 96);
+    if (!ok) { delete c; return KZGB_BADARGS; }
+    *out = c;
+    return KZGB_OK;
+}
+void kzgb_ctx_free(kzgb_ctx* c) { delete c; }
+
+kzgb_ret kzgb_g1_decompress_batch(uint8_t* aff, uint8_t* st, const uint8_t* in, size_t m, kzgb_ctx*) {
+    for (size_t i = 0; i < m; ++i) {
+        u32 w[12];
+        words_from_be(w, in + 48 * i, 12);
+        G1Aff p;
+        st[i] = (u8)g1_decompress_validate(p, w);
+        aff_to_be96(aff + 96 * i, p);
+    }
+    return KZGB_OK;
+}
+
+static void emu_digests(std::vector<u8>& dig, const u8* C, const u8* z, const u8* y, const u8* pi, size_t n) {
+    std::vector<u32> leaves(8 * n);
+    for (size_t i = 0; i < n; ++i) {
+        u32 cw[12], pw[12], zw[8], yw[8];
+        words_from_be(cw, C + 48 * i, 12); words_from_be(pw, pi + 48 * i, 12);
+        words_from_be(zw, z + 32 * i, 8); words_from_be(yw, y + 32 * i, 8);
+        fs_leaf_words(&leaves[8 * i], cw, zw, yw, pw);
+    }
+    size_t nch = (n + 1023) / 1024;
+    dig.resize(32 * nch);
+    for (size_t j = 0; j < nch; ++j) {
+        u32 h[8];
+        size_t lo = j * 1024;
+        fs_chunk_words(h, &leaves[8 * lo], (u32)std::min<size_t>(1024, n - lo));
+        words_to_be(&dig[32 * j], h, 8);
+    }
+}
+// root hash through the device-side compression function (message = tag | deg | n | digests)
+static void emu_root(u8 root[32], const std::vector<u8>& dig, u64 n) {
+    std::vector<u8> msg;
+    const char* tag = "KZGB200/root_v1_";
+    msg.insert(msg.end(), tag, tag + 16);
+    for (int i = 0; i < 8; ++i) msg.push_back((u8)((u64)4096 >> (56 - 8 * i)));
+    for (int i = 0; i < 8; ++i) msg.push_back((u8)(n >> (56 - 8 * i)));
+    msg.insert(msg.end(), dig.begin(), dig.end());
+    u64 bits = msg.size() * 8;
+    msg.push_back(0x80);
+    while (msg.size() % 64 != 56) msg.push_back(0);
+    for (int i = 0; i < 8; ++i) msg.push_back((u8)(bits >> (56 - 8 * i)));
+    u32 h[8];
+    sha256_init(h);
+    for (size_t b = 0; b < msg.size(); b += 64) {
+        u32 w[16];
+        words_from_be(w, &msg[b], 16);
+        sha256_compress(h, w);
+    }
+    words_to_be(root, h, 8);
+}
+
+kzgb_ret kzgb_fs_challenges(uint8_t root[32], uint8_t* r_out, const uint8_t* C, const uint8_t* z, const uint8_t* y,
+                            const uint8_t* pi, size_t n, kzgb_ctx*) {
+    std::vector<u8> dig;
+    emu_digests(dig, C, z, y, pi, n);
+    emu_root(root, dig, n);
+    u32 rw[8];
+    words_from_be(rw, root, 8);
+    for (size_t i = 0; i < n; ++i) {
+        u32 r[4];
+        fs_r_limbs(r, rw, i);
+        u32 be[4] = {r[3], r[2], r[1], r[0]};
+        words_to_be(r_out + 16 * i, be, 4);
+    }
+    return KZGB_OK;
+}
+
+static kzgb_ret emu_verify(bool* ok, const u8* C, const u8* z, const u8* y, const u8* pi, size_t n, kzgb_ctx* c, bool single) {
+    *ok = false;
+    if (!n) return KZGB_BADARGS;
+    memset(&c->art, 0, sizeof c->art);
+    c->art.n = n;
+    c->have_sums = false;
+    std::vector<Fp> pts(2 * (2 * n + 1));
+    u32 badp = 0, bads = 0;
+    for (size_t i = 0; i < 2 * n; ++i) {
+        u32 w[12];
+        words_from_be(w, i < n ? C + 48 * i : pi + 48 * (i - n), 12);
+        G1Aff p;
+        badp += g1_decompress_validate(p, w) != ST_OK;
+        pts[2 * i] = p.x; pts[2 * i + 1] = p.y;
+    }
+    std::vector<u8> dig;
+    emu_digests(dig, C, z, y, pi, n);
+    u8 root[32] = {0};
+    if (!single) emu_root(root, dig, n);
+    memcpy(c->art.root, root, 32);
+    u32 rw[8];
+    words_from_be(rw, root, 8);
+    std::vector<u32> r(4 * n), rz(8 * (n + 1));
+    Fr sum = fr_zero();
+    for (size_t i = 0; i < n; ++i) {
+        Fr ri = fr_zero(), zr, yr;
+        if (single) ri.v[0] = 1; else fs_r_limbs(ri.v, rw, i);
+        fr_raw_from_be(zr, z + 32 * i); fr_raw_from_be(yr, y + 32 * i);
+        bads += !fr_raw_is_canonical(zr); bads += !fr_raw_is_canonical(yr);
+        Fr v = fr_mul(ri, fr_to_mont(zr));
+        sum = fr_add(sum, fr_mul(ri, fr_to_mont(yr)));
+        for (int k = 0; k < 4; ++k) r[4 * i + k] = ri.v[k];
+        for (int k = 0; k < 8; ++k) rz[8 * i + k] = v.v[k];
+    }
+    c->art.n_bad_points = badp; c->art.n_bad_scalars = bads;
+    if (badp || bads) return KZGB_BADARGS;
+    Fr neg = fr_neg(sum);
+    for (int k = 0; k < 8; ++k) rz[8 * n + k] = neg.v[k];
+    pts[2 * 2 * n] = c->g1.x; pts[2 * 2 * n + 1] = c->g1.y;
+    c->sums[0] = emu_msm(pts.data(), r.data(), 4, n, 128);
+    c->sums[2] = emu_msm(pts.data() + 2 * n, r.data(), 4, n, 128);
+    c->sums[1] = emu_msm(pts.data() + 2 * n, rz.data(), 8, n + 1, 255);
+    c->sum_ry = sum;
+    c->have_sums = true;
+    G1Jac AB[2] = {jac_add(c->sums[0], c->sums[1]), jac_neg(c->sums[2])};
+    PairScratch S;
+    coop_pairing_check(S, c->lines, AB);
+    *ok = S.result == 1;
+    return KZGB_OK;
+}
+kzgb_ret verify_kzg_proof(bool* ok, const uint8_t C[48], const uint8_t z[32], const uint8_t y[32], const uint8_t pi[48], kzgb_ctx* c) {
+    return emu_verify(ok, C, z, y, pi, 1, c, true);
+}
+kzgb_ret verify_kzg_proof_batch(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n, kzgb_ctx* c) {
+    return emu_verify(ok, C, z, y, pi, n, c, false);
+}
+kzgb_ret kzgb_last_artifacts(kzgb_ctx* c, kzgb_artifacts* out) {
+    if (c->have_sums) {
+        u32 k[8];
+        for (int i = 0; i < 8; ++i) k[i] = c->sum_ry.v[i];
+        G1Jac s2 = jac_add(c->sums[1], jac_mul_limbs(jac_from_aff(c->g1), k, 8));
+        aff_to_be96(c->art.S1, jac_to_aff(c->sums[0]));
+        aff_to_be96(c->art.S2, jac_to_aff(s2));
+        aff_to_be96(c->art.S3, jac_to_aff(c->sums[2]));
+        aff_to_be96(c->art.A, jac_to_aff(jac_add(c->sums[0], c->sums[1])));
+        aff_to_be96(c->art.B, jac_to_aff(jac_neg(c->sums[2])));
+        fr_raw_to_be(c->art.sum_ry, c->sum_ry);
+    }
+    *out = c->art;
+    return KZGB_OK;
+}
+kzgb_ret kzgb_g1_msm(uint8_t out[96], const uint8_t* pa, const uint8_t* sc, size_t m, int nbits, kzgb_ctx*) {
+    std::vector<Fp> pts(2 * m + 2);
+    std::vector<u32> k(8 * m + 8);
+    for (size_t i = 0; i < m; ++i) {
+        G1Aff p;
+        if (!aff_from_be96(p, pa + 96 * i)) return KZGB_BADARGS;
+        pts[2 * i] = p.x; pts[2 * i + 1] = p.y;
+        Fr v;
+        fr_raw_from_be(v, sc + 32 * i);
+        if (!fr_raw_is_canonical(v)) return KZGB_BADARGS;
+        for (int j = 0; j < 8; ++j) k[8 * i + j] = v.v[j];
+    }
+    if (m == 0) { memset(out, 0, 96); return KZGB_OK; }
+    aff_to_be96(out, jac_to_aff(emu_msm(pts.data(), k.data(), 8, m, nbits)));
+    return KZGB_OK;
+}
+kzgb_ret kzgb_pairing_check(bool* ok, const uint8_t A[96], const uint8_t B[96], kzgb_ctx* c) {
+    G1Aff a, b;
+    if (!aff_from_be96(a, A) || !aff_from_be96(b, B)) return KZGB_BADARGS;
+    G1Jac AB[2] = {jac_from_aff(a), jac_from_aff(b)};
+    PairScratch S;
+    coop_pairing_check(S, c->lines, AB);
+    *ok = S.result == 1;
+    return KZGB_OK;
+}
+kzgb_ret kzgb_synth_instance(kzgb_ctx*, uint64_t seed, uint64_t offset, size_t n, uint8_t* C, uint8_t* z, uint8_t* y, uint8_t* pi, int) {
+    G1Aff g = {fp_const(G1_GEN_X), fp_const(G1_GEN_Y)};
+    for (size_t i = 0; i < n; ++i) {
+        u64 idx = offset + i;
+        Fr a = prng_fr(seed, 1, idx), zz = prng_fr(seed, 2, idx), yy = prng_fr(seed, 3, idx);
+        Fr q = fr_mul(fr_sub(a, yy), fr_inv(fr_sub(fr_const(FR_TEST_TAU), zz)));
+        Fr ac = fr_from_mont(a), qc = fr_from_mont(q);
+        u32 w[12];
+        g1_compress_words(w, jac_to_aff(jac_mul_limbs(jac_from_aff(g), ac.v, 8)));
+        words_to_be(C + 48 * i, w, 12);
+        g1_compress_words(w, jac_to_aff(jac_mul_limbs(jac_from_aff(g), qc.v, 8)));
+        words_to_be(pi + 48 * i, w, 12);
+        fr_raw_to_be(z + 32 * i, fr_from_mont(zz));
+        fr_raw_to_be(y + 32 * i, fr_from_mont(yy));
+    }
+    return KZGB_OK;
+}
+
+static void fp12_from_be(Fp12& f, const u8* in) {
+    for (int t = 0; t < 12; ++t) { Fp v; fp_from_be(v, in + 48 * t); if (t & 1) f.c[t >> 1].c1 = v; else f.c[t >> 1].c0 = v; }
+}
+static void fp12_to_be(u8* out, const Fp12& f) {
+    for (int t = 0; t < 12; ++t) fp_to_be(out + 48 * t, (t & 1) ? f.c[t >> 1].c1 : f.c[t >> 1].c0);
+}
+kzgb_ret kzgb_debug_op(kzgb_ctx* c, int op, const uint8_t* in, uint8_t* out, size_t count) {
+    for (size_t i = 0; i < count; ++i) {
+        switch (op) {
+            case 1: case 3: case 4: {
+                Fp a, b;
+                fp_from_be(a, in + 96 * i); fp_from_be(b, in + 96 * i + 48);
+                fp_to_be(out + 48 * i, op == 1 ? fp_mul(a, b) : (op == 3 ? fp_add(a, b) : fp_sub(a, b)));
+                break;
+            }
+            case 2: case 5: case 6: {
+                Fp a;
+                fp_from_be(a, in + 48 * i);
+                fp_to_be(out + 48 * i, op == 2 ? fp_sqr(a) : (op == 5 ? fp_inv(a) : fp_sqrt_candidate(a)));
+                break;
+            }
+            case 7: case 8: {
+                Fr a, b;
+                fr_raw_from_be(a, in + 64 * i); fr_raw_from_be(b, in + 64 * i + 32);
+                a = fr_to_mont(a); b = fr_to_mont(b);
+                fr_raw_to_be(out + 32 * i, fr_from_mont(op == 7 ? fr_mul(a, b) : fr_add(a, b)));
+                break;
+            }
+            case 9: {
+                G1Aff p, q;
+                aff_from_be96(p, in + 192 * i); aff_from_be96(q, in + 192 * i + 96);
+                aff_to_be96(out + 96 * i, jac_to_aff(jac_add(jac_from_aff(p), jac_from_aff(q))));
+                break;
+            }
+            case 10: case 12: {
+                G1Aff p;
+                aff_from_be96(p, in + 96 * i);
+                G1Jac r = aff_is_inf(p) ? jac_inf() : (op == 10 ? jac_dbl(jac_from_aff(p)) : jac_mul_xabs(jac_mul_xabs_aff(p)));
+                aff_to_be96(out + 96 * i, jac_to_aff(r));
+                break;
+            }
+            case 11: {
+                G1Aff p;
+                aff_from_be96(p, in + 128 * i);
+                Fr k;
+                fr_raw_from_be(k, in + 128 * i + 96);
+                aff_to_be96(out + 96 * i, jac_to_aff(jac_mul_limbs(jac_from_aff(p), k.v, 8)));
+                break;
+            }
+            case 13: case 14: case 15: case 16: case 17: case 18: {
+                PairScratch S;
+                if (op == 13) { fp12_from_be(S.a, in + 1152 * i); fp12_from_be(S.b, in + 1152 * i + 576); coop_mul(S, S.f, S.a, S.b); }
+                else if (op == 14) { fp12_from_be(S.a, in + 576 * i); coop_frob1(S.f, S.a); }
+                else if (op == 15) { fp12_from_be(S.a, in + 576 * i); coop_frob2(S.f, S.a); }
+                else if (op == 16) { fp12_from_be(S.f, in + 576 * i); coop_inv(S, S.l0, S.f); coop_copy(S.f, S.l0); }
+                else if (op == 17) { fp12_from_be(S.f, in + 576 * i); coop_final_exp(S); }
+                else {
+                    G1Aff a, b;
+                    aff_from_be96(a, in + 192 * i); aff_from_be96(b, in + 192 * i + 96);
+                    G1Jac P[2] = {jac_from_aff(a), jac_from_aff(b)};
+                    coop_miller(S, c->lines, P);
+                    coop_final_exp(S);
+                }
+                fp12_to_be(out + 576 * i, S.f);
+                break;
+            }
+            case 19: {
+                u32 h[8], w[16];
+                sha256_init(h);
+                words_from_be(w, in + 64 * i, 16);
+                sha256_compress(h, w);
+                for (int k = 0; k < 14; ++k) w[k] = 0;
+                w[0] = 0x80000000u; w[14] = 0; w[15] = 512;
+                sha256_compress(h, w);
+                words_to_be(out + 32 * i, h, 8);
+                break;
+            }
+            default: return KZGB_BADARGS;
+        }
+    }
+    return KZGB_OK;
+}
+
+// entry points of kzgb200.h that the emulation does not model
+kzgb_ret verify_kzg_proof_batch_device(bool*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, kzgb_ctx*, void*) { return KZGB_ERROR; }
+kzgb_ret kzgb_shard_phase1(kzgb_ctx*, int, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, int, void*, uint8_t*, uint32_t*) { return KZGB_ERROR; }
+kzgb_ret kzgb_fs_root(uint8_t*, const uint8_t*, size_t, uint64_t) { return KZGB_ERROR; }
+kzgb_ret kzgb_shard_phase2(kzgb_ctx*, int, const uint8_t*, uint64_t, void*, uint8_t*) { return KZGB_ERROR; }
+kzgb_ret kzgb_combine_verify(kzgb_ctx*, const uint8_t*, int, bool*) { return KZGB_ERROR; }
+kzgb_ret kzgb_g1_msm_times(float*, kzgb_ctx*) { return KZGB_ERROR; }
+kzgb_ret kzgb_synth_setup(uint8_t*, size_t, uint8_t*, size_t) { return KZGB_ERROR; }
+kzgb_ret kzgb_imad_peak(kzgb_ctx*, double*, double*) { return KZGB_ERROR; }
+uint64_t kzgb_launch_count(const kzgb_ctx*) { return 0; }
+int kzgb_set_threads(kzgb_ctx*, int) { return 0; }
+}

@@ -1,0 +1,161 @@
+"""Parity checks shared by the emulation tests (CPU, -m "not gpu") and the CUDA tests (-m gpu).
+
+Every check drives the library under test and the CPU oracle through the same C ABI
+(include/kzgb200.h) on the same seeded inputs and demands byte equality (BASELINE.json:5: "bit-exact
+against the CPU oracle: the accept/reject decision, every canonical affine MSM output and every
+decompressed point").
+"""
+import random
+
+from oracle.pymodel import bls12_381 as b
+from oracle.pymodel import kzg_model as k
+from tests.helpers import (P, R, edge_fps, f12_bytes, fp_bytes, fr_bytes, negative_g1_encodings, rand_curve_point, rand_g1)
+
+
+def _same(ctx, oracle, op, data):
+    rc1, o1 = ctx.debug_op(op, data)
+    rc2, o2 = oracle.debug_op(op, data)
+    assert rc1 == 0 and rc2 == 0, (op, rc1, rc2)
+    assert o1 == o2, f"debug op {op} differs"
+
+
+def check_field_ops(ctx, oracle, n_random=200):
+    rnd = random.Random(101)
+    vals = edge_fps() + [rnd.randrange(P) for _ in range(30)]
+    pairs = [(x, y) for x in vals[:13] for y in vals[:13]] + [(rnd.randrange(P), rnd.randrange(P)) for _ in range(n_random)]
+    data = b"".join(fp_bytes(x) + fp_bytes(y) for x, y in pairs)
+    for op in ("FP_MUL", "FP_ADD", "FP_SUB"):
+        _same(ctx, oracle, op, data)
+    data = b"".join(fp_bytes(x) for x in vals)
+    for op in ("FP_SQR", "FP_INV", "FP_SQRT_CAND"):
+        _same(ctx, oracle, op, data)
+    frs = [0, 1, R - 1, R - 2, 2 ** 128 - 1, 2 ** 254, 2 ** 32 - 1] + [rnd.randrange(R) for _ in range(60)]
+    prs = [(x, y) for x in frs[:7] for y in frs[:7]] + [(rnd.randrange(R), rnd.randrange(R)) for _ in range(n_random)]
+    data = b"".join(fr_bytes(x) + fr_bytes(y) for x, y in prs)
+    for op in ("FR_MUL", "FR_ADD"):
+        _same(ctx, oracle, op, data)
+
+
+def check_g1_ops(ctx, oracle):
+    rnd = random.Random(102)
+    pts = [rand_g1(rnd) for _ in range(5)] + [None, rand_curve_point(rnd), (0, 2)]
+    pairs = [(p, q) for p in pts for q in pts] + [(pts[0], b.g1_neg(pts[0]))]
+    _same(ctx, oracle, "G1_ADD", b"".join(b.g1_affine_bytes(p) + b.g1_affine_bytes(q) for p, q in pairs))
+    data = b"".join(b.g1_affine_bytes(p) for p in pts)
+    _same(ctx, oracle, "G1_DBL", data)
+    _same(ctx, oracle, "G1_MUL_XSQ", data)
+    ks = [0, 1, 2, R - 1, 2 ** 128 - 1] + [rnd.randrange(R) for _ in range(3)]
+    _same(ctx, oracle, "G1_MUL", b"".join(b.g1_affine_bytes(pts[i % 5]) + fr_bytes(kk) for i, kk in enumerate(ks)))
+
+
+def check_decompress(ctx, oracle, n_valid=40):
+    rnd = random.Random(103)
+    cases = negative_g1_encodings(rnd)
+    valid = [b.g1_compress(rand_g1(rnd)) for _ in range(n_valid)]
+    order = [c for c, _ in cases] + valid
+    rnd.shuffle(order)
+    data = b"".join(order)
+    rc1, a1, s1 = ctx.g1_decompress_batch(data)
+    rc2, a2, s2 = oracle.g1_decompress_batch(data)
+    assert rc1 == 0 and rc2 == 0
+    assert s1 == s2, "status bytes differ"
+    assert a1 == a2, "decompressed points differ"
+    want = dict(cases)
+    for i, enc in enumerate(order):
+        if enc in want:
+            assert s1[i] == want[enc]
+    for m in (1, 2, 3):                                   # odd / tiny sizes
+        assert ctx.g1_decompress_batch(data[:48 * m]) == oracle.g1_decompress_batch(data[:48 * m])
+
+
+def check_tower_and_pairing(ctx, oracle):
+    rnd = random.Random(104)
+    a = [(rnd.randrange(P), rnd.randrange(P)) for _ in range(6)]
+    c = [(rnd.randrange(P), rnd.randrange(P)) for _ in range(6)]
+    _same(ctx, oracle, "FP12_MUL", f12_bytes(a) + f12_bytes(c))
+    sparse = [a[0], (0, 0), a[2], (a[3][0], 0), (0, 0), (0, 0)]
+    _same(ctx, oracle, "FP12_MUL", f12_bytes(c) + f12_bytes(sparse))
+    for op in ("FP12_FROB1", "FP12_FROB2", "FP12_INV", "FINAL_EXP"):
+        _same(ctx, oracle, op, f12_bytes(a))
+    A, B = rand_g1(rnd), rand_g1(rnd)
+    _same(ctx, oracle, "MILLER_FE", b.g1_affine_bytes(A) + b.g1_affine_bytes(B))
+    _same(ctx, oracle, "MILLER_FE", b.g1_affine_bytes(A) + bytes(96))
+    Bp = rand_g1(rnd)
+    Ap = b.g1_neg(b.g1_mul(k.TAU, Bp))
+    for lib in (ctx, oracle):
+        assert lib.pairing_check(b.g1_affine_bytes(Ap), b.g1_affine_bytes(Bp)) == (0, True)
+        assert lib.pairing_check(b.g1_affine_bytes(A), b.g1_affine_bytes(B)) == (0, False)
+        assert lib.pairing_check(bytes(96), bytes(96)) == (0, True)
+        assert lib.pairing_check(b.g1_affine_bytes(A), bytes(96)) == (0, False)
+
+
+def check_fs(ctx, oracle, sizes=(1, 2, 63, 1023, 1024, 1025, 2500)):
+    seed = 0x4B5A4703
+    nmax = max(sizes)
+    C, Z, Y, PI = oracle.synth_instance(seed, 0, nmax)
+    for n in sizes:
+        args = (C[:48 * n], Z[:32 * n], Y[:32 * n], PI[:48 * n], n)
+        r1 = ctx.fs_challenges(*args)
+        r2 = oracle.fs_challenges(*args)
+        assert r1 == r2, f"fs challenges differ at n={n}"
+
+
+def check_msm(ctx, oracle, sizes=((1, 255), (2, 255), (7, 255), (64, 255), (64, 128), (300, 255), (300, 128))):
+    rnd = random.Random(105)
+    base = [rand_g1(rnd) for _ in range(24)]
+    for m, nbits in sizes:
+        pts = [rnd.choice(base) if rnd.random() < 0.9 else None for _ in range(m)]
+        ks = [rnd.randrange(2 ** 128 if nbits == 128 else R) for _ in range(m)]
+        if m >= 7:
+            pts[1] = pts[0]; pts[2] = b.g1_neg(pts[0])                     # duplicate and negation share buckets
+            ks[1] = ks[0]; ks[2] = ks[0]; ks[3] = 0
+            ks[4] = (2 ** 128 - 1) if nbits == 128 else R - 1              # all-ones / maximal scalar
+            ks[5] = 1
+        pb = b"".join(b.g1_affine_bytes(p_) for p_ in pts)
+        kb = b"".join(fr_bytes(k_) for k_ in ks)
+        r1 = ctx.g1_msm(pb, kb, nbits)
+        r2 = oracle.g1_msm(pb, kb, nbits)
+        assert r1[0] == 0 and r1 == r2, f"msm differs at m={m} nbits={nbits}"
+
+
+def check_synth(ctx, oracle, n=10):
+    seed = 0x4B5A4701
+    assert ctx.synth_instance(seed, 0, n) == oracle.synth_instance(seed, 0, n)
+    assert ctx.synth_instance(seed, 5, 3) == oracle.synth_instance(seed, 5, 3)
+
+
+def check_verify(ctx, oracle, oracle_lib, sizes=(1, 2, 9, 64), seed=0x4B5A4701):
+    """Full batch verification: verdicts, artefacts, planted invalid proof, malformed inputs."""
+    import ctypes
+    for n in sizes:
+        C, Z, Y, PI = oracle.synth_instance(seed, 0, n)
+        r1 = ctx.verify_kzg_proof_batch(C, Z, Y, PI, n)
+        r2 = oracle.verify_kzg_proof_batch(C, Z, Y, PI, n)
+        assert r1 == r2 == (0, True), (n, r1, r2)
+        a1, a2 = ctx.last_artifacts(), oracle.last_artifacts()
+        for key in ("S1", "S2", "S3", "A", "B", "sum_ry", "root"):
+            assert a1[key] == a2[key], (n, key)
+        j = oracle_lib.lib.kzgb_oracle_plant_index(ctypes.c_uint64(seed), ctypes.c_uint64(n))
+        bad = bytearray(PI)
+        oracle_lib.lib.kzgb_oracle_plant_invalid((ctypes.c_uint8 * len(bad)).from_buffer(bad), ctypes.c_size_t(j))
+        bad = bytes(bad)
+        assert ctx.verify_kzg_proof_batch(C, Z, Y, bad, n) == (0, False)
+        assert oracle.verify_kzg_proof_batch(C, Z, Y, bad, n) == (0, False)
+        a1, a2 = ctx.last_artifacts(), oracle.last_artifacts()
+        assert a1["A"] == a2["A"] and a1["B"] == a2["B"]
+    C, Z, Y, PI = oracle.synth_instance(seed, 0, 4)
+    for lib in (ctx, oracle):
+        assert lib.verify_kzg_proof(C[:48], Z[:32], Y[:32], PI[:48]) == (0, True)
+        assert lib.verify_kzg_proof(C[:48], Z[:32], Y[:32], PI[48:96]) == (0, False)
+        assert lib.verify_kzg_proof_batch(b.g1_compress((0, 2)) + C[48:], Z, Y, PI, 4) == (1, False)       # off-subgroup
+        assert lib.verify_kzg_proof_batch(C, R.to_bytes(32, "big") + Z[32:], Y, PI, 4) == (1, False)       # z >= r
+        assert lib.verify_kzg_proof_batch(C, Z, Y[:96] + (2 ** 256 - 1).to_bytes(32, "big"), PI, 4) == (1, False)
+        assert lib.verify_kzg_proof_batch(C, Z, Y, PI, 0) == (1, False)
+        # infinity commitment/proof are valid encodings: C = O, pi = O verifies iff y = 0
+        inf = b.g1_compress(None)
+        assert lib.verify_kzg_proof(inf, Z[:32], bytes(32), inf) == (0, True)
+        assert lib.verify_kzg_proof(inf, Z[:32], (1).to_bytes(32, "big"), inf) == (0, False)
+    # duplicate proofs in one batch (same bucket collisions, P+P paths)
+    Cd, Zd, Yd, PId = C[:48] * 6, Z[:32] * 6, Y[:32] * 6, PI[:48] * 6
+    assert ctx.verify_kzg_proof_batch(Cd, Zd, Yd, PId, 6) == oracle.verify_kzg_proof_batch(Cd, Zd, Yd, PId, 6) == (0, True)
+    assert ctx.last_artifacts()["A"] == oracle.last_artifacts()["A"]

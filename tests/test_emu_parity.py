@@ -1,0 +1,60 @@
+"""CPU-side checks of the CUDA kernels' per-thread logic: the device headers are compiled for the host
+(-DKZGB_EMU, tests/emu) and diffed against the oracle with the same suite the GPU tests use."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from tests import parity_suite as ps
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def emu_ctx(oracle_lib):
+    subprocess.run(["make", "-s", "-C", str(ROOT / "tests" / "emu")], check=True)
+    from kzg_batch_verification_scheme_b200.api import KzgLib
+    lib = KzgLib(ROOT / "tests" / "emu" / "libkzgb_emu.so")
+    g1, g2 = oracle_lib.synth_setup(1, 2)
+    ctx = lib.context(g1, g2)
+    yield ctx
+    ctx.close()
+
+
+def test_emu_field_ops(emu_ctx, oracle_ctx):
+    ps.check_field_ops(emu_ctx, oracle_ctx)
+
+
+def test_emu_sha_single_block(emu_ctx, oracle_ctx):
+    import random
+    rnd = random.Random(1)
+    data = bytes(rnd.randrange(256) for _ in range(64 * 5))
+    assert emu_ctx.debug_op("SHA256_64", data) == oracle_ctx.debug_op("SHA256_64", data)
+
+
+def test_emu_g1_ops(emu_ctx, oracle_ctx):
+    ps.check_g1_ops(emu_ctx, oracle_ctx)
+
+
+def test_emu_decompress(emu_ctx, oracle_ctx):
+    ps.check_decompress(emu_ctx, oracle_ctx, n_valid=6)
+
+
+def test_emu_tower_and_pairing(emu_ctx, oracle_ctx):
+    ps.check_tower_and_pairing(emu_ctx, oracle_ctx)
+
+
+def test_emu_fs(emu_ctx, oracle_ctx):
+    ps.check_fs(emu_ctx, oracle_ctx, sizes=(1, 2, 63, 1024, 1025))
+
+
+def test_emu_msm(emu_ctx, oracle_ctx):
+    ps.check_msm(emu_ctx, oracle_ctx, sizes=((1, 255), (2, 255), (7, 255), (64, 255), (64, 128), (300, 128)))
+
+
+def test_emu_synth(emu_ctx, oracle_ctx):
+    ps.check_synth(emu_ctx, oracle_ctx, n=4)
+
+
+def test_emu_verify(emu_ctx, oracle_ctx, oracle_lib):
+    ps.check_verify(emu_ctx, oracle_ctx, oracle_lib, sizes=(1, 2, 9))

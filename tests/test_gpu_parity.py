@@ -1,0 +1,153 @@
+"""CUDA library vs CPU oracle through the C ABI (include/kzgb200.h) -- the parity tests proper.
+Run on a B200 with `pytest -m gpu`.  Bit-exact or fail (BASELINE.json:5)."""
+import ctypes
+import random
+
+import pytest
+
+from oracle.pymodel import bls12_381 as b
+from tests import parity_suite as ps
+from tests.helpers import rand_g1
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_lib_is_the_cuda_build(gpu_lib):
+    assert "cuda" in gpu_lib.version()
+
+
+def test_gpu_field_ops(gpu_ctx, oracle_ctx):
+    ps.check_field_ops(gpu_ctx, oracle_ctx, n_random=2000)
+
+
+def test_gpu_g1_ops(gpu_ctx, oracle_ctx):
+    ps.check_g1_ops(gpu_ctx, oracle_ctx)
+
+
+def test_gpu_decompress(gpu_ctx, oracle_ctx):
+    ps.check_decompress(gpu_ctx, oracle_ctx, n_valid=300)
+
+
+def test_gpu_tower_and_pairing(gpu_ctx, oracle_ctx):
+    ps.check_tower_and_pairing(gpu_ctx, oracle_ctx)
+
+
+def test_gpu_fs(gpu_ctx, oracle_ctx):
+    ps.check_fs(gpu_ctx, oracle_ctx)
+
+
+def test_gpu_msm(gpu_ctx, oracle_ctx):
+    ps.check_msm(gpu_ctx, oracle_ctx)
+
+
+def test_gpu_synth_matches_oracle_generator(gpu_ctx, oracle_ctx):
+    ps.check_synth(gpu_ctx, oracle_ctx, n=300)
+
+
+def test_gpu_verify_small(gpu_ctx, oracle_ctx, oracle_lib):
+    ps.check_verify(gpu_ctx, oracle_ctx, oracle_lib, sizes=(1, 2, 9, 64, 1025))
+
+
+def test_gpu_msm_4096_vs_oracle(gpu_ctx, oracle_ctx):
+    """MSM over 4096 distinct subgroup points (from the generator), 255- and 128-bit scalars."""
+    C, Z, Y, PI = oracle_ctx.synth_instance(0x4B5A4701, 0, 2048)
+    rc, aff, st = oracle_ctx.g1_decompress_batch(C + PI)
+    assert rc == 0 and not any(st)
+    rnd = random.Random(77)
+    for nbits in (255, 128):
+        ks = b"".join(rnd.randrange(2 ** 128 if nbits == 128 else b.R).to_bytes(32, "big") for _ in range(4096))
+        r1 = gpu_ctx.g1_msm(aff, ks, nbits)
+        r2 = oracle_ctx.g1_msm(aff, ks, nbits)
+        assert r1[0] == 0 and r1 == r2
+
+
+def test_gpu_config_n4096(gpu_ctx, oracle_ctx):
+    """BASELINE.json config[1]: n=4096 compressed inputs incl. decompression + subgroup checks."""
+    n, seed = 4096, 0x4B5A4701
+    C, Z, Y, PI = oracle_ctx.synth_instance(seed, 0, n)
+    assert gpu_ctx.synth_instance(seed, 0, n) == (C, Z, Y, PI)
+    assert gpu_ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    assert oracle_ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    a1, a2 = gpu_ctx.last_artifacts(), oracle_ctx.last_artifacts()
+    for key in ("S1", "S2", "S3", "A", "B", "sum_ry", "root"):
+        assert a1[key] == a2[key], key
+    rc1, aff1, st1 = gpu_ctx.g1_decompress_batch(C + PI)
+    rc2, aff2, st2 = oracle_ctx.g1_decompress_batch(C + PI)
+    assert (rc1, aff1, st1) == (rc2, aff2, st2)
+
+
+def test_gpu_config_n65536_planted_invalid(gpu_lib, oracle_lib):
+    """BASELINE.json config[2]: n=2^16 with one planted invalid proof: must reject; valid batch accepts.
+    Verdicts are cross-checked pairing-free with the known test tau (A + tau*B == O)."""
+    n, seed = 1 << 16, 0x4B5A4702
+    ctx = gpu_lib.context(n_max=n)
+    octx = oracle_lib.context()
+    C, Z, Y, PI = ctx.synth_instance(seed, 0, n)
+    assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    art = ctx.last_artifacts()
+    assert oracle_lib.lib.kzgb_oracle_tau_shortcut(art["A"], art["B"]) == 1
+    assert octx.pairing_check(art["A"], art["B"]) == (0, True)
+    # spot parity of the oracle generator on a slice of the same stream
+    assert octx.synth_instance(seed, 12345, 64) == tuple(x[s * 12345:s * (12345 + 64)] for x, s in ((C, 48), (Z, 32), (Y, 32), (PI, 48)))
+    j = oracle_lib.lib.kzgb_oracle_plant_index(ctypes.c_uint64(seed), ctypes.c_uint64(n))
+    bad = bytearray(PI)
+    assert oracle_lib.lib.kzgb_oracle_plant_invalid((ctypes.c_uint8 * len(bad)).from_buffer(bad), ctypes.c_size_t(j)) == 0
+    assert ctx.verify_kzg_proof_batch(C, Z, Y, bytes(bad), n) == (0, False)
+    art = ctx.last_artifacts()
+    assert oracle_lib.lib.kzgb_oracle_tau_shortcut(art["A"], art["B"]) == 0
+    # an off-subgroup point anywhere in the batch is BADARGS
+    bad2 = bytearray(C)
+    bad2[48 * 777:48 * 778] = b.g1_compress((0, 2))
+    assert ctx.verify_kzg_proof_batch(bytes(bad2), Z, Y, PI, n) == (1, False)
+    assert ctx.last_artifacts()["n_bad_points"] == 1
+    ctx.close()
+    octx.close()
+
+
+def test_gpu_shards_equal_single_and_cross_library_combine(gpu_lib, oracle_lib):
+    """Shard-count invariance on ONE device (G virtual shards run sequentially) and the
+    cross-library check: partials produced by the CUDA library are accepted by the oracle's combine."""
+    n, seed = 5 * 1024 + 100, 0x4B5A4703
+    ctx = gpu_lib.context(devices=[0, 0, 0], n_max=n)
+    octx = oracle_lib.context()
+    C, Z, Y, PI = ctx.synth_instance(seed, 0, n)
+    assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)        # 3 slots on device 0
+    ref_root = ctx.last_artifacts()["root"]
+    for bounds in ([0, n], [0, 2048, n], [0, 1024, 4096, n]):
+        digs = b""
+        for s in range(len(bounds) - 1):
+            lo, hi = bounds[s], bounds[s + 1]
+            rc, d, _ = ctx.shard_phase1(s, C[48 * lo:48 * hi], Z[32 * lo:32 * hi], Y[32 * lo:32 * hi], PI[48 * lo:48 * hi], hi - lo)
+            assert rc == 0
+            digs += d
+        root = ctx.fs_root(digs, n)
+        assert root == ref_root == octx.fs_root(digs, n)
+        parts = b""
+        for s in range(len(bounds) - 1):
+            rc, p = ctx.shard_phase2(s, root, bounds[s])
+            assert rc == 0
+            parts += p
+        assert ctx.combine_verify(parts) == (0, True)
+        assert octx.combine_verify(parts) == (0, True)
+        a1, a2 = ctx.last_artifacts(), octx.last_artifacts()
+        assert a1["A"] == a2["A"] and a1["B"] == a2["B"] and a1["sum_ry"] == a2["sum_ry"]
+    ctx.close()
+    octx.close()
+
+
+def test_gpu_device_resident_entry_point(gpu_lib):
+    import torch
+    n, seed = 4096, 0x4B5A4704
+    ctx = gpu_lib.context(n_max=n)
+    bufs = [torch.empty(s * n, dtype=torch.uint8, device="cuda") for s in (48, 32, 32, 48)]
+    ctx.synth_instance(seed, 0, n, device_ptrs=tuple(t.data_ptr() for t in bufs))
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+    assert ctx.verify_kzg_proof_batch_device(*[t.data_ptr() for t in bufs], n, stream) == (0, True)
+    host = [bytes(t.cpu().numpy().tobytes()) for t in bufs]
+    assert ctx.verify_kzg_proof_batch(*host, n) == (0, True)
+    bufs[3][48 * 5 + 47] ^= 1           # corrupt one proof byte on the device: not a valid encoding any more (w.h.p.) or wrong proof
+    rc, ok = ctx.verify_kzg_proof_batch_device(*[t.data_ptr() for t in bufs], n, stream)
+    assert not ok
+    assert ctx.launch_count() > 0
+    ctx.close()
