@@ -164,7 +164,22 @@ KZ_HD Fr fr_zero() { Fr r; KZ_UNROLL for (int i = 0; i < 8; ++i) r.v[i] = 0; ret
 KZ_HD Fr fr_const(const u32* c) { Fr r; KZ_UNROLL for (int i = 0; i < 8; ++i) r.v[i] = c[i]; return r; }
 KZ_HD Fr fr_neg(const Fr& a) { return fr_sub(fr_zero(), a); }
 KZ_HD bool fr_is_zero(const Fr& a) { u32 o = 0; KZ_UNROLL for (int i = 0; i < 8; ++i) o |= a.v[i]; return o == 0; }
-KZ_HD Fr fr_to_mont(const Fr& raw) { return fr_mul(raw, fr_const(FR_R2)); }      // raw may be any value < 2^256
+KZ_HD Fr fr_to_mont(const Fr& raw) { return fr_mul(raw, fr_const(FR_R2)); }      // raw MUST be < r (the PTX product keeps no top carry)
+// any 256-bit value -> [0, r): 2^256 < 3r, so two conditional subtractions suffice
+KZ_HD Fr fr_reduce_raw(const Fr& a) {
+    Fr r = a;
+#if defined(KZGB_EMU)
+    for (int rep = 0; rep < 2; ++rep) {
+        u32 t[8]; u64 bw = 0;
+        for (int j = 0; j < 8; ++j) { u64 v = (u64)r.v[j] - FR_P[j] - bw; t[j] = (u32)v; bw = (v >> 32) & 1; }
+        if (!bw) for (int j = 0; j < 8; ++j) r.v[j] = t[j];
+    }
+#else
+    fr_reduce_ptx(r.v);
+    fr_reduce_ptx(r.v);
+#endif
+    return r;
+}
 KZ_HD Fr fr_from_mont(const Fr& a) { Fr o = fr_zero(); o.v[0] = 1; return fr_mul(a, o); }
 KZ_HD bool limbs_ge8(const u32* a, const u32* b) {
     u32 bw = 0;

@@ -43,6 +43,7 @@ struct DeviceSlot {
     size_t max_bucketsR = 0, max_bucketsZ = 0, max_segs = 0;
     void* cub_temp = nullptr;
     size_t cub_temp_bytes = 0;
+    ChunkRecs recs = {nullptr, nullptr, nullptr, nullptr, nullptr};
     G1Jac* sums = nullptr;             // [0] S1 [1] S2' [2] S3 [3] A [4] B
     uint8_t* partial_dev = nullptr;    // 320
     uint8_t* partials_in = nullptr;    // 320 * 64
@@ -110,7 +111,16 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     if (slot_alloc_sort(s.sortZ, capZ, s.max_bucketsZ + 512)) return KZGB_ERROR;
     CK(dmalloc(s.bucketsA, s.max_bucketsR + 512)); CK(dmalloc(s.bucketsB, s.max_bucketsR + 512));
     CK(dmalloc(s.bucketsC, s.max_bucketsZ + 512));
-    CK(dmalloc(s.segsums, s.max_segs + 512)); CK(dmalloc(s.winsums, KZ_MSM_MAX_WINDOWS));
+    CK(dmalloc(s.segsums, 3 * (s.max_segs + 512))); CK(dmalloc(s.winsums, 3 * KZ_MSM_MAX_WINDOWS));
+    {   // chunk records for the balanced accumulation: worst case over the chunk-length schedule
+        auto mn = [](size_t a, size_t b) { return a < b ? a : b; };
+        size_t tmax = capZ / msm_chunk_len(capZ) + 1;
+        size_t cands[3] = {mn(capZ, (size_t)1 << 21) / 16 + 1, mn(capZ, (size_t)1 << 20) / 8 + 1, mn(capZ, (size_t)1 << 18) / 4 + 1};
+        for (size_t t : cands) if (t > tmax) tmax = t;
+        tmax += 64;
+        CK(dmalloc(s.recs.head, tmax)); CK(dmalloc(s.recs.tail, tmax));
+        CK(dmalloc(s.recs.head_key, tmax)); CK(dmalloc(s.recs.tail_key, tmax)); CK(dmalloc(s.recs.head_flags, tmax));
+    }
     s.cub_temp_bytes = msm_cub_temp_bytes(capZ) + 256;
     CK(cudaMalloc(&s.cub_temp, s.cub_temp_bytes));
     CK(dmalloc(s.sums, 5)); CK(dmalloc(s.partial_dev, KZGB_PARTIAL_BYTES)); CK(dmalloc(s.partials_in, KZGB_PARTIAL_BYTES * 64));
@@ -139,7 +149,8 @@ void slot_free(DeviceSlot& s) {
                    s.partials, s.sum_ry, s.sortR.keys, s.sortR.vals, s.sortR.keys_alt, s.sortR.vals_alt, s.sortR.bucket_start,
                    s.sortZ.keys, s.sortZ.vals, s.sortZ.keys_alt, s.sortZ.vals_alt, s.sortZ.bucket_start, s.bucketsA,
                    s.bucketsB, s.bucketsC, s.segsums, s.winsums, s.cub_temp, s.sums, s.partial_dev, s.partials_in,
-                   s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb};
+                   s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb, s.recs.head, s.recs.tail,
+                   s.recs.head_key, s.recs.tail_key, s.recs.head_flags};
     for (void* p : dev) if (p) cudaFree(p);
     if (s.h_digests) cudaFreeHost(s.h_digests);
     if (s.h_small) cudaFreeHost(s.h_small);
@@ -152,7 +163,7 @@ MsmWorkspace make_ws(DeviceSlot& s, SortBuf& b, G1Xyzz* buckets) {
     MsmWorkspace ws;
     ws.keys = b.keys; ws.vals = b.vals; ws.keys_alt = b.keys_alt; ws.vals_alt = b.vals_alt;
     ws.capacity = b.capacity; ws.bucket_start = b.bucket_start; ws.buckets = buckets; ws.segsums = s.segsums;
-    ws.winsums = s.winsums; ws.cub_temp = s.cub_temp; ws.cub_temp_bytes = s.cub_temp_bytes;
+    ws.winsums = s.winsums; ws.recs = s.recs; ws.cub_temp = s.cub_temp; ws.cub_temp_bytes = s.cub_temp_bytes;
     ws.max_buckets = 0; ws.max_segs = s.max_segs;
     return ws;
 }
@@ -230,9 +241,12 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     msm_accumulate_stage(st, s.planR, s.pts + 2 * n, n, wr2);        // S3 over pi_i
     msm_accumulate_stage(st, s.planZ, s.pts + 2 * n, n + 1, wz);     // S2' over pi_i and G
     CK(cudaEventRecord(s.ev[6], st));
-    msm_reduce_stage(st, s.planR, wr, s.sums + 0);
-    msm_reduce_stage(st, s.planR, wr2, s.sums + 2);
-    msm_reduce_stage(st, s.planZ, wz, s.sums + 1);
+    wr2.segsums = s.segsums + (s.max_segs + 512); wr2.winsums = s.winsums + KZ_MSM_MAX_WINDOWS;
+    wz.segsums = s.segsums + 2 * (s.max_segs + 512); wz.winsums = s.winsums + 2 * KZ_MSM_MAX_WINDOWS;
+    const MsmPlan* plans[3] = {&s.planR, &s.planR, &s.planZ};
+    MsmWorkspace* wss[3] = {&wr, &wr2, &wz};
+    G1Jac* outs[3] = {s.sums + 0, s.sums + 2, s.sums + 1};
+    msm_reduce_stage_multi(st, plans, wss, outs, 3);
     launch_make_partial(st, s.sums + 0, s.sums + 1, s.sums + 2, s.sum_ry, s.partial_dev);
     CK(cudaMemcpyAsync(s.h_partial, s.partial_dev, KZGB_PARTIAL_BYTES, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_small, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

@@ -30,12 +30,18 @@ __global__ void k_bucket_bounds(const u32* __restrict__ keys, size_t N, u32 tota
     if (i == N - 1) { for (u32 b = k + 1; b <= total_buckets + 1; ++b) start[b] = (u32)N; }
 }
 
-__global__ void __launch_bounds__(128) k_msm_accumulate(const Fp* __restrict__ pts, const u32* __restrict__ vals,
-                                                        const u32* __restrict__ start, u32 total_buckets,
-                                                        G1Xyzz* __restrict__ buckets) {
-    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= total_buckets) return;
-    buckets[b] = msm_bucket_body(pts, vals, start[b], start[b + 1]);
+__global__ void __launch_bounds__(128) k_msm_chunk_pass1(const Fp* __restrict__ pts, const u32* __restrict__ keys,
+                                                         const u32* __restrict__ vals, const u32* __restrict__ start,
+                                                         u32 total_buckets, u32 L, u32 T, G1Xyzz* __restrict__ buckets,
+                                                         ChunkRecs R) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    msm_chunk_pass1(pts, keys, vals, start[total_buckets], L, t, buckets, R);
+}
+__global__ void __launch_bounds__(128) k_msm_chunk_pass2(u32 T, G1Xyzz* __restrict__ buckets, ChunkRecs R) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    msm_chunk_pass2(T, t, buckets, R);
 }
 
 __global__ void __launch_bounds__(128) k_msm_segments(const G1Xyzz* __restrict__ buckets, G1Xyzz* __restrict__ segsums,
@@ -65,9 +71,16 @@ __global__ void __launch_bounds__(KZ_WIN_THREADS) k_msm_window_sum(const G1Xyzz*
     }
     if (threadIdx.x == 0) winsums[w] = red[0];
 }
-__global__ void k_msm_combine(const G1Xyzz* __restrict__ winsums, int W, int c, G1Jac* out) {
-    if (threadIdx.x || blockIdx.x) return;
-    *out = xyzz_to_jac(msm_combine_body(winsums, W, c));
+// Horner combine; one block per job so the three sums of a batch run their serial chains concurrently
+struct CombineJobs {
+    const G1Xyzz* winsums[3];
+    G1Jac* out[3];
+    int W[3], c[3];
+};
+__global__ void k_msm_combine(CombineJobs jobs) {
+    if (threadIdx.x) return;
+    int j = blockIdx.x;
+    *jobs.out[j] = xyzz_to_jac(msm_combine_body(jobs.winsums[j], jobs.W[j], jobs.c[j]));
 }
 
 size_t msm_cub_temp_bytes(size_t entries) {
@@ -91,17 +104,35 @@ void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars
     k_bucket_bounds<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(ws.keys, N, plan.total_buckets, ws.bucket_start);
     KZ_COUNT_LAUNCH();
 }
+u32 msm_chunk_len(size_t N) { return N >= (1u << 21) ? 32u : N >= (1u << 20) ? 16u : N >= (1u << 18) ? 8u : 4u; }
+
 void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, size_t m, MsmWorkspace& ws) {
-    (void)m;
-    k_msm_accumulate<<<(plan.total_buckets + 127) / 128, 128, 0, s>>>(pts, ws.vals, ws.bucket_start, plan.total_buckets,
-                                                                      ws.buckets);
+    size_t N = m * (size_t)plan.W;
+    u32 L = msm_chunk_len(N);
+    u32 T = (u32)((N + L - 1) / L);
+    cudaMemsetAsync(ws.buckets, 0, sizeof(G1Xyzz) * (size_t)plan.total_buckets, s);      // empty buckets = infinity
+    k_msm_chunk_pass1<<<(T + 127) / 128, 128, 0, s>>>(pts, ws.keys, ws.vals, ws.bucket_start, plan.total_buckets, L, T,
+                                                      ws.buckets, ws.recs);
+    KZ_COUNT_LAUNCH();
+    k_msm_chunk_pass2<<<(T + 127) / 128, 128, 0, s>>>(T, ws.buckets, ws.recs);
+    KZ_COUNT_LAUNCH();
+}
+void msm_reduce_stage_multi(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs) {
+    CombineJobs cj;
+    for (int j = 0; j < njobs; ++j) {
+        const MsmPlan& plan = *plans[j];
+        MsmWorkspace& ws = *wss[j];
+        k_msm_segments<<<(plan.total_segs + 127) / 128, 128, 0, s>>>(ws.buckets, ws.segsums, plan);
+        KZ_COUNT_LAUNCH();
+        k_msm_window_sum<<<plan.W, KZ_WIN_THREADS, 0, s>>>(ws.segsums, ws.winsums, plan);
+        KZ_COUNT_LAUNCH();
+        cj.winsums[j] = ws.winsums; cj.out[j] = outs[j]; cj.W[j] = plan.W; cj.c[j] = plan.c;
+    }
+    k_msm_combine<<<njobs, 32, 0, s>>>(cj);
     KZ_COUNT_LAUNCH();
 }
 void msm_reduce_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, G1Jac* out) {
-    k_msm_segments<<<(plan.total_segs + 127) / 128, 128, 0, s>>>(ws.buckets, ws.segsums, plan);
-    KZ_COUNT_LAUNCH();
-    k_msm_window_sum<<<plan.W, KZ_WIN_THREADS, 0, s>>>(ws.segsums, ws.winsums, plan);
-    KZ_COUNT_LAUNCH();
-    k_msm_combine<<<1, 32, 0, s>>>(ws.winsums, plan.W, plan.c, out);
-    KZ_COUNT_LAUNCH();
+    const MsmPlan* p = &plan;
+    MsmWorkspace* w = &ws;
+    msm_reduce_stage_multi(s, &p, &w, &out, 1);
 }

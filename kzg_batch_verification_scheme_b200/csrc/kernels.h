@@ -45,16 +45,20 @@ struct MsmWorkspace {
     G1Xyzz* buckets;                               // max total buckets
     G1Xyzz* segsums;                               // max total segs
     G1Xyzz* winsums;                               // KZ_MSM_MAX_WINDOWS
+    ChunkRecs recs;                                // partial records, capacity/4 + 1 chunks
     void* cub_temp;
     size_t cub_temp_bytes;
     size_t max_buckets, max_segs;
 };
 size_t msm_cub_temp_bytes(size_t entries);
+uint32_t msm_chunk_len(size_t N);
 // digits + sort + bucket boundaries for `m` scalars of `nl` limbs each
 void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars, int nl, size_t m, MsmWorkspace& ws);
 // accumulate + reduce + combine over points `pts` (2 Fp each, m points) using the sorted entries in ws
 void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, size_t m, MsmWorkspace& ws);
 void msm_reduce_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, G1Jac* out);
+// up to 3 jobs; each job needs its own buckets / segsums / winsums; the serial Horner chains run concurrently
+void msm_reduce_stage_multi(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs);
 
 // ---- k_pairing.cu
 // setup: decompress the two G2 points, subgroup-check, precompute lines.  status[0] = 1 on success.

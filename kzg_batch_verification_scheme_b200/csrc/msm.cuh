@@ -78,6 +78,78 @@ KZ_HD G1Xyzz msm_bucket_body(const Fp* pts, const u32* vals, u32 lo, u32 hi) {
     return acc;
 }
 
+// ---- balanced accumulation: every thread takes a fixed run of L sorted entries regardless of bucket
+// boundaries, so a skewed bucket (e.g. the narrow top window) is spread over many threads.
+//   pass 1: buckets lying entirely inside a chunk are written directly; the first / last run of a chunk
+//           that continues into a neighbour chunk is parked as a partial record (head / tail).
+//   pass 2: the chunk holding the first entry of such a bucket adds up the following head records.
+#define KZ_KEY_NONE 0xFFFFFFFFu
+struct ChunkRecs {
+    G1Xyzz* head;        // [T] partial sum of the first run of chunk t
+    G1Xyzz* tail;        // [T] partial sum of the last run of chunk t (when different from the first)
+    u32* head_key;       // [T] bucket key or KZ_KEY_NONE
+    u32* tail_key;       // [T]
+    u32* head_flags;     // [T] bit0: run starts its bucket, bit1: run ends its bucket, bit2: run covers the whole chunk
+};
+KZ_HD void msm_chunk_pass1(const Fp* pts, const u32* keys, const u32* vals, u32 n_valid, u32 L, u32 t,
+                           G1Xyzz* buckets, const ChunkRecs& R) {
+    R.head_key[t] = KZ_KEY_NONE;
+    R.tail_key[t] = KZ_KEY_NONE;
+    u32 lo = t * L;
+    if (lo >= n_valid) return;
+    u32 hi = lo + L < n_valid ? lo + L : n_valid;
+    u32 prev_key = lo ? keys[lo - 1] : KZ_KEY_NONE;
+    u32 next_key = hi < n_valid ? keys[hi] : KZ_KEY_NONE;
+    u32 cur = keys[lo];
+    bool is_head = true;
+    G1Xyzz acc = xyzz_inf();
+    for (u32 j = lo; j <= hi; ++j) {
+        u32 k = j < hi ? keys[j] : KZ_KEY_NONE;
+        if (k != cur) {                                        // flush the finished run
+            bool is_tail = j == hi;
+            bool starts = is_head ? prev_key != cur : true;
+            bool ends = is_tail ? next_key != cur : true;
+            if (starts && ends) buckets[cur] = acc;
+            else if (is_head) { R.head[t] = acc; R.head_key[t] = cur; R.head_flags[t] = (starts ? 1u : 0u) | (ends ? 2u : 0u) | (is_tail ? 4u : 0u); }
+            else { R.tail[t] = acc; R.tail_key[t] = cur; }     // a tail that is not the head starts here and continues
+            if (j == hi) break;
+            cur = k;
+            is_head = false;
+            acc = xyzz_inf();
+        }
+        u32 v = vals[j];
+        G1Aff p = load_point(pts, v & 0x7FFFFFFFu);
+        if (aff_is_inf(p)) continue;
+        if (v >> 31) p.y = fp_neg(p.y);
+        acc = xyzz_madd(acc, p);
+    }
+}
+KZ_HD void msm_chunk_pass2(u32 T, u32 t, G1Xyzz* buckets, const ChunkRecs& R) {
+    // owner of a spanning bucket = the chunk where it starts: either its tail run, or a head run that
+    // starts the bucket and covers the whole chunk
+    for (int which = 0; which < 2; ++which) {
+        u32 key;
+        G1Xyzz sum;
+        if (which == 0) {
+            key = R.tail_key[t];
+            if (key == KZ_KEY_NONE) continue;
+            sum = R.tail[t];
+        } else {
+            key = R.head_key[t];
+            if (key == KZ_KEY_NONE) continue;
+            u32 f = R.head_flags[t];
+            if (!(f & 1u) || (f & 2u)) continue;              // does not start here, or already complete
+            sum = R.head[t];
+        }
+        for (u32 u = t + 1; u < T; ++u) {
+            if (R.head_key[u] != key) break;
+            sum = xyzz_add(sum, R.head[u]);
+            if (R.head_flags[u] & 2u) break;
+        }
+        buckets[key] = sum;
+    }
+}
+
 // [k]P by double-and-add for a small k (< 2^17)
 KZ_COLD G1Xyzz xyzz_mul_small(const G1Xyzz& p, u32 k) {
     G1Xyzz r = xyzz_inf();

@@ -116,6 +116,6 @@ KZ_HD Fr prng_fr(u64 seed, u64 stream, u64 idx) {
     prng_block_words(lo, seed, stream, 2 * idx + 1);
     Fr a, b;
     KZ_UNROLL for (int i = 0; i < 8; ++i) { a.v[i] = hi[7 - i]; b.v[i] = lo[7 - i]; }
-    // a*2^256 + b: to_mont accepts any raw value < 2^256
-    return fr_add(fr_mul(fr_to_mont(a), fr_const(FR_2_256)), fr_to_mont(b));
+    // a*2^256 + b with both halves first reduced below r
+    return fr_add(fr_mul(fr_to_mont(fr_reduce_raw(a)), fr_const(FR_2_256)), fr_to_mont(fr_reduce_raw(b)));
 }

@@ -4,6 +4,8 @@
 // indices) so the no-GPU CI can exercise the SAME decompression / subgroup / SHA / MSM / pairing logic
 // that runs on the B200 and diff it against the oracle.  Nothing in the product library links this.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/kzgb200.h"
@@ -45,7 +47,23 @@ static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nb
     std::vector<u32> start(plan.total_buckets + 2);
     for (u32 b = 0; b <= plan.total_buckets + 1; ++b) start[b] = (u32)(std::lower_bound(sk.begin(), sk.end(), b) - sk.begin());
     std::vector<G1Xyzz> buckets(plan.total_buckets), segs(plan.total_segs), wins(plan.W);
-    for (u32 b = 0; b < plan.total_buckets; ++b) buckets[b] = msm_bucket_body(pts, sv.data(), start[b], start[b + 1]);
+    // balanced two-pass accumulation with a short chunk so that buckets straddle many chunks
+    {
+        u32 L = 3, n_valid = start[plan.total_buckets], T = (u32)((N + L - 1) / L);
+        for (auto& bk : buckets) bk = xyzz_inf();
+        std::vector<G1Xyzz> head(T + 1), tail(T + 1);
+        std::vector<u32> hk(T + 1), tk(T + 1), hf(T + 1);
+        ChunkRecs R{head.data(), tail.data(), hk.data(), tk.data(), hf.data()};
+        for (u32 t = 0; t < T; ++t) msm_chunk_pass1(pts, sk.data(), sv.data(), n_valid, L, t, buckets.data(), R);
+        for (u32 t = 0; t < T; ++t) msm_chunk_pass2(T, t, buckets.data(), R);
+        // cross-check against the plain one-thread-per-bucket body
+        for (u32 b = 0; b < plan.total_buckets; ++b) {
+            G1Xyzz ref = msm_bucket_body(pts, sv.data(), start[b], start[b + 1]);
+            G1Jac a = xyzz_to_jac(ref), c2 = xyzz_to_jac(buckets[b]);
+            bool same = jac_is_inf(a) ? jac_is_inf(c2) : (!jac_is_inf(c2) && aff_is_inf(jac_to_aff(jac_add(a, jac_neg(c2)))));
+            if (!same) { fprintf(stderr, "emu: bucket %u differs\n", b); abort(); }
+        }
+    }
     for (u32 s = 0; s < plan.total_segs; ++s) {
         int w = 0;
         while (s >= plan.seg_off[w + 1]) ++w;
