@@ -213,7 +213,7 @@ def main():
             ok = step(ptrs, on_device)
             assert ok, "batch must verify"
             if not multi or rank == 0 or True:
-                for k, v in ctx.last_artifacts()["stage_ms"].items():
+                for k, v in ctx.last_stage_ms().items():
                     stage_acc[k] = stage_acc.get(k, 0.0) + v
         e1.record()
         barrier()
@@ -290,7 +290,7 @@ def main():
                 for _ in range(4):
                     rc, ok = ctx.verify_kzg_proof_batch_device(*dptr, n2, stream)
                     assert (rc, ok) == (0, True)
-                    t = ctx.last_artifacts()["stage_ms"]["total"]
+                    t = ctx.last_stage_ms()["total"]
                     best = t if best is None else min(best, t)
                 extras["n65536_proofs_per_s"] = n2 / (best * 1e-3)
                 extras["n65536_ms"] = best

@@ -130,8 +130,14 @@ enum {
 kzgb_ret kzgb_debug_op(kzgb_ctx *ctx, int op, const uint8_t *in, uint8_t *out, size_t count);
 
 /* ---- measurement helpers (product library only; oracle returns KZGB_ERROR) */
-/* IMAD.WIDE.U32 issue-rate microbenchmark: thread-level multiply-adds per second over all SMs */
+/* integer multiply-add issue-rate microbenchmarks, thread-level operations per second over all SMs:
+ * kzgb_imad_peak   carry-chained 32x32->64 multiply-adds (SASS IMAD.WIDE.U32.X), the instruction the
+ *                  Montgomery products consist of -- the roofline denominator;
+ * kzgb_imad32_peak plain 32-bit IMAD (the pipe's nominal issue rate, for context). */
 kzgb_ret kzgb_imad_peak(kzgb_ctx *ctx, double *imad_per_sec_out, double *ms_out);
+kzgb_ret kzgb_imad32_peak(kzgb_ctx *ctx, double *imad_per_sec_out, double *ms_out);
+/* per-stage device ms of the last verify call without computing the artefacts (see kzgb_artifacts.stage_ms) */
+kzgb_ret kzgb_last_stage_ms(kzgb_ctx *ctx, float ms_out[KZGB_N_STAGES]);
 /* number of kernel launches issued by this library since ctx creation (for bench gpu_launches) */
 uint64_t kzgb_launch_count(const kzgb_ctx *ctx);
 /* threads the oracle uses (oracle library only; product returns 0) */

@@ -85,6 +85,8 @@ class KzgLib:
             "kzgb_synth_setup": [vp, sz, vp, sz],
             "kzgb_debug_op": [vp, i32, vp, vp, sz],
             "kzgb_imad_peak": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+            "kzgb_imad32_peak": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+            "kzgb_last_stage_ms": [vp, C.POINTER(C.c_float * N_STAGES)],
         }
         for name, args in sig.items():
             f = getattr(lib, name)
@@ -98,7 +100,7 @@ class KzgLib:
                "verify_kzg_proof_batch_device", "kzgb_shard_phase1", "kzgb_fs_root", "kzgb_shard_phase2",
                "kzgb_combine_verify", "kzgb_g1_decompress_batch", "kzgb_fs_challenges", "kzgb_g1_msm",
                "kzgb_g1_msm_times", "kzgb_pairing_check", "kzgb_last_artifacts", "kzgb_synth_instance",
-               "kzgb_synth_setup", "kzgb_debug_op", "kzgb_imad_peak", "kzgb_launch_count", "kzgb_set_threads",
+               "kzgb_synth_setup", "kzgb_debug_op", "kzgb_imad_peak", "kzgb_imad32_peak", "kzgb_last_stage_ms", "kzgb_launch_count", "kzgb_set_threads",
                "kzgb_version"]
 
     def version(self) -> str:
@@ -245,12 +247,21 @@ class Context:
         rc = self.lib.kzgb_debug_op(self.h, op, _ptr(data), _ptr(out), cnt)
         return rc, out.raw
 
-    def imad_peak(self):
+    def imad_peak(self, wide=True):
+        """(ops/s, ms) of the multiply-add microbenchmark: wide=True -> IMAD.WIDE.U32.X carry chains."""
         v, ms = C.c_double(0), C.c_double(0)
-        rc = self.lib.kzgb_imad_peak(self.h, C.byref(v), C.byref(ms))
+        fn = self.lib.kzgb_imad_peak if wide else self.lib.kzgb_imad32_peak
+        rc = fn(self.h, C.byref(v), C.byref(ms))
         if rc:
             raise KzgError(f"kzgb_imad_peak -> {rc}")
         return v.value, ms.value
+
+    def last_stage_ms(self) -> dict:
+        ms = (C.c_float * N_STAGES)()
+        rc = self.lib.kzgb_last_stage_ms(self.h, C.byref(ms))
+        if rc:
+            raise KzgError(f"kzgb_last_stage_ms -> {rc}")
+        return {STAGE_NAMES[i]: ms[i] for i in range(N_STAGES)}
 
     def launch_count(self) -> int:
         return int(self.lib.kzgb_launch_count(self.h))

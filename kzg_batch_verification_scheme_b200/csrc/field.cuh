@@ -56,7 +56,16 @@ KZ_HD Fp fp_mul(const Fp& a, const Fp& b) {
 #endif
     return r;
 }
-KZ_HD Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
+KZ_HD Fp fp_sqr(const Fp& a) {
+#if defined(KZGB_EMU)
+    return fp_mul(a, a);
+#else
+    Fp r;
+    fp_mont_sqr_ptx(r.v, a.v);          // dedicated squaring: 234 instead of 300 wide multiply-adds
+    fp_reduce_ptx(r.v);
+    return r;
+#endif
+}
 KZ_HD Fp fp_add(const Fp& a, const Fp& b) {
     Fp r;
 #if defined(KZGB_EMU)

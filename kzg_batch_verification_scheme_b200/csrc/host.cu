@@ -31,6 +31,7 @@ struct DeviceSlot {
     int device = 0;
     size_t n_max = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;    // high-priority side stream: hashes, challenges and sorts overlap K1
     // staged inputs (host-pointer API)
     uint8_t *dC = nullptr, *dz = nullptr, *dy = nullptr, *dpi = nullptr;
     Fp* pts = nullptr;                 // 2*n_max + 1 affine points: C | pi | G
@@ -58,7 +59,7 @@ struct DeviceSlot {
     uint8_t* h_digests = nullptr;      // 32 * ceil(n_max/1024)
     uint32_t* h_small = nullptr;       // 64 words: [0..1] counters, [8..15] root words, [16] result
     uint8_t* h_partial = nullptr;      // 320 * 64
-    cudaEvent_t ev[12] = {};
+    cudaEvent_t ev[16] = {};
     // current shard (between phase 1 and phase 2)
     const uint8_t *cur_C = nullptr, *cur_z = nullptr, *cur_y = nullptr, *cur_pi = nullptr;
     size_t cur_n = 0;
@@ -92,6 +93,11 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     s.n_max = n_max;
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    {
+        int lo_pri = 0, hi_pri = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        CK(cudaStreamCreateWithPriority(&s.stream2, cudaStreamNonBlocking, hi_pri));
+    }
     for (auto& e : s.ev) CK(cudaEventCreate(&e));
     CK(dmalloc(s.dC, 48 * (n_max + 1))); CK(dmalloc(s.dz, 32 * (n_max + 1))); CK(dmalloc(s.dy, 32 * (n_max + 1))); CK(dmalloc(s.dpi, 48 * (n_max + 1)));
     CK(dmalloc(s.pts, 2 * (2 * n_max + 2)));
@@ -145,6 +151,7 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
 void slot_free(DeviceSlot& s) {
     cudaSetDevice(s.device);
     if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.stream2) cudaStreamSynchronize(s.stream2);
     void* dev[] = {s.dC, s.dz, s.dy, s.dpi, s.pts, s.status, s.counters, s.leaves, s.digests, s.root_words, s.r, s.rz,
                    s.partials, s.sum_ry, s.sortR.keys, s.sortR.vals, s.sortR.keys_alt, s.sortR.vals_alt, s.sortR.bucket_start,
                    s.sortZ.keys, s.sortZ.vals, s.sortZ.keys_alt, s.sortZ.vals_alt, s.sortZ.bucket_start, s.bucketsA,
@@ -156,6 +163,7 @@ void slot_free(DeviceSlot& s) {
     if (s.h_small) cudaFreeHost(s.h_small);
     if (s.h_partial) cudaFreeHost(s.h_partial);
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
+    if (s.stream2) cudaStreamDestroy(s.stream2);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -198,13 +206,16 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
     }
     s.cur_n = n;
     s.have_sums = false;
-    CK(cudaEventRecord(s.ev[1], st));
     CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), st));
-    launch_leaf_hash(st, s.cur_C, s.cur_z, s.cur_y, s.cur_pi, n, s.leaves, s.counters);
-    launch_chunk_hash(st, s.leaves, n, s.digests);
+    CK(cudaEventRecord(s.ev[1], st));
+    // side stream (high priority): hashes first, so they start before K1 fills the SMs
+    cudaStream_t s2 = s.stream2;
+    CK(cudaStreamWaitEvent(s2, s.ev[1], 0));
+    launch_leaf_hash(s2, s.cur_C, s.cur_z, s.cur_y, s.cur_pi, n, s.leaves, s.counters);
+    launch_chunk_hash(s2, s.leaves, n, s.digests);
     size_t nch = (n + KZGB_CHUNK - 1) / KZGB_CHUNK;
-    CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(s.ev[2], st));
+    CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, s2));
+    CK(cudaEventRecord(s.ev[2], s2));
     launch_decompress(st, s.cur_C, s.cur_pi, n, s.pts, s.status, s.counters);
     CK(cudaEventRecord(s.ev[3], st));
     CK(cudaEventSynchronize(s.ev[2]));
@@ -217,13 +228,15 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     size_t n = s.cur_n;
     if (!n) return KZGB_BADARGS;
     CK(cudaSetDevice(s.device));
-    cudaStream_t st = s.stream;
+    cudaStream_t st = s.stream, s2 = s.stream2;
+    // challenges, scalar products and both sorts depend only on the raw inputs: they run on the side
+    // stream while K1 (decompress + subgroup checks) is still busy on the main stream
     be_to_words(s.h_small + 8, root, 8);
-    CK(cudaMemcpyAsync(s.root_words, s.h_small + 8, 32, cudaMemcpyHostToDevice, st));
-    launch_challenges(st, s.root_words, global_offset, s.cur_z, s.cur_y, n, single ? 1 : 0, s.r, s.rz, s.partials, s.sum_ry);
+    CK(cudaMemcpyAsync(s.root_words, s.h_small + 8, 32, cudaMemcpyHostToDevice, s2));
+    launch_challenges(s2, s.root_words, global_offset, s.cur_z, s.cur_y, n, single ? 1 : 0, s.r, s.rz, s.partials, s.sum_ry);
     // the setup point G joins the 255-bit sum with scalar -(sum r_i y_i): point slot 2n
-    CK(cudaMemcpyAsync(s.pts + 2 * (2 * n), s.g1_pt, 2 * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
-    CK(cudaEventRecord(s.ev[4], st));
+    CK(cudaMemcpyAsync(s.pts + 2 * (2 * n), s.g1_pt, 2 * sizeof(Fp), cudaMemcpyDeviceToDevice, s2));
+    CK(cudaEventRecord(s.ev[4], s2));
     s.planR = msm_make_plan(n, 128);
     s.planZ = msm_make_plan(n + 1, 255);
     if ((size_t)s.planR.W * n > s.sortR.capacity || (size_t)s.planZ.W * (n + 1) > s.sortZ.capacity ||
@@ -231,10 +244,11 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
         s.planZ.total_segs > s.max_segs + 512 || s.planR.total_segs > s.max_segs + 512)
         return KZGB_BADARGS;
     MsmWorkspace wr = make_ws(s, s.sortR, s.bucketsA), wz = make_ws(s, s.sortZ, s.bucketsC);
-    msm_sort_stage(st, s.planR, s.r, 4, n, wr);
-    msm_sort_stage(st, s.planZ, s.rz, 8, n + 1, wz);
+    msm_sort_stage(s2, s.planR, s.r, 4, n, wr);
+    msm_sort_stage(s2, s.planZ, s.rz, 8, n + 1, wz);
     save_ws(s.sortR, wr); save_ws(s.sortZ, wz);
-    CK(cudaEventRecord(s.ev[5], st));
+    CK(cudaEventRecord(s.ev[5], s2));
+    CK(cudaStreamWaitEvent(st, s.ev[5], 0));
     MsmWorkspace wr2 = wr;
     wr2.buckets = s.bucketsB;
     msm_accumulate_stage(st, s.planR, s.pts, n, wr);                 // S1 over C_i
@@ -329,13 +343,15 @@ kzgb_ret verify_common(bool* ok, const uint8_t* C, const uint8_t* z, const uint8
     kzgb_ret rc = combine(s0, parts.data(), (int)G, ok);
     if (rc) return rc;
     if (G > 1) s0.have_sums = false;
+    // stages overlap (side stream): hash/challenges/sort are measured on the side stream, decompress and
+    // the rest on the main stream; "accumulate" starts when K1 has finished
     art.stage_ms[0] = ev_ms(s0.ev[0], s0.ev[1]);
     art.stage_ms[2] = ev_ms(s0.ev[1], s0.ev[2]);
-    art.stage_ms[1] = ev_ms(s0.ev[2], s0.ev[3]);
+    art.stage_ms[1] = ev_ms(s0.ev[1], s0.ev[3]);
     art.stage_ms[3] = root_ms;
-    art.stage_ms[4] = ev_ms(s0.ev[3], s0.ev[4]);
+    art.stage_ms[4] = ev_ms(s0.ev[2], s0.ev[4]);
     art.stage_ms[5] = ev_ms(s0.ev[4], s0.ev[5]);
-    art.stage_ms[6] = ev_ms(s0.ev[5], s0.ev[6]);
+    art.stage_ms[6] = ev_ms(s0.ev[3], s0.ev[6]);
     art.stage_ms[7] = ev_ms(s0.ev[6], s0.ev[7]);
     art.stage_ms[8] = ev_ms(s0.ev[7], s0.ev[8]);
     art.stage_ms[9] = ev_ms(s0.ev[0], s0.ev[8]);
@@ -391,8 +407,8 @@ kzgb_ret verify_kzg_proof_batch_device(bool* ok, const uint8_t* dC, const uint8_
     if (ctx && !ctx->slots.empty()) {
         DeviceSlot& s = ctx->slots[0];
         CK(cudaSetDevice(s.device));
-        CK(cudaEventRecord(s.ev[11], (cudaStream_t)stream));
-        CK(cudaStreamWaitEvent(s.stream, s.ev[11], 0));
+        CK(cudaEventRecord(s.ev[15], (cudaStream_t)stream));
+        CK(cudaStreamWaitEvent(s.stream, s.ev[15], 0));
     }
     return verify_common(ok, dC, dz, dy, dpi, n, ctx, true, false);
 }
@@ -403,8 +419,8 @@ kzgb_ret kzgb_shard_phase1(kzgb_ctx* ctx, int slot, const uint8_t* C, const uint
     DeviceSlot& s = ctx->slots[slot];
     if (on_device) {
         CK(cudaSetDevice(s.device));
-        CK(cudaEventRecord(s.ev[11], (cudaStream_t)stream));
-        CK(cudaStreamWaitEvent(s.stream, s.ev[11], 0));
+        CK(cudaEventRecord(s.ev[15], (cudaStream_t)stream));
+        CK(cudaStreamWaitEvent(s.stream, s.ev[15], 0));
     }
     kzgb_ret rc = phase1(s, C, z, y, pi, n_local, on_device != 0, digests_out);
     if (n_bad_out) *n_bad_out = 0;      // malformed elements are reported by phase 2 (K1 is still running)
@@ -635,27 +651,37 @@ kzgb_ret kzgb_debug_op(kzgb_ctx* ctx, int op, const uint8_t* in, uint8_t* out, s
     return KZGB_OK;
 }
 
-kzgb_ret kzgb_imad_peak(kzgb_ctx* ctx, double* imad_per_sec_out, double* ms_out) {
-    if (!ctx || !imad_per_sec_out) return KZGB_BADARGS;
-    DeviceSlot& s = ctx->slots[0];
+static kzgb_ret imad_rate(DeviceSlot& s, int mode, double* rate, double* ms_out) {
     CK(cudaSetDevice(s.device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, s.device));
-    int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4000;
-    launch_imad_bench(s.stream, (uint32_t*)s.scratch, blocks, threads, 200);      // warm-up
+    int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2000;
+    launch_imad_bench(s.stream, (uint32_t*)s.scratch, blocks, threads, 100, mode);      // warm-up
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         CK(cudaEventRecord(s.ev[9], s.stream));
-        launch_imad_bench(s.stream, (uint32_t*)s.scratch, blocks, threads, iters);
+        launch_imad_bench(s.stream, (uint32_t*)s.scratch, blocks, threads, iters, mode);
         CK(cudaEventRecord(s.ev[10], s.stream));
         CK(cudaStreamSynchronize(s.stream));
         float ms = ev_ms(s.ev[9], s.ev[10]);
         if (ms < best) best = ms;
     }
     CK(cudaGetLastError());
-    double total = (double)blocks * threads * (double)iters * 128.0;
-    *imad_per_sec_out = total / (best * 1e-3);
+    *rate = (double)blocks * threads * (double)iters * 128.0 / (best * 1e-3);
     if (ms_out) *ms_out = best;
+    return KZGB_OK;
+}
+kzgb_ret kzgb_imad_peak(kzgb_ctx* ctx, double* imad_per_sec_out, double* ms_out) {
+    if (!ctx || !imad_per_sec_out) return KZGB_BADARGS;
+    return imad_rate(ctx->slots[0], 0, imad_per_sec_out, ms_out);
+}
+kzgb_ret kzgb_imad32_peak(kzgb_ctx* ctx, double* imad_per_sec_out, double* ms_out) {
+    if (!ctx || !imad_per_sec_out) return KZGB_BADARGS;
+    return imad_rate(ctx->slots[0], 1, imad_per_sec_out, ms_out);
+}
+kzgb_ret kzgb_last_stage_ms(kzgb_ctx* ctx, float ms_out[KZGB_N_STAGES]) {
+    if (!ctx || !ms_out) return KZGB_BADARGS;
+    memcpy(ms_out, ctx->art.stage_ms, sizeof ctx->art.stage_ms);
     return KZGB_OK;
 }
 uint64_t kzgb_launch_count(const kzgb_ctx*) { return g_kzgb_launches.load(); }

@@ -2,15 +2,20 @@
 // integer work of a batch verification.  One thread per point; 48-byte inputs are
 // read with three 128-bit loads, the 96-byte Montgomery affine result is written with six.
 // Also hosts the small conversion kernels, the primitive debug operator and the IMAD microbenchmark.
+#include <cstdlib>
+
 #include "kernels.h"
 
 std::atomic<uint64_t> g_kzgb_launches{0};
 
 __device__ __forceinline__ u32 ld_be32(u32 x) { return __byte_perm(x, 0, 0x0123); }
 
-__global__ void __launch_bounds__(128) k_decompress(const u8* __restrict__ inC, const u8* __restrict__ inPi, size_t n,
-                                                    Fp* __restrict__ out_pts, u8* __restrict__ status,
-                                                    u32* __restrict__ counters) {
+// MINB = minimum resident blocks per SM the register allocation must allow (occupancy knob; the
+// variant is picked at run time with KZGB_K1_MINB, default below)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_decompress(const u8* __restrict__ inC, const u8* __restrict__ inPi, size_t n,
+                                                          Fp* __restrict__ out_pts, u8* __restrict__ status,
+                                                          u32* __restrict__ counters) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n) return;
     const u8* src = i < n ? inC + 48 * i : inPi + 48 * (i - n);
@@ -34,7 +39,10 @@ void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, 
                        uint32_t* counters) {
     if (!n) return;
     size_t blocks = (2 * n + 127) / 128;
-    k_decompress<<<(unsigned)blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
+    static const int minb = [] { const char* e = getenv("KZGB_K1_MINB"); return e ? atoi(e) : 2; }();
+    if (minb >= 4) k_decompress<4><<<(unsigned)blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
+    else if (minb == 3) k_decompress<3><<<(unsigned)blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
+    else k_decompress<2><<<(unsigned)blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
     KZ_COUNT_LAUNCH();
 }
 
@@ -132,29 +140,50 @@ void launch_debug_op(cudaStream_t s, int op, const uint8_t* in, uint8_t* out, si
     KZ_COUNT_LAUNCH();
 }
 
-// ---- IMAD.WIDE.U32 issue-rate microbenchmark: 8 independent carry-less chains per thread.
-// Each loop iteration issues 8 x 16 wide multiply-adds; total per thread = iters * 128.
-__global__ void k_imad_bench(u32* sink, int iters) {
+// ---- integer multiply-add issue-rate microbenchmarks (roofline denominators, measured on the box).
+// mode 0: carry-chained mad.lo.cc/madc.hi.cc pairs -> IMAD.WIDE.U32.X, the instruction every Montgomery
+//         product in this library is made of (32 independent 8-pair chains per loop trip and thread);
+// mode 1: plain 32-bit mad.lo.u32 -> IMAD (the pipe's nominal issue rate).
+// Multiplicands are loop-carried registers so ptxas cannot hoist the products out of the loop.
+// Each loop trip issues 128 multiply-adds per thread in both modes.
+__global__ void k_imad_bench(u32* sink, int iters, int mode) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    u64 a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
-    u32 x = t | 1, y = (t * 2654435761u) | 1;
-    for (int i = 0; i < iters; ++i) {
+    u32 y = (t * 2654435761u) | 1;
+    u32 r[32];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0) : "r"(x), "r"(y));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1) : "r"(x), "r"(y));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a2) : "r"(x), "r"(y));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a3) : "r"(x), "r"(y));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a4) : "r"(x), "r"(y));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a5) : "r"(x), "r"(y));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a6) : "r"(x), "r"(y));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a7) : "r"(x), "r"(y));
+    for (int i = 0; i < 32; ++i) r[i] = t + i;
+    if (mode == 0) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    u32* q = &r[8 * c];
+                    asm volatile(
+                        "mad.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+                        "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
+                        "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+                        "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.u32 %7,%8,%9,%7;"
+                        : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7])
+                        : "r"(r[(8 * c + 9) & 31]), "r"(y));
+                }
+            }
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) asm volatile("mad.lo.u32 %0,%1,%2,%0;" : "+r"(r[i]) : "r"(r[(i + 1) & 31]), "r"(y));
+            }
         }
     }
-    u64 r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
-    if (r == 0x123456789ull) sink[0] = (u32)r;      // never true in practice; keeps the chains alive
+    u32 z = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) z ^= r[i];
+    if (z == 0x23456789u) sink[0] = z;      // practically never; keeps the chains alive
 }
-void launch_imad_bench(cudaStream_t s, uint32_t* sink, int blocks, int threads, int iters) {
-    k_imad_bench<<<blocks, threads, 0, s>>>(sink, iters);
+void launch_imad_bench(cudaStream_t s, uint32_t* sink, int blocks, int threads, int iters, int mode) {
+    k_imad_bench<<<blocks, threads, 0, s>>>(sink, iters, mode);
     KZ_COUNT_LAUNCH();
 }

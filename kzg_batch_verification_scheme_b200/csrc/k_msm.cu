@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) k_msm_segments(const G1Xyzz* __restrict__
     if (s >= plan.total_segs) return;
     int w = 0;
     while (s >= plan.seg_off[w + 1]) ++w;
-    segsums[s] = msm_segment_body(buckets + plan.bucket_off[w], plan.nb[w], s - plan.seg_off[w]);
+    segsums[s] = msm_segment_body(buckets + plan.bucket_off[w], plan.nb[w], s - plan.seg_off[w], plan.seg);
 }
 
 // one block per window: sum of its segment sums

@@ -20,7 +20,7 @@ void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, 
 void launch_points_to_be(cudaStream_t s, const Fp* pts, size_t m, uint8_t* out96);           // canonical x||y
 void launch_points_from_be(cudaStream_t s, const uint8_t* in96, size_t m, Fp* pts, uint32_t* counters);
 void launch_debug_op(cudaStream_t s, int op, const uint8_t* in, uint8_t* out, size_t count);
-void launch_imad_bench(cudaStream_t s, uint32_t* sink, int blocks, int threads, int iters);
+void launch_imad_bench(cudaStream_t s, uint32_t* sink, int blocks, int threads, int iters, int mode);
 
 // ---- k_fs.cu
 void launch_leaf_hash(cudaStream_t s, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,

@@ -5,12 +5,12 @@
 #include "g1.cuh"
 
 #define KZ_MSM_MAX_WINDOWS 96
-#define KZ_MSM_SEG 32            // buckets per reduction segment
 
 struct MsmPlan {
     int nbits;                   // scalar width: 128 or 255
     int c;                       // window width
     int W;                       // number of windows = ceil(nbits / c)
+    u32 seg;                     // buckets per reduction segment
     u32 nb[KZ_MSM_MAX_WINDOWS];          // buckets per window (top window is unsigned)
     u32 bucket_off[KZ_MSM_MAX_WINDOWS + 1];   // prefix sums of nb
     u32 seg_off[KZ_MSM_MAX_WINDOWS + 1];      // prefix sums of ceil(nb / SEG)
@@ -29,13 +29,14 @@ inline MsmPlan msm_make_plan(size_t n, int nbits) {
     p.nbits = nbits;
     p.c = c;
     p.W = (nbits + c - 1) / c;
+    p.seg = c >= 15 ? 16u : 8u;   // short serial chains: the reduction is latency-bound
     p.bucket_off[0] = 0;
     p.seg_off[0] = 0;
     for (int w = 0; w < p.W; ++w) {
         int tb = nbits - c * (p.W - 1);
         p.nb[w] = (w < p.W - 1) ? (1u << (c - 1)) : (1u << tb);
         p.bucket_off[w + 1] = p.bucket_off[w] + p.nb[w];
-        p.seg_off[w + 1] = p.seg_off[w] + (p.nb[w] + KZ_MSM_SEG - 1) / KZ_MSM_SEG;
+        p.seg_off[w + 1] = p.seg_off[w] + (p.nb[w] + p.seg - 1) / p.seg;
     }
     p.total_buckets = p.bucket_off[p.W];
     p.total_segs = p.seg_off[p.W];
@@ -152,18 +153,21 @@ KZ_HD void msm_chunk_pass2(u32 T, u32 t, G1Xyzz* buckets, const ChunkRecs& R) {
 
 // [k]P by double-and-add for a small k (< 2^17)
 KZ_COLD G1Xyzz xyzz_mul_small(const G1Xyzz& p, u32 k) {
-    G1Xyzz r = xyzz_inf();
-    for (int i = 16; i >= 0; --i) {
+    if (!k) return xyzz_inf();
+    int top = 16;
+    while (!((k >> top) & 1)) --top;
+    G1Xyzz r = p;
+    for (int i = top - 1; i >= 0; --i) {
         r = xyzz_dbl(r);
         if ((k >> i) & 1) r = xyzz_add(r, p);
     }
     return r;
 }
-// segment `seg` of window w: local buckets k = base+1 .. min(base+SEG, nb), base = seg*SEG.
+// segment `seg` of window w: local buckets k = base+1 .. min(base+seglen, nb), base = seg*seglen.
 // returns sum_k k * B_k  (running-sum trick inside the segment plus [base] * run).
-KZ_HD G1Xyzz msm_segment_body(const G1Xyzz* buckets, u32 nb, u32 seg) {
-    u32 base = seg * KZ_MSM_SEG;
-    u32 top = base + KZ_MSM_SEG < nb ? base + KZ_MSM_SEG : nb;
+KZ_HD G1Xyzz msm_segment_body(const G1Xyzz* buckets, u32 nb, u32 seg, u32 seglen) {
+    u32 base = seg * seglen;
+    u32 top = base + seglen < nb ? base + seglen : nb;
     G1Xyzz run = xyzz_inf(), acc = xyzz_inf();
     for (u32 k = top; k > base; --k) {          // bucket with value k is stored at index k-1
         run = xyzz_add(run, buckets[k - 1]);

@@ -368,6 +368,12 @@ kzgb_ret kzgb_debug_op(kzgb_ctx* c, int op, const uint8_t* in, uint8_t* out, siz
 }
 
 kzgb_ret kzgb_imad_peak(kzgb_ctx*, double*, double*) { return KZGB_ERROR; }
+kzgb_ret kzgb_imad32_peak(kzgb_ctx*, double*, double*) { return KZGB_ERROR; }
+kzgb_ret kzgb_last_stage_ms(kzgb_ctx* c, float ms[KZGB_N_STAGES]) {
+    if (!c || !ms) return KZGB_BADARGS;
+    memcpy(ms, c->stage_ms, sizeof c->stage_ms);
+    return KZGB_OK;
+}
 uint64_t kzgb_launch_count(const kzgb_ctx*) { return 0; }
 
 }  // extern "C"

@@ -67,7 +67,7 @@ static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nb
     for (u32 s = 0; s < plan.total_segs; ++s) {
         int w = 0;
         while (s >= plan.seg_off[w + 1]) ++w;
-        segs[s] = msm_segment_body(buckets.data() + plan.bucket_off[w], plan.nb[w], s - plan.seg_off[w]);
+        segs[s] = msm_segment_body(buckets.data() + plan.bucket_off[w], plan.nb[w], s - plan.seg_off[w], plan.seg);
     }
     for (int w = 0; w < plan.W; ++w) {
         G1Xyzz acc = xyzz_inf();
@@ -366,6 +366,8 @@ kzgb_ret kzgb_combine_verify(kzgb_ctx*, const uint8_t*, int, bool*) { return KZG
 kzgb_ret kzgb_g1_msm_times(float*, kzgb_ctx*) { return KZGB_ERROR; }
 kzgb_ret kzgb_synth_setup(uint8_t*, size_t, uint8_t*, size_t) { return KZGB_ERROR; }
 kzgb_ret kzgb_imad_peak(kzgb_ctx*, double*, double*) { return KZGB_ERROR; }
+kzgb_ret kzgb_imad32_peak(kzgb_ctx*, double*, double*) { return KZGB_ERROR; }
+kzgb_ret kzgb_last_stage_ms(kzgb_ctx*, float*) { return KZGB_ERROR; }
 uint64_t kzgb_launch_count(const kzgb_ctx*) { return 0; }
 int kzgb_set_threads(kzgb_ctx*, int) { return 0; }
 }

@@ -126,6 +126,112 @@ def gen_mul(n, mod, a, b, out, sqr=False):
     return pg, E + O + ["m"]
 
 
+def gen_sqr(n, mod, a, out):
+    """Montgomery square a*a/2^(32n), result in [0, 2*mod).  n(n-1)/2 + n wide multiply-adds for the
+    2n-limb square (off-diagonal products once, doubled, plus the diagonal) and n^2 + n for the reduction
+    of its low half ("multiply by 1" with the limb shift fused into the m*p_odd chain): 234 for n = 12.
+
+    Off-diagonal products a_i*a_(i+d) sit at limbs (2i+d, 2i+d+1): for a fixed difference d they do not
+    overlap, so each d is ONE carry chain; even d go to array ev*, odd d to od* (true limb positions).
+    Processing d from large to small makes every chain's carry-out land in a limb no earlier chain has
+    touched."""
+    pl = limbs(mod, n)
+    m0 = (-pow(mod, -1, 1 << 32)) & MASK
+    pg = Prog()
+    EV = [f"v{k}" for k in range(2 * n)]
+    OD = [f"w{k}" for k in range(2 * n)]
+    for arr, ds in ((EV, range(n - 2, 0, -2)), (OD, range(n - 1, 0, -2))):
+        touched = set()
+        for d in ds:
+            cnt = n - d
+            chain_open = False
+            for i in range(cnt):
+                lo, hi = 2 * i + d, 2 * i + d + 1
+                alo = arr[lo] if lo in touched else 0
+                ahi = arr[hi] if hi in touched else 0
+                if not chain_open and alo == 0 and ahi == 0:
+                    pg.op("mul.lo.u32", arr[lo], a[i], a[i + d])          # fresh pair, nothing to carry
+                    pg.op("mul.hi.u32", arr[hi], a[i], a[i + d])
+                else:
+                    pg.op("madc.lo.cc.u32" if chain_open else "mad.lo.cc.u32", arr[lo], a[i], a[i + d], alo)
+                    pg.op("madc.hi.cc.u32", arr[hi], a[i], a[i + d], ahi)
+                    chain_open = True
+                touched.update((lo, hi))
+            if chain_open:
+                top = 2 * (cnt - 1) + d + 2
+                assert top not in touched
+                pg.op("addc.u32", arr[top], 0, 0)
+                touched.add(top)
+        for k in range(2 * n):
+            if k not in touched:
+                pg.op("mov.u32", arr[k], 0)
+    # S = EV + OD ; T = 2S + diag.  (S < 2^(64n-1), so nothing is lost)
+    T = [f"t{k}" for k in range(2 * n)]
+    for k in range(2 * n):
+        pg.op("add.cc.u32" if k == 0 else ("addc.cc.u32" if k < 2 * n - 1 else "addc.u32"), T[k], EV[k], OD[k])
+    for k in range(2 * n):
+        pg.op("add.cc.u32" if k == 0 else ("addc.cc.u32" if k < 2 * n - 1 else "addc.u32"), T[k], T[k], T[k])
+    for i in range(n):
+        pg.op("mad.lo.cc.u32" if i == 0 else "madc.lo.cc.u32", T[2 * i], a[i], a[i], T[2 * i])
+        pg.op("madc.hi.cc.u32" if i < n - 1 else "madc.hi.u32", T[2 * i + 1], a[i], a[i], T[2 * i + 1])
+    # reduction of the low half: X = T[0..n) at limb k, Y = 0 at limb k+1; roles swap every iteration
+    A = T[:n]
+    Bq = [f"q{k}" for k in range(n)]
+    for i in range(n):
+        X, Y = (A, Bq) if i % 2 == 0 else (Bq, A)
+        if i == 0:
+            pg.op("mul.lo.u32", "m", X[0], m0)
+            for k in range(0, n, 2):
+                pg.op("mul.lo.u32", Y[k], "m", pl[k + 1])
+                pg.op("mul.hi.u32", Y[k + 1], "m", pl[k + 1])
+        else:
+            pg.op("add.cc.u32", X[0], X[0], Y[1])
+            pg.op("mul.lo.u32", "m", X[0], m0)                      # does not touch the carry flag
+            for k in range(0, n - 2, 2):
+                pg.op("madc.lo.cc.u32", Y[k], "m", pl[k + 1], Y[k + 2])
+                pg.op("madc.hi.cc.u32", Y[k + 1], "m", pl[k + 1], Y[k + 3])
+            pg.op("madc.lo.cc.u32", Y[n - 2], "m", pl[n - 1], 0)
+            pg.op("madc.hi.u32", Y[n - 1], "m", pl[n - 1], 0)
+        cmad_chain(pg, X, [pl[k] for k in range(0, n, 2)], "m")
+        pg.op("addc.u32", Y[n - 1], Y[n - 1], 0)
+    X, Y = (A, Bq) if (n - 1) % 2 == 0 else (Bq, A)
+    U = [f"u{k}" for k in range(n)]
+    for k in range(n - 1):
+        pg.op("add.cc.u32" if k == 0 else "addc.cc.u32", U[k], Y[k], X[k + 1])
+    pg.op("addc.u32", U[n - 1], Y[n - 1], 0)
+    for k in range(n):
+        pg.op("add.cc.u32" if k == 0 else ("addc.cc.u32" if k < n - 1 else "addc.u32"), out[k], U[k], T[n + k])
+    return pg, EV + OD + T + Bq + U + ["m"]
+
+
+def check_sqr(n, mod, trials=300):
+    rnd = random.Random(50 + n)
+    a = [f"a{k}" for k in range(n)]
+    out = [f"r{k}" for k in range(n)]
+    pg, _ = gen_sqr(n, mod, a, out)
+    rinv = pow(1 << (32 * n), -1, mod)
+    edge = [0, 1, 2, mod - 1, mod - 2, (1 << (32 * n)) % mod, mod >> 1, (1 << (32 * n - 3)) - 1,
+            sum(0xFFFFFFFF << (64 * k) for k in range(n // 2)) % mod]
+    for x in edge + [rnd.randrange(mod) for _ in range(trials)]:
+        env = {a[k]: limbs(x, n)[k] for k in range(n)}
+        simulate(pg, env)
+        got = sum(env[out[k]] << (32 * k) for k in range(n))
+        assert got < 2 * mod and got % mod == x * x * rinv % mod, (n, hex(x))
+    nim = sum(1 for nm, _, _ in pg.ins if ".hi" in nm) + sum(1 for nm, _, _ in pg.ins if nm == "mul.lo.u32" and False)
+    return len(pg.ins), nim
+
+
+def emit_sqr_fn(fname, n, mod):
+    a = [f"a{k}" for k in range(n)]
+    out = [f"r{k}" for k in range(n)]
+    pg, temps = gen_sqr(n, mod, a, out)
+    body = emit_asm(pg, [(out[k], f"r[{k}]") for k in range(n)], [(a[k], f"a[{k}]") for k in range(n)], temps)
+    nim = sum(1 for nm, _, _ in pg.ins if ".hi" in nm)
+    return (f"// Montgomery square, result in [0, 2p).  {nim} wide multiply-adds + {n} mul.lo.\n"
+            f"__device__ __forceinline__ void {fname}(uint32_t (&r)[{n}], const uint32_t (&a)[{n}]) {{\n"
+            f"{body}\n}}\n")
+
+
 def gen_add(n, mod):
     """r = a + b (no overflow: a,b < p < 2^(32n-1)); t = r - p; bw = all-ones iff r < p."""
     pl = limbs(mod, n)
@@ -282,12 +388,14 @@ def main():
     n2 = check_mul(8, R)
     check_addsub(12, P)
     check_addsub(8, R)
+    ns, nim = check_sqr(12, P)
+    check_sqr(8, R)
     if args.selftest:
-        print(f"selftest ok: fp_mul {n1} instrs, fr_mul {n2} instrs")
+        print(f"selftest ok: fp_mul {n1} instrs, fr_mul {n2} instrs, fp_sqr {ns} instrs ({nim} wide mads)")
         return
     txt = ["// GENERATED by tools/gen_mont.py -- do not edit.  Inline-PTX Montgomery products (sm_100a).",
            "#pragma once", "#include <cstdint>", "",
-           emit_mul_fn("fp_mont_mul_ptx", 12, P), emit_mul_fn("fr_mont_mul_ptx", 8, R),
+           emit_mul_fn("fp_mont_mul_ptx", 12, P), emit_mul_fn("fr_mont_mul_ptx", 8, R), emit_sqr_fn("fp_mont_sqr_ptx", 12, P),
            emit_addsub_fns("fp", 12, P), emit_addsub_fns("fr", 8, R)]
     Path(args.o).write_text("\n".join(txt))
     print(f"wrote {args.o}: fp_mul {n1} instrs, fr_mul {n2} instrs")

@@ -31,7 +31,7 @@ for n in sizes:
         t0 = time.time()
         rc, ok = ctx.verify_kzg_proof_batch_device(*ptrs, n, stream)
         wall = (time.time() - t0) * 1e3
-        st = ctx.last_artifacts()["stage_ms"]
+        st = ctx.last_stage_ms()
         if best is None or st["total"] < best["total"]:
             best = dict(st, wall_ms=wall, rc=rc, ok=ok)
     best["gen_s"] = gen_s
