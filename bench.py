@@ -24,10 +24,16 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-# algorithmic work model (DESIGN.md "Work model"): one Fp Montgomery product = 300 wide
-# multiply-adds; K1 per point = sqrt (471 mul) + subgroup check (1021 mul)
-IMAD_PER_FPMUL = 300
-K1_FPMUL_PER_POINT = 471 + 1021
+# algorithmic work model (DESIGN.md "Work model").  Unit = one 32x32->64 multiply-add.
+# Generic Montgomery product: 2N^2+N = 300 (N = 12); dedicated squaring: N(N-1)/2 + N + N^2 + N = 234.
+# K1 per point: sqrt a^((p+1)/4) = 379 S + 103 M (4-bit windows), on-curve check 2 S + 1 M, two |x| chains =
+# 126 doublings (2M+5S) + 5 mixed additions (8M+3S) + 5 full additions (12M+4S) + compare (3M+1S):
+IMAD_PER_FPMUL, IMAD_PER_FPSQR = 300, 234
+K1_M_PER_POINT = 103 + 1 + 126 * 2 + 5 * 8 + 5 * 12 + 3 + 2          # + to/from Montgomery
+K1_S_PER_POINT = 379 + 2 + 126 * 5 + 5 * 3 + 5 * 4 + 1
+K1_IMAD_PER_POINT = K1_M_PER_POINT * IMAD_PER_FPMUL + K1_S_PER_POINT * IMAD_PER_FPSQR
+K1_IMAD_PER_POINT_SURVEY = (471 + 1021) * 300                          # SURVEY.md 8(d) model, M = S = 300
+MSM_FPMUL_PER_PROOF = 370                                              # SURVEY.md App. C, n = 2^20
 SEED = 0x4B5A4703
 
 
@@ -145,6 +151,7 @@ def main():
     import torch
     import torch.distributed as dist
     from kzg_batch_verification_scheme_b200.api import CHUNK, PARTIAL_BYTES, load
+    from kzg_batch_verification_scheme_b200.sharded import sharded_verify
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -186,20 +193,9 @@ def main():
                 rc, ok = ctx.verify_kzg_proof_batch(*ptrs, n_local)
             assert rc == 0, rc
             return ok
-        rc, dig, _ = ctx.shard_phase1(0, *ptrs, n_local, on_device=on_device, stream=stream)
+        rc, ok = sharded_verify(ctx, dist, rank, world, *ptrs, n_local, on_device=on_device, stream=stream)
         assert rc == 0, rc
-        gathered = [None] * world
-        dist.all_gather_object(gathered, dig)
-        root = ctx.fs_root(b"".join(gathered), n_total)
-        rc, part = ctx.shard_phase2(0, root, rank * n_local)
-        assert rc == 0, rc
-        parts = [None] * world
-        dist.gather_object(part, parts if rank == 0 else None, dst=0)
-        if rank == 0:
-            rc, ok = ctx.combine_verify(b"".join(parts))
-            assert rc == 0, rc
-            return ok
-        return True
+        return True if ok is None else ok
 
     def timed(ptrs, on_device, steps, warmup):
         for _ in range(warmup):
@@ -250,21 +246,27 @@ def main():
         peaks_path = ROOT / "MEASURED_PEAKS.json"
         peaks = json.loads(peaks_path.read_text()) if peaks_path.exists() else {}
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        imad_peak, imad_ms = ctx.imad_peak()
+        imad_peak, imad_ms = ctx.imad_peak(wide=True)          # IMAD.WIDE.U32.X carry chains (what the kernels issue)
+        imad32_peak, _ = ctx.imad_peak(wide=False)             # plain 32-bit IMAD, context only
         k1_ms = stages.get("decompress", 0.0)
         if k1_ms > 0:
-            k1_imad = 2 * n_local * K1_FPMUL_PER_POINT * IMAD_PER_FPMUL
+            k1_imad = 2 * n_local * K1_IMAD_PER_POINT
             ach = k1_imad / (k1_ms * 1e-3)
-            roofline = {"bound": "imad", "kernel": "k_decompress", "achieved": ach / 1e12, "peak": imad_peak / 1e12,
-                        "unit": "T IMAD.WIDE/s", "frac": ach / imad_peak, "traffic": None,
-                        "peak_source": "kzgb_imad_peak microbenchmark measured in this run (mad.wide.u32 chains on all SMs)",
+            roofline = {"bound": "imad", "kernel": "K1 = k_decompress_sqrt + k_subgroup_chain1 + k_subgroup_chain2 (one stage, 3 launches)",
+                        "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T wide-IMAD/s", "frac": ach / imad_peak,
+                        "traffic": None,
+                        "peak_source": "kzgb_imad_peak: carry-chained mad.lo.cc/madc.hi.cc (SASS IMAD.WIDE.U32.X) microbenchmark on all SMs, "
+                                       "measured in this run; 32 lanes/clk/SM on B200",
+                        "imad32_issue_peak": imad32_peak / 1e12,
                         "algorithmic_per_launch": k1_imad, "launch_ms": k1_ms,
-                        "whole_batch_frac": (n_local * (2 * K1_FPMUL_PER_POINT + 370) * IMAD_PER_FPMUL) / (stages.get("total", ms_dev) * 1e-3) / imad_peak}
-            k1_bytes = 2 * n_local * (48 + 96 + 1)
-            roofline_hbm = {"bound": "hbm", "kernel": "k_decompress", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                        "formula": f"2n x ({K1_M_PER_POINT} M x 300 + {K1_S_PER_POINT} S x 234) wide multiply-adds; stage time from CUDA events on the library's stream",
+                        "frac_survey_model": 2 * n_local * K1_IMAD_PER_POINT_SURVEY / (k1_ms * 1e-3) / imad_peak,
+                        "whole_batch_frac": (n_local * (2 * K1_IMAD_PER_POINT + MSM_FPMUL_PER_PROOF * 300)) / (stages.get("total", ms_dev) * 1e-3) / imad_peak}
+            k1_bytes = 2 * n_local * (48 + 96 + 1 + 2 * 144 + 2 * 96)
+            roofline_hbm = {"bound": "hbm", "kernel": "K1", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak,
                             "unit": "GB/s", "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                            "note": "K1 is integer-pipe bound by construction (~1500 Fp products per 145 bytes); HBM fraction reported for completeness"}
+                            "note": "K1 is integer-pipe bound by construction (~1500 Fp products per ~625 bytes moved); HBM fraction reported for completeness"}
         if not args.no_extras:
             # CPU baseline: oracle port on the box's host cores, bounded sample (~10-20 s)
             try:
@@ -314,7 +316,7 @@ def main():
                         best = t if best is None or t[3] < best[3] else best
                     extras[f"msm_{nbits}bit_mpts_per_s"] = m / (best[3] * 1e-3) / 1e6
                     extras[f"msm_{nbits}bit_ms"] = {"sort": best[0], "accumulate": best[1], "reduce": best[2], "total": best[3]}
-                    ipp = 52.2e3 if nbits == 255 else 29.4e3          # SURVEY 8(d) IMAD per point at c=16
+                    ipp = 52.2e3 if nbits == 255 else 29.4e3          # SURVEY 8(d) multiply-adds per point at c=16
                     extras[f"msm_{nbits}bit_imad_frac"] = m * ipp / (best[3] * 1e-3) / imad_peak
         line = {
             "metric": "verified KZG proofs/s", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,

@@ -195,22 +195,16 @@ KZ_HD G1Jac jac_mul_xabs(const G1Jac& p) {
     return acc;
 }
 // P in G1  <=>  sigma(P) == -[x^2]P with sigma(x,y) = (beta x, y)   (P != infinity)
-KZ_HD bool g1_in_subgroup(const G1Aff& p) {
-    G1Jac q = jac_mul_xabs(jac_mul_xabs_aff(p));
-    if (jac_is_inf(q)) return false;
-    Fp zz = fp_sqr(q.Z);
-    Fp bx = fp_mul(fp_const(FP_BETA), p.x);
-    if (!fp_eq(q.X, fp_mul(bx, zz))) return false;
-    Fp zzz = fp_mul(zz, q.Z);
-    return fp_eq(q.Y, fp_neg(fp_mul(p.y, zzz)));
-}
+KZ_HD bool g1_subgroup_compare(const G1Aff& p, const G1Jac& q);
+KZ_HD bool g1_in_subgroup(const G1Aff& p) { return g1_subgroup_compare(p, jac_mul_xabs(jac_mul_xabs_aff(p))); }
 
 // ------------------------------------------------------------------ decompress + validate (K1 body)
 enum { ST_OK = 0, ST_BAD_FLAGS = 1, ST_X_GE_P = 2, ST_NOT_ON_CURVE = 3, ST_NOT_IN_G1 = 4 };
 
 // in: 48 bytes big-endian as 12 big-endian-loaded words w[0..11] (w[0] holds bytes 0..3).
-// out: affine point in Montgomery form ((0,0) for infinity or any failure).  Returns the status byte.
-KZ_HD u32 g1_decompress_validate(G1Aff& out, const u32* w, bool check_subgroup = true) {
+// Stage 1 (flags, range, square root, sign): out = affine point in Montgomery form, (0,0) for infinity or
+// any failure.  Returns the status byte; ST_OK here still lacks the subgroup check.
+KZ_HD u32 g1_decompress_sqrt(G1Aff& out, const u32* w) {
     out = aff_inf();
     u32 b0 = w[0] >> 24;
     if (!(b0 & 0x80)) return ST_BAD_FLAGS;
@@ -230,7 +224,25 @@ KZ_HD u32 g1_decompress_validate(G1Aff& out, const u32* w, bool check_subgroup =
     Fp y = fp_sqrt_candidate(rhs);
     if (!fp_eq(fp_sqr(y), rhs)) return ST_NOT_ON_CURVE;
     if (fp_is_lex_largest(y) != ((b0 & 0x20) != 0)) y = fp_neg(y);
-    G1Aff p = {x, y};
+    out = {x, y};
+    return ST_OK;
+}
+// Stage 3 of the subgroup check: given Q = [x^2]P (Jacobian), decide sigma(P) == -Q.
+KZ_HD bool g1_subgroup_compare(const G1Aff& p, const G1Jac& q) {
+    if (jac_is_inf(q)) return false;
+    Fp zz = fp_sqr(q.Z);
+    Fp bx = fp_mul(fp_const(FP_BETA), p.x);
+    if (!fp_eq(q.X, fp_mul(bx, zz))) return false;
+    Fp zzz = fp_mul(zz, q.Z);
+    return fp_eq(q.Y, fp_neg(fp_mul(p.y, zzz)));
+}
+// fused form (debug operator, setup point, emulation)
+KZ_HD u32 g1_decompress_validate(G1Aff& out, const u32* w, bool check_subgroup = true) {
+    G1Aff p;
+    u32 st = g1_decompress_sqrt(p, w);
+    out = aff_inf();
+    if (st != ST_OK) return st;
+    if (aff_is_inf(p)) return ST_OK;
     if (check_subgroup && !g1_in_subgroup(p)) return ST_NOT_IN_G1;
     out = p;
     return ST_OK;

@@ -35,6 +35,7 @@ struct DeviceSlot {
     // staged inputs (host-pointer API)
     uint8_t *dC = nullptr, *dz = nullptr, *dy = nullptr, *dpi = nullptr;
     Fp* pts = nullptr;                 // 2*n_max + 1 affine points: C | pi | G
+    Fp* k1_tmp = nullptr;              // 3 Fp per point: [|x|]P between the subgroup-check kernels
     uint8_t* status = nullptr;         // 2*n_max
     uint32_t* counters = nullptr;      // [0] bad points [1] bad scalars
     uint32_t *leaves = nullptr, *digests = nullptr, *root_words = nullptr;
@@ -101,6 +102,7 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     for (auto& e : s.ev) CK(cudaEventCreate(&e));
     CK(dmalloc(s.dC, 48 * (n_max + 1))); CK(dmalloc(s.dz, 32 * (n_max + 1))); CK(dmalloc(s.dy, 32 * (n_max + 1))); CK(dmalloc(s.dpi, 48 * (n_max + 1)));
     CK(dmalloc(s.pts, 2 * (2 * n_max + 2)));
+    CK(dmalloc(s.k1_tmp, 3 * (2 * n_max + 2)));
     CK(dmalloc(s.status, 2 * n_max + 2));
     CK(dmalloc(s.counters, 8));
     size_t nch = (n_max + KZGB_CHUNK - 1) / KZGB_CHUNK;
@@ -152,7 +154,7 @@ void slot_free(DeviceSlot& s) {
     cudaSetDevice(s.device);
     if (s.stream) cudaStreamSynchronize(s.stream);
     if (s.stream2) cudaStreamSynchronize(s.stream2);
-    void* dev[] = {s.dC, s.dz, s.dy, s.dpi, s.pts, s.status, s.counters, s.leaves, s.digests, s.root_words, s.r, s.rz,
+    void* dev[] = {s.dC, s.dz, s.dy, s.dpi, s.pts, s.k1_tmp, s.status, s.counters, s.leaves, s.digests, s.root_words, s.r, s.rz,
                    s.partials, s.sum_ry, s.sortR.keys, s.sortR.vals, s.sortR.keys_alt, s.sortR.vals_alt, s.sortR.bucket_start,
                    s.sortZ.keys, s.sortZ.vals, s.sortZ.keys_alt, s.sortZ.vals_alt, s.sortZ.bucket_start, s.bucketsA,
                    s.bucketsB, s.bucketsC, s.segsums, s.winsums, s.cub_temp, s.sums, s.partial_dev, s.partials_in,
@@ -216,7 +218,7 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
     size_t nch = (n + KZGB_CHUNK - 1) / KZGB_CHUNK;
     CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, s2));
     CK(cudaEventRecord(s.ev[2], s2));
-    launch_decompress(st, s.cur_C, s.cur_pi, n, s.pts, s.status, s.counters);
+    launch_decompress(st, s.cur_C, s.cur_pi, n, s.pts, s.k1_tmp, s.status, s.counters);
     CK(cudaEventRecord(s.ev[3], st));
     CK(cudaEventSynchronize(s.ev[2]));
     words_to_be(digests_out, (const uint32_t*)s.h_digests, 8 * nch);
@@ -466,7 +468,7 @@ kzgb_ret kzgb_g1_decompress_batch(uint8_t* affine_out, uint8_t* status_out, cons
         CK(cudaMemsetAsync(s.dC + 48 * k, 0, 48, s.stream));             // pad slot when k is odd
         CK(cudaMemcpyAsync(s.dC, in + 48 * done, 48 * k, cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), s.stream));
-        launch_decompress(s.stream, s.dC, s.dC + 48 * h, h, s.pts, s.status, s.counters);
+        launch_decompress(s.stream, s.dC, s.dC + 48 * h, h, s.pts, s.k1_tmp, s.status, s.counters);
         launch_points_to_be(s.stream, s.pts, k, d_be);
         CK(cudaMemcpyAsync(affine_out + 96 * done, d_be, 96 * k, cudaMemcpyDeviceToHost, s.stream));
         CK(cudaMemcpyAsync(status_out + done, s.status, k, cudaMemcpyDeviceToHost, s.stream));

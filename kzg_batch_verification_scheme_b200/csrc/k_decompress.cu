@@ -10,12 +10,17 @@ std::atomic<uint64_t> g_kzgb_launches{0};
 
 __device__ __forceinline__ u32 ld_be32(u32 x) { return __byte_perm(x, 0, 0x0123); }
 
-// MINB = minimum resident blocks per SM the register allocation must allow (occupancy knob; the
-// variant is picked at run time with KZGB_K1_MINB, default below)
+// K1 is split into three kernels so that each stays within a register budget that allows 12-16 resident
+// warps per SM (the fused kernel needed 255 registers = 8 warps and was latency-bound, profiles/):
+//   K1a  flags, range check, y = sqrt(x^3+4), sign            -> affine P            (~480 Fp products)
+//   K1b  T = [|x|]P, Jacobian double-and-add, mixed additions -> T (144 B scratch)   (~500)
+//   K1c  Q = [|x|]T, full additions; sigma(P) == -Q ?         -> status, P or zeros  (~525)
+// The 240 B/point of extra traffic is ~0.1 % of the kernels' run time.
+// MINB = minimum resident blocks per SM the register allocation must allow (run-time pick: KZGB_K1_MINB).
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_decompress(const u8* __restrict__ inC, const u8* __restrict__ inPi, size_t n,
-                                                          Fp* __restrict__ out_pts, u8* __restrict__ status,
-                                                          u32* __restrict__ counters) {
+__global__ void __launch_bounds__(128, MINB) k_decompress_sqrt(const u8* __restrict__ inC, const u8* __restrict__ inPi, size_t n,
+                                                               Fp* __restrict__ out_pts, u8* __restrict__ status,
+                                                               u32* __restrict__ counters) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n) return;
     const u8* src = i < n ? inC + 48 * i : inPi + 48 * (i - n);
@@ -24,7 +29,7 @@ __global__ void __launch_bounds__(128, MINB) k_decompress(const u8* __restrict__
     u32 w[12] = {ld_be32(q0.x), ld_be32(q0.y), ld_be32(q0.z), ld_be32(q0.w), ld_be32(q1.x), ld_be32(q1.y),
                  ld_be32(q1.z), ld_be32(q1.w), ld_be32(q2.x), ld_be32(q2.y), ld_be32(q2.z), ld_be32(q2.w)};
     G1Aff p;
-    u32 st = g1_decompress_validate(p, w);
+    u32 st = g1_decompress_sqrt(p, w);
     uint4* d4 = reinterpret_cast<uint4*>(out_pts + 2 * i);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -34,16 +39,67 @@ __global__ void __launch_bounds__(128, MINB) k_decompress(const u8* __restrict__
     status[i] = (u8)st;
     if (st) atomicAdd(counters, 1u);
 }
+__device__ __forceinline__ Fp ld_fp(const Fp* p) {
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4 a = s[0], b = s[1], c = s[2];
+    Fp r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    r.v[8] = c.x; r.v[9] = c.y; r.v[10] = c.z; r.v[11] = c.w;
+    return r;
+}
+__device__ __forceinline__ void st_fp(Fp* p, const Fp& r) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    d[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    d[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+    d[2] = make_uint4(r.v[8], r.v[9], r.v[10], r.v[11]);
+}
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_subgroup_chain1(const Fp* __restrict__ pts, size_t m, Fp* __restrict__ tmp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    G1Aff p = {ld_fp(pts + 2 * i), ld_fp(pts + 2 * i + 1)};
+    if (aff_is_inf(p)) return;                       // infinity or already rejected: nothing to check
+    G1Jac t = jac_mul_xabs_aff(p);
+    st_fp(tmp + 3 * i, t.X); st_fp(tmp + 3 * i + 1, t.Y); st_fp(tmp + 3 * i + 2, t.Z);
+}
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_subgroup_chain2(Fp* __restrict__ pts, size_t m, const Fp* __restrict__ tmp,
+                                                               u8* __restrict__ status, u32* __restrict__ counters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    Fp px = ld_fp(pts + 2 * i);
+    {
+        Fp py = ld_fp(pts + 2 * i + 1);
+        if (fp_is_zero(px) && fp_is_zero(py)) return;
+    }
+    G1Jac t = {ld_fp(tmp + 3 * i), ld_fp(tmp + 3 * i + 1), ld_fp(tmp + 3 * i + 2)};
+    G1Jac q = jac_mul_xabs(t);
+    G1Aff p = {px, ld_fp(pts + 2 * i + 1)};
+    if (!g1_subgroup_compare(p, q)) {
+        Fp z = fp_zero();
+        st_fp(pts + 2 * i, z); st_fp(pts + 2 * i + 1, z);
+        status[i] = (u8)ST_NOT_IN_G1;
+        atomicAdd(counters, 1u);
+    }
+}
 
-void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, Fp* out_pts, uint8_t* status,
+// per-kernel occupancy choice "abc" (digits 2..4 for K1a, K1b, K1c), e.g. KZGB_K1_MINB=433
+void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, Fp* out_pts, Fp* tmp, uint8_t* status,
                        uint32_t* counters) {
     if (!n) return;
-    size_t blocks = (2 * n + 127) / 128;
-    static const int minb = [] { const char* e = getenv("KZGB_K1_MINB"); return e ? atoi(e) : 2; }();
-    if (minb >= 4) k_decompress<4><<<(unsigned)blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
-    else if (minb == 3) k_decompress<3><<<(unsigned)blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
-    else k_decompress<2><<<(unsigned)blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
-    KZ_COUNT_LAUNCH();
+    static const int cfg = [] { const char* e = getenv("KZGB_K1_MINB"); int v = e ? atoi(e) : 222; return (v >= 222 && v <= 444) ? v : 222; }();
+    const int ma = cfg / 100, mb = cfg / 10 % 10, mc = cfg % 10;
+    unsigned blocks = (unsigned)((2 * n + 127) / 128);
+    if (ma >= 4) k_decompress_sqrt<4><<<blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
+    else if (ma == 3) k_decompress_sqrt<3><<<blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
+    else k_decompress_sqrt<2><<<blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
+    if (mb >= 4) k_subgroup_chain1<4><<<blocks, 128, 0, s>>>(out_pts, 2 * n, tmp);
+    else if (mb == 3) k_subgroup_chain1<3><<<blocks, 128, 0, s>>>(out_pts, 2 * n, tmp);
+    else k_subgroup_chain1<2><<<blocks, 128, 0, s>>>(out_pts, 2 * n, tmp);
+    if (mc >= 4) k_subgroup_chain2<4><<<blocks, 128, 0, s>>>(out_pts, 2 * n, tmp, status, counters);
+    else if (mc == 3) k_subgroup_chain2<3><<<blocks, 128, 0, s>>>(out_pts, 2 * n, tmp, status, counters);
+    else k_subgroup_chain2<2><<<blocks, 128, 0, s>>>(out_pts, 2 * n, tmp, status, counters);
+    KZ_COUNT_LAUNCH(); KZ_COUNT_LAUNCH(); KZ_COUNT_LAUNCH();
 }
 
 // ---- conversions between device Montgomery affine and canonical big-endian bytes
@@ -142,20 +198,21 @@ void launch_debug_op(cudaStream_t s, int op, const uint8_t* in, uint8_t* out, si
 
 // ---- integer multiply-add issue-rate microbenchmarks (roofline denominators, measured on the box).
 // mode 0: carry-chained mad.lo.cc/madc.hi.cc pairs -> IMAD.WIDE.U32.X, the instruction every Montgomery
-//         product in this library is made of (32 independent 8-pair chains per loop trip and thread);
+//         product in this library is made of (8 independent 16-long chains per loop trip and thread);
 // mode 1: plain 32-bit mad.lo.u32 -> IMAD (the pipe's nominal issue rate).
 // Multiplicands are loop-carried registers so ptxas cannot hoist the products out of the loop.
 // Each loop trip issues 128 multiply-adds per thread in both modes.
-__global__ void k_imad_bench(u32* sink, int iters, int mode) {
+template <int MODE>
+__global__ void k_imad_bench(u32* sink, int iters) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     u32 y = (t * 2654435761u) | 1;
     u32 r[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) r[i] = t + i;
-    if (mode == 0) {
-        for (int it = 0; it < iters; ++it) {
+    for (int it = 0; it < iters; ++it) {
+        if (MODE == 0) {
 #pragma unroll
-            for (int rep = 0; rep < 4; ++rep) {
+            for (int rep = 0; rep < 2; ++rep) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     u32* q = &r[8 * c];
@@ -163,14 +220,16 @@ __global__ void k_imad_bench(u32* sink, int iters, int mode) {
                         "mad.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
                         "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
                         "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+                        "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
+                        "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+                        "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
+                        "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
                         "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.u32 %7,%8,%9,%7;"
                         : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7])
                         : "r"(r[(8 * c + 9) & 31]), "r"(y));
                 }
             }
-        }
-    } else {
-        for (int it = 0; it < iters; ++it) {
+        } else {
 #pragma unroll
             for (int rep = 0; rep < 4; ++rep) {
 #pragma unroll
@@ -184,6 +243,7 @@ __global__ void k_imad_bench(u32* sink, int iters, int mode) {
     if (z == 0x23456789u) sink[0] = z;      // practically never; keeps the chains alive
 }
 void launch_imad_bench(cudaStream_t s, uint32_t* sink, int blocks, int threads, int iters, int mode) {
-    k_imad_bench<<<blocks, threads, 0, s>>>(sink, iters, mode);
+    if (mode == 0) k_imad_bench<0><<<blocks, threads, 0, s>>>(sink, iters);
+    else k_imad_bench<1><<<blocks, threads, 0, s>>>(sink, iters);
     KZ_COUNT_LAUNCH();
 }

@@ -15,7 +15,8 @@ extern std::atomic<uint64_t> g_kzgb_launches;      // counts every kernel launch
 // ---- k_decompress.cu
 // points [0,n): from inC, [n,2n): from inPi (48 B compressed each).  out_pts: 2 Fp per point (Montgomery
 // affine, (0,0) = infinity/invalid).  counters[0] += number of points with status != 0.
-void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, Fp* out_pts, uint8_t* status,
+// tmp: 3 Fp per point of scratch (Jacobian [|x|]P between the two subgroup-check kernels).
+void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, Fp* out_pts, Fp* tmp, uint8_t* status,
                        uint32_t* counters);
 void launch_points_to_be(cudaStream_t s, const Fp* pts, size_t m, uint8_t* out96);           // canonical x||y
 void launch_points_from_be(cudaStream_t s, const uint8_t* in96, size_t m, Fp* pts, uint32_t* counters);
