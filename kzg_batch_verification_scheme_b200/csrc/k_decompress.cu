@@ -202,48 +202,58 @@ void launch_debug_op(cudaStream_t s, int op, const uint8_t* in, uint8_t* out, si
 // mode 1: plain 32-bit mad.lo.u32 -> IMAD (the pipe's nominal issue rate).
 // Multiplicands are loop-carried registers so ptxas cannot hoist the products out of the loop.
 // Each loop trip issues 128 multiply-adds per thread in both modes.
-template <int MODE>
-__global__ void k_imad_bench(u32* sink, int iters) {
+__global__ void k_imad_wide_bench(u32* sink, int iters) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     u32 y = (t * 2654435761u) | 1;
     u32 r[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = t + i;
+    for (int i = 0; i < 32; i++) r[i] = t + i;
     for (int it = 0; it < iters; ++it) {
-        if (MODE == 0) {
 #pragma unroll
-            for (int rep = 0; rep < 2; ++rep) {
+        for (int rep = 0; rep < 2; rep++) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    u32* q = &r[8 * c];
-                    asm volatile(
-                        "mad.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
-                        "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
-                        "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
-                        "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
-                        "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
-                        "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
-                        "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
-                        "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.u32 %7,%8,%9,%7;"
-                        : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7])
-                        : "r"(r[(8 * c + 9) & 31]), "r"(y));
-                }
-            }
-        } else {
-#pragma unroll
-            for (int rep = 0; rep < 4; ++rep) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) asm volatile("mad.lo.u32 %0,%1,%2,%0;" : "+r"(r[i]) : "r"(r[(i + 1) & 31]), "r"(y));
+            for (int c = 0; c < 4; c++) {
+                u32* q = &r[8 * c];
+                asm volatile(
+                    "mad.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+                    "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
+                    "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+                    "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
+                    "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+                    "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
+                    "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+                    "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.u32 %7,%8,%9,%7;"
+                    : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7])
+                    : "r"(r[(8 * c + 9) & 31]), "r"(y)
+                    : "memory");                     // keep each 16-long chain contiguous in the schedule
             }
         }
     }
     u32 z = 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) z ^= r[i];
+    for (int i = 0; i < 32; i++) z ^= r[i];
     if (z == 0x23456789u) sink[0] = z;      // practically never; keeps the chains alive
 }
+__global__ void k_imad32_bench(u32* sink, int iters) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 y = (t * 2654435761u) | 1;
+    u32 r[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) r[i] = t + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 4; rep++) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) asm volatile("mad.lo.u32 %0,%1,%2,%0;" : "+r"(r[i]) : "r"(r[(i + 1) & 31]), "r"(y));
+        }
+    }
+    u32 z = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) z ^= r[i];
+    if (z == 0x23456789u) sink[0] = z;
+}
 void launch_imad_bench(cudaStream_t s, uint32_t* sink, int blocks, int threads, int iters, int mode) {
-    if (mode == 0) k_imad_bench<0><<<blocks, threads, 0, s>>>(sink, iters);
-    else k_imad_bench<1><<<blocks, threads, 0, s>>>(sink, iters);
+    if (mode == 0) k_imad_wide_bench<<<blocks, threads, 0, s>>>(sink, iters);
+    else k_imad32_bench<<<blocks, threads, 0, s>>>(sink, iters);
     KZ_COUNT_LAUNCH();
 }
