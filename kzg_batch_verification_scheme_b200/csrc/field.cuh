@@ -8,8 +8,8 @@
 #include "mont_gen.cuh"
 #endif
 
-struct Fp { u32 v[12]; };
-struct Fr { u32 v[8]; };
+struct alignas(16) Fp { u32 v[12]; };     // 16-byte aligned: 128-bit loads/stores for global, shared and local copies
+struct alignas(16) Fr { u32 v[8]; };
 
 #if defined(KZGB_EMU)
 // ---- portable limb loops (host emulation of the PTX blocks; tests only)

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128, MINB) k_subgroup_chain2(Fp* __restrict__ 
 void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, Fp* out_pts, Fp* tmp, uint8_t* status,
                        uint32_t* counters) {
     if (!n) return;
-    static const int cfg = [] { const char* e = getenv("KZGB_K1_MINB"); int v = e ? atoi(e) : 222; return (v >= 222 && v <= 444) ? v : 222; }();
+    static const int cfg = [] { const char* e = getenv("KZGB_K1_MINB"); int v = e ? atoi(e) : 322; return (v >= 222 && v <= 444) ? v : 322; }();
     const int ma = cfg / 100, mb = cfg / 10 % 10, mc = cfg % 10;
     unsigned blocks = (unsigned)((2 * n + 127) / 128);
     if (ma >= 4) k_decompress_sqrt<4><<<blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);

@@ -4,7 +4,7 @@
 // group additions themselves run here so that the product library holds no host-side field code).
 #include "kernels.h"
 
-#define KZ_PAIR_THREADS 96
+#define KZ_PAIR_THREADS 128            // 4 warps = one per SM sub-partition; the widest phase uses 108 threads
 
 // cold helpers kept out of line to bound code size
 __device__ __noinline__ G1Aff d_jac_to_aff(const G1Jac& p) { return jac_to_aff(p); }

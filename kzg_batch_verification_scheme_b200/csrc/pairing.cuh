@@ -152,31 +152,50 @@ struct PairScratch {
     Fp12 f, a, b, c, t;          // working values
     Fp12 l0, l1;                 // sparse line values (entries 0, 2, 3 only)
     Fp2 prod[36];
+    Fp kar[36][3];               // Karatsuba parts of the 36 partial products
+    Fp fold[12][3];              // partial folds
     Fp pz3[2], pxz[2], py[2];    // per-pair  Z^3, X*Z, Y
     int pinf[2];
     int result;
 };
 
+// dst = x * y.  Four short phases, every thread does at most ONE Fp product:
+//   P1 108 threads: Karatsuba parts of the 36 Fp2 partial products  v0 = a0 b0, v1 = a1 b1, v2 = (a0+a1)(b0+b1)
+//   P2  72 threads: real / imaginary part of each partial product   c0 = v0 - v1, c1 = v2 - v0 - v1
+//   P3  36 threads: three partial folds per output coefficient (w^6 = xi = 1+u)
+//   P4  12 threads: final sum.  dst may alias x or y.
 KZ_COLD void coop_mul(PairScratch& S, Fp12& dst, const Fp12& x, const Fp12& y) {
-    COOP_FOR(t, 72) {
-        int q = t >> 1, i = q / 6, j = q % 6;
-        Fp a0 = x.c[i].c0, a1 = x.c[i].c1, b0 = y.c[j].c0, b1 = y.c[j].c1;
-        if ((t & 1) == 0) S.prod[q].c0 = fp_sub(fp_mul(a0, b0), fp_mul(a1, b1));
-        else S.prod[q].c1 = fp_add(fp_mul(a0, b1), fp_mul(a1, b0));
+    COOP_FOR(t, 108) {
+        int q = t / 3, part = t - 3 * q, i = q / 6, j = q - 6 * i;
+        Fp v;
+        if (part == 0) v = fp_mul(x.c[i].c0, y.c[j].c0);
+        else if (part == 1) v = fp_mul(x.c[i].c1, y.c[j].c1);
+        else v = fp_mul(fp_add(x.c[i].c0, x.c[i].c1), fp_add(y.c[j].c0, y.c[j].c1));
+        S.kar[q][part] = v;
     }
     COOP_SYNC();
-    COOP_FOR(t, 12) {
-        int k = t >> 1, h = t & 1;
+    COOP_FOR(t, 72) {
+        int q = t >> 1;
+        if ((t & 1) == 0) S.prod[q].c0 = fp_sub(S.kar[q][0], S.kar[q][1]);
+        else S.prod[q].c1 = fp_sub(fp_sub(S.kar[q][2], S.kar[q][0]), S.kar[q][1]);
+    }
+    COOP_SYNC();
+    COOP_FOR(t, 36) {
+        int o = t / 3, s = t - 3 * o, k = o >> 1, h = o & 1;
         Fp lo = fp_zero(), h0 = fp_zero(), h1 = fp_zero();
-        for (int i = 0; i < 6; ++i) {
+        for (int i = s; i < 6; i += 3) {
             int j = k - i;
             if (j >= 0 && j < 6) lo = fp_add(lo, h ? S.prod[i * 6 + j].c1 : S.prod[i * 6 + j].c0);
             j = k + 6 - i;
             if (j >= 0 && j < 6) { h0 = fp_add(h0, S.prod[i * 6 + j].c0); h1 = fp_add(h1, S.prod[i * 6 + j].c1); }
         }
         // xi * (h0 + h1 u) = (h0 - h1) + (h0 + h1) u
-        Fp r = h ? fp_add(lo, fp_add(h0, h1)) : fp_add(lo, fp_sub(h0, h1));
-        if (h) dst.c[k].c1 = r; else dst.c[k].c0 = r;
+        S.fold[o][s] = h ? fp_add(lo, fp_add(h0, h1)) : fp_add(lo, fp_sub(h0, h1));
+    }
+    COOP_SYNC();
+    COOP_FOR(t, 12) {
+        Fp r = fp_add(fp_add(S.fold[t][0], S.fold[t][1]), S.fold[t][2]);
+        if (t & 1) dst.c[t >> 1].c1 = r; else dst.c[t >> 1].c0 = r;
     }
     COOP_SYNC();
 }

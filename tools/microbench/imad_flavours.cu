@@ -60,6 +60,51 @@ template<int MODE> __global__ void k(u32* sink, int iters){
         asm volatile("mad.wide.u32 %0,%1,%2,%0;":"+l"(a6):"r"((u32)a7),"r"(y)); asm volatile("addc.cc.u32 %0,%0,%1;":"+r"(r[6]):"r"(x));
         asm volatile("mad.wide.u32 %0,%1,%2,%0;":"+l"(a7):"r"((u32)a0),"r"(y)); asm volatile("addc.u32 %0,%0,%1;":"+r"(r[7]):"r"(x));
       }
+    } else if (MODE==7 || MODE==8){ // 8 chains of 16 wide mads per trip = 128; MODE 7 links them through the carry flag
+      #pragma unroll
+      for(int rep=0;rep<2;rep++){
+        if (MODE==7) asm volatile("add.cc.u32 %0,%0,0;":"+r"(r[0]));      // defines CF (=0) for the first link
+      #pragma unroll
+      for(int c=0;c<4;c++){
+        u32* q=&r[8*c];
+        if (MODE==7) asm volatile(
+            "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+            "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
+            "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+            "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
+            :"+r"(q[0]),"+r"(q[1]),"+r"(q[2]),"+r"(q[3]),"+r"(q[4]),"+r"(q[5]),"+r"(q[6]),"+r"(q[7]):"r"(r[(8*c+9)&31]),"r"(y));
+        else asm volatile(
+            "mad.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+            "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
+            "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+            "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
+            :"+r"(q[0]),"+r"(q[1]),"+r"(q[2]),"+r"(q[3]),"+r"(q[4]),"+r"(q[5]),"+r"(q[6]),"+r"(q[7]):"r"(r[(8*c+9)&31]),"r"(y));
+      }}
+    } else if (MODE==9 || MODE==10){ // 64 wide mads + 64 (or 128) independent ALU ops (xor/add on other registers)
+      u32 e0=r[16],e1=r[17],e2=r[18],e3=r[19],e4=r[20],e5=r[21],e6=r[22],e7=r[23];
+      #pragma unroll
+      for(int rep=0;rep<2;rep++){
+      #pragma unroll
+      for(int c=0;c<2;c++){
+        u32* q=&r[8*c];
+        #pragma unroll
+        for(int h2=0;h2<2;h2++){
+        asm volatile(
+            "mad.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+            "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.cc.u32 %7,%8,%9,%7;"
+            "madc.lo.cc.u32 %0,%8,%9,%0; madc.hi.cc.u32 %1,%8,%9,%1; madc.lo.cc.u32 %2,%8,%9,%2; madc.hi.cc.u32 %3,%8,%9,%3;"
+            "madc.lo.cc.u32 %4,%8,%9,%4; madc.hi.cc.u32 %5,%8,%9,%5; madc.lo.cc.u32 %6,%8,%9,%6; madc.hi.u32 %7,%8,%9,%7;"
+            :"+r"(q[0]),"+r"(q[1]),"+r"(q[2]),"+r"(q[3]),"+r"(q[4]),"+r"(q[5]),"+r"(q[6]),"+r"(q[7]):"r"(r[24+c]),"r"(y));
+        #pragma unroll
+        for(int z2=0; z2<(MODE==9?1:2); z2++){
+          asm volatile("xor.b32 %0,%0,%1; add.u32 %2,%2,%3; xor.b32 %4,%4,%5; add.u32 %6,%6,%7;":"+r"(e0),"+r"(e1),"+r"(e2),"+r"(e3),"+r"(e4),"+r"(e5),"+r"(e6),"+r"(e7));
+          asm volatile("add.u32 %0,%0,%1; xor.b32 %2,%2,%3; add.u32 %4,%4,%5; xor.b32 %6,%6,%7;":"+r"(e1),"+r"(e2),"+r"(e3),"+r"(e4),"+r"(e5),"+r"(e6),"+r"(e7),"+r"(e0));
+          asm volatile("xor.b32 %0,%0,%1; add.u32 %2,%2,%3; xor.b32 %4,%4,%5; add.u32 %6,%6,%7;":"+r"(e0),"+r"(e1),"+r"(e2),"+r"(e3),"+r"(e4),"+r"(e5),"+r"(e6),"+r"(e7));
+          asm volatile("add.u32 %0,%0,%1; xor.b32 %2,%2,%3; add.u32 %4,%4,%5; xor.b32 %6,%6,%7;":"+r"(e1),"+r"(e2),"+r"(e3),"+r"(e4),"+r"(e5),"+r"(e6),"+r"(e7),"+r"(e0));
+        }
+        }
+      }}
+      r[16]=e0;r[17]=e1;r[18]=e2;r[19]=e3;r[20]=e4;r[21]=e5;r[22]=e6;r[23]=e7;
     } else if (MODE==5){ // DFMA: 8 chains x 16
       double d0=__longlong_as_double(a0|0x3ff0000000000000ull),d1=d0+1,d2=d0+2,d3=d0+3,d4=d0+4,d5=d0+5,d6=d0+6,d7=d0+7;
       double fx=1.0000001, fy=1e-9;
@@ -102,4 +147,8 @@ int main(){ int sms; cudaDeviceGetAttribute(&sms,cudaDevAttrMultiProcessorCount,
   run<4>("mad.wide + add.cc chain interleaved (64 imad)",64,sms);
   run<5>("DFMA",128,sms);
   run<6>("mad.wide + DFMA interleaved (64 imad+64 dfma)",128,sms);
+  run<7>("IMAD.WIDE.X, 4 chains LINKED via carry flag",64,sms);
+  run<8>("IMAD.WIDE.X, 4 chains independent asm blocks",64,sms);
+  run<9>("IMAD.WIDE.X 64 + 64 independent ALU ops (wide/s)",64,sms);
+  run<10>("IMAD.WIDE.X 64 + 128 independent ALU ops (wide/s)",64,sms);
   return 0; }
