@@ -212,7 +212,8 @@ def check_sqr(n, mod, trials=300):
     rinv = pow(1 << (32 * n), -1, mod)
     edge = [0, 1, 2, mod - 1, mod - 2, (1 << (32 * n)) % mod, mod >> 1, (1 << (32 * n - 3)) - 1,
             sum(0xFFFFFFFF << (64 * k) for k in range(n // 2)) % mod]
-    for x in edge + [rnd.randrange(mod) for _ in range(trials)]:
+    lazy = 4 * mod < (1 << (32 * n))
+    for x in edge + ([mod, mod + 1, 2 * mod - 1] if lazy else []) + [rnd.randrange(2 * mod if lazy else mod) for _ in range(trials)]:
         env = {a[k]: limbs(x, n)[k] for k in range(n)}
         simulate(pg, env)
         got = sum(env[out[k]] << (32 * k) for k in range(n))
@@ -337,6 +338,27 @@ def emit_addsub_fns(prefix, n, mod):
     return "\n".join(out)
 
 
+def check_addsub_lazy(n, mod, trials=300):
+    """add/sub generated for the modulus 2p, operands in [0, 2p): results in [0, 2p) and correct mod p."""
+    rnd = random.Random(200 + n)
+    m2 = 2 * mod
+    edge = [0, 1, mod - 1, mod, mod + 1, m2 - 1, m2 - 2]
+    cases = [(x, y) for x in edge for y in edge] + [(rnd.randrange(m2), rnd.randrange(m2)) for _ in range(trials)]
+    for x, y in cases:
+        env = {}
+        for k in range(n):
+            env[f"a{k}"] = limbs(x, n)[k]
+            env[f"b{k}"] = limbs(y, n)[k]
+        e = simulate(gen_add(n, m2), dict(env))
+        r = sum(e[f"r{k}"] << (32 * k) for k in range(n)); t = sum(e[f"t{k}"] << (32 * k) for k in range(n))
+        got = r if e["bw"] else t
+        assert got < m2 and got % mod == (x + y) % mod
+        e = simulate(gen_sub(n, m2), dict(env))
+        r = sum(e[f"r{k}"] << (32 * k) for k in range(n)); t = sum(e[f"t{k}"] << (32 * k) for k in range(n))
+        got = t if e["bw"] else r
+        assert got < m2 and got % mod == (x - y) % mod
+
+
 def check_addsub(n, mod, trials=300):
     rnd = random.Random(100 + n)
     edge = [0, 1, mod - 1, mod - 2, mod >> 1, (mod >> 1) + 1]
@@ -366,8 +388,10 @@ def check_mul(n, mod, trials=300):
     out = [f"r{k}" for k in range(n)]
     pg, _ = gen_mul(n, mod, a, b, out)
     rinv = pow(1 << (32 * n), -1, mod)
-    edge = [0, 1, mod - 1, mod - 2, (1 << (32 * n)) % mod, mod >> 1]
-    cases = [(x, y) for x in edge for y in edge] + [(rnd.randrange(mod), rnd.randrange(mod)) for _ in range(trials)]
+    lazy = 4 * mod < (1 << (32 * n))          # operands may live in [0, 2p) when the modulus has >= 2 spare bits
+    top = 2 * mod if lazy else mod
+    edge = [0, 1, mod - 1, mod - 2, (1 << (32 * n)) % mod, mod >> 1] + ([mod, mod + 1, 2 * mod - 1] if lazy else [])
+    cases = [(x, y) for x in edge for y in edge] + [(rnd.randrange(top), rnd.randrange(top)) for _ in range(trials)]
     for x, y in cases:
         env = {}
         for k in range(n):
@@ -388,6 +412,7 @@ def main():
     n2 = check_mul(8, R)
     check_addsub(12, P)
     check_addsub(8, R)
+    check_addsub_lazy(12, P)
     ns, nim = check_sqr(12, P)
     check_sqr(8, R)
     if args.selftest:
@@ -396,7 +421,8 @@ def main():
     txt = ["// GENERATED by tools/gen_mont.py -- do not edit.  Inline-PTX Montgomery products (sm_100a).",
            "#pragma once", "#include <cstdint>", "",
            emit_mul_fn("fp_mont_mul_ptx", 12, P), emit_mul_fn("fr_mont_mul_ptx", 8, R), emit_sqr_fn("fp_mont_sqr_ptx", 12, P),
-           emit_addsub_fns("fp", 12, P), emit_addsub_fns("fr", 8, R)]
+           emit_addsub_fns("fp", 12, P), emit_addsub_fns("fr", 8, R),
+           "// lazy domain: operands and results in [0, 2p) (modulus 2p)\n" + emit_addsub_fns("fp2p", 12, 2 * P)]
     Path(args.o).write_text("\n".join(txt))
     print(f"wrote {args.o}: fp_mul {n1} instrs, fr_mul {n2} instrs")
 
