@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <chrono>
 #include <new>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/kzgb200.h"
@@ -34,12 +35,12 @@ struct DeviceSlot {
     cudaStream_t stream2 = nullptr;    // high-priority side stream: hashes, challenges and sorts overlap K1
     // staged inputs (host-pointer API)
     uint8_t *dC = nullptr, *dz = nullptr, *dy = nullptr, *dpi = nullptr;
-    Fp* pts = nullptr;                 // 2*n_max + 1 affine points: C | pi | G
+    Fp* pts = nullptr;                 // 3*n_max + 2 affine points: C | pi | G | phi(pi) | phi(G)
     Fp* k1_tmp = nullptr;              // 3 Fp per point: [|x|]P between the subgroup-check kernels
     uint8_t* status = nullptr;         // 2*n_max
     uint32_t* counters = nullptr;      // [0] bad points [1] bad scalars
     uint32_t *leaves = nullptr, *digests = nullptr, *root_words = nullptr;
-    uint32_t *r = nullptr, *rz = nullptr, *partials = nullptr, *sum_ry = nullptr;
+    uint32_t *r = nullptr, *rz = nullptr, *zs = nullptr, *partials = nullptr, *sum_ry = nullptr;   // zs: GLV halves of rz
     SortBuf sortR, sortZ;
     G1Xyzz *bucketsA = nullptr, *bucketsB = nullptr, *bucketsC = nullptr, *segsums = nullptr, *winsums = nullptr;
     size_t max_bucketsR = 0, max_bucketsZ = 0, max_segs = 0;
@@ -101,20 +102,31 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     }
     for (auto& e : s.ev) CK(cudaEventCreate(&e));
     CK(dmalloc(s.dC, 48 * (n_max + 1))); CK(dmalloc(s.dz, 32 * (n_max + 1))); CK(dmalloc(s.dy, 32 * (n_max + 1))); CK(dmalloc(s.dpi, 48 * (n_max + 1)));
-    CK(dmalloc(s.pts, 2 * (2 * n_max + 2)));
+    CK(dmalloc(s.pts, 2 * (3 * n_max + 4)));
     CK(dmalloc(s.k1_tmp, 3 * (2 * n_max + 2)));
     CK(dmalloc(s.status, 2 * n_max + 2));
     CK(dmalloc(s.counters, 8));
     size_t nch = (n_max + KZGB_CHUNK - 1) / KZGB_CHUNK;
     CK(dmalloc(s.leaves, 8 * n_max)); CK(dmalloc(s.digests, 8 * nch)); CK(dmalloc(s.root_words, 8));
-    CK(dmalloc(s.r, 4 * n_max)); CK(dmalloc(s.rz, 8 * (n_max + 1)));
+    CK(dmalloc(s.r, 4 * n_max)); CK(dmalloc(s.rz, 8 * (n_max + 1))); CK(dmalloc(s.zs, 4 * 2 * (n_max + 1)));
     CK(dmalloc(s.partials, 8 * ((n_max + 127) / 128 + 1))); CK(dmalloc(s.sum_ry, 8));
-    MsmPlan pr = msm_make_plan(n_max, 128), pz = msm_make_plan(n_max + 1, 255);
-    s.max_bucketsR = pr.total_buckets;
-    s.max_bucketsZ = pz.total_buckets;
-    s.max_segs = pz.total_segs > pr.total_segs ? pz.total_segs : pr.total_segs;
-    // small n use narrower windows (more of them): keep generous floors so every n <= n_max fits
-    size_t capR = (size_t)pr.W * n_max + 4096, capZ = (size_t)pz.W * (n_max + 1) + 8192;
+    // the 255-bit sum is GLV-split into 2(n+1) 128-bit scalars.  Window widths depend on n (msm_make_plan),
+    // so size every workspace for the worst case over batch sizes up to n_max
+    size_t capR = 0, capZ = 0;
+    s.max_bucketsR = s.max_bucketsZ = s.max_segs = 0;
+    for (int k = 1; k <= 64; ++k) {
+        size_t nn = n_max * (size_t)k / 64;
+        if (nn < 1) nn = 1;
+        MsmPlan pr = msm_make_plan(nn, 128), pz = msm_make_plan(2 * (nn + 1), 128);
+        capR = std::max(capR, (size_t)pr.W * nn);
+        capZ = std::max(capZ, (size_t)pz.W * 2 * (nn + 1));
+        s.max_bucketsR = std::max(s.max_bucketsR, (size_t)pr.total_buckets);
+        s.max_bucketsZ = std::max(s.max_bucketsZ, (size_t)pz.total_buckets);
+        s.max_segs = std::max(s.max_segs, (size_t)std::max(pr.total_segs, pz.total_segs));
+    }
+    capR += capR / 8 + 4096;
+    capZ += capZ / 8 + 8192;
+    s.max_bucketsR += 4096; s.max_bucketsZ += 4096; s.max_segs += 4096;
     if (slot_alloc_sort(s.sortR, capR, s.max_bucketsR + 512)) return KZGB_ERROR;
     if (slot_alloc_sort(s.sortZ, capZ, s.max_bucketsZ + 512)) return KZGB_ERROR;
     CK(dmalloc(s.bucketsA, s.max_bucketsR + 512)); CK(dmalloc(s.bucketsB, s.max_bucketsR + 512));
@@ -155,7 +167,7 @@ void slot_free(DeviceSlot& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     if (s.stream2) cudaStreamSynchronize(s.stream2);
     void* dev[] = {s.dC, s.dz, s.dy, s.dpi, s.pts, s.k1_tmp, s.status, s.counters, s.leaves, s.digests, s.root_words, s.r, s.rz,
-                   s.partials, s.sum_ry, s.sortR.keys, s.sortR.vals, s.sortR.keys_alt, s.sortR.vals_alt, s.sortR.bucket_start,
+                   s.partials, s.sum_ry, s.zs, s.sortR.keys, s.sortR.vals, s.sortR.keys_alt, s.sortR.vals_alt, s.sortR.bucket_start,
                    s.sortZ.keys, s.sortZ.vals, s.sortZ.keys_alt, s.sortZ.vals_alt, s.sortZ.bucket_start, s.bucketsA,
                    s.bucketsB, s.bucketsC, s.segsums, s.winsums, s.cub_temp, s.sums, s.partial_dev, s.partials_in,
                    s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb, s.recs.head, s.recs.tail,
@@ -219,6 +231,9 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
     CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, s2));
     CK(cudaEventRecord(s.ev[2], s2));
     launch_decompress(st, s.cur_C, s.cur_pi, n, s.pts, s.k1_tmp, s.status, s.counters);
+    // the setup point G joins the GLV-split sum with scalar -(sum r_i y_i): point slot 2n; then phi(pi_i), phi(G)
+    CK(cudaMemcpyAsync(s.pts + 2 * (2 * n), s.g1_pt, 2 * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    launch_endo_points(st, s.pts + 2 * n, n + 1, s.pts + 2 * (2 * n + 1));
     CK(cudaEventRecord(s.ev[3], st));
     CK(cudaEventSynchronize(s.ev[2]));
     words_to_be(digests_out, (const uint32_t*)s.h_digests, 8 * nch);
@@ -236,18 +251,17 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     be_to_words(s.h_small + 8, root, 8);
     CK(cudaMemcpyAsync(s.root_words, s.h_small + 8, 32, cudaMemcpyHostToDevice, s2));
     launch_challenges(s2, s.root_words, global_offset, s.cur_z, s.cur_y, n, single ? 1 : 0, s.r, s.rz, s.partials, s.sum_ry);
-    // the setup point G joins the 255-bit sum with scalar -(sum r_i y_i): point slot 2n
-    CK(cudaMemcpyAsync(s.pts + 2 * (2 * n), s.g1_pt, 2 * sizeof(Fp), cudaMemcpyDeviceToDevice, s2));
+    launch_glv_split(s2, s.rz, n + 1, s.zs);       // r_i z_i and -(sum r_i y_i) -> 2(n+1) 128-bit scalars
     CK(cudaEventRecord(s.ev[4], s2));
     s.planR = msm_make_plan(n, 128);
-    s.planZ = msm_make_plan(n + 1, 255);
-    if ((size_t)s.planR.W * n > s.sortR.capacity || (size_t)s.planZ.W * (n + 1) > s.sortZ.capacity ||
+    s.planZ = msm_make_plan(2 * (n + 1), 128);
+    if ((size_t)s.planR.W * n > s.sortR.capacity || (size_t)s.planZ.W * 2 * (n + 1) > s.sortZ.capacity ||
         s.planR.total_buckets > s.max_bucketsR + 512 || s.planZ.total_buckets > s.max_bucketsZ + 512 ||
         s.planZ.total_segs > s.max_segs + 512 || s.planR.total_segs > s.max_segs + 512)
         return KZGB_BADARGS;
     MsmWorkspace wr = make_ws(s, s.sortR, s.bucketsA), wz = make_ws(s, s.sortZ, s.bucketsC);
     msm_sort_stage(s2, s.planR, s.r, 4, n, wr);
-    msm_sort_stage(s2, s.planZ, s.rz, 8, n + 1, wz);
+    msm_sort_stage(s2, s.planZ, s.zs, 4, 2 * (n + 1), wz);
     save_ws(s.sortR, wr); save_ws(s.sortZ, wz);
     CK(cudaEventRecord(s.ev[5], s2));
     CK(cudaStreamWaitEvent(st, s.ev[5], 0));
@@ -255,7 +269,7 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     wr2.buckets = s.bucketsB;
     msm_accumulate_stage(st, s.planR, s.pts, n, wr);                 // S1 over C_i
     msm_accumulate_stage(st, s.planR, s.pts + 2 * n, n, wr2);        // S3 over pi_i
-    msm_accumulate_stage(st, s.planZ, s.pts + 2 * n, n + 1, wz);     // S2' over pi_i and G
+    msm_accumulate_stage(st, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);     // S2' over pi_i, G and their phi images
     CK(cudaEventRecord(s.ev[6], st));
     wr2.segsums = s.segsums + (s.max_segs + 512); wr2.winsums = s.winsums + KZ_MSM_MAX_WINDOWS;
     wz.segsums = s.segsums + 2 * (s.max_segs + 512); wz.winsums = s.winsums + 2 * KZ_MSM_MAX_WINDOWS;
@@ -291,6 +305,21 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0; }
     return ms;
+}
+
+// stages overlap (side stream): hash/challenges/sort are measured on the side stream, decompress and the
+// rest on the main stream; "accumulate" starts when K1 has finished.  Valid after the slot's streams synced.
+void fill_stage_ms(kzgb_artifacts& art, DeviceSlot& s0, float root_ms) {
+    art.stage_ms[0] = ev_ms(s0.ev[0], s0.ev[1]);
+    art.stage_ms[2] = ev_ms(s0.ev[1], s0.ev[2]);
+    art.stage_ms[1] = ev_ms(s0.ev[1], s0.ev[3]);
+    art.stage_ms[3] = root_ms;
+    art.stage_ms[4] = ev_ms(s0.ev[2], s0.ev[4]);
+    art.stage_ms[5] = ev_ms(s0.ev[4], s0.ev[5]);
+    art.stage_ms[6] = ev_ms(s0.ev[3], s0.ev[6]);
+    art.stage_ms[7] = ev_ms(s0.ev[6], s0.ev[7]);
+    art.stage_ms[8] = 0;
+    art.stage_ms[9] = ev_ms(s0.ev[0], s0.ev[7]);
 }
 
 kzgb_ret verify_common(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
@@ -345,16 +374,7 @@ kzgb_ret verify_common(bool* ok, const uint8_t* C, const uint8_t* z, const uint8
     kzgb_ret rc = combine(s0, parts.data(), (int)G, ok);
     if (rc) return rc;
     if (G > 1) s0.have_sums = false;
-    // stages overlap (side stream): hash/challenges/sort are measured on the side stream, decompress and
-    // the rest on the main stream; "accumulate" starts when K1 has finished
-    art.stage_ms[0] = ev_ms(s0.ev[0], s0.ev[1]);
-    art.stage_ms[2] = ev_ms(s0.ev[1], s0.ev[2]);
-    art.stage_ms[1] = ev_ms(s0.ev[1], s0.ev[3]);
-    art.stage_ms[3] = root_ms;
-    art.stage_ms[4] = ev_ms(s0.ev[2], s0.ev[4]);
-    art.stage_ms[5] = ev_ms(s0.ev[4], s0.ev[5]);
-    art.stage_ms[6] = ev_ms(s0.ev[3], s0.ev[6]);
-    art.stage_ms[7] = ev_ms(s0.ev[6], s0.ev[7]);
+    fill_stage_ms(art, s0, root_ms);
     art.stage_ms[8] = ev_ms(s0.ev[7], s0.ev[8]);
     art.stage_ms[9] = ev_ms(s0.ev[0], s0.ev[8]);
     return KZGB_OK;
@@ -442,6 +462,7 @@ kzgb_ret kzgb_shard_phase2(kzgb_ctx* ctx, int slot, const uint8_t root[32], uint
     CK(cudaStreamSynchronize(s.stream));
     CK(cudaGetLastError());
     memcpy(partial_out, s.h_partial, KZGB_PARTIAL_BYTES);
+    fill_stage_ms(ctx->art, s, 0.0f);
     ctx->art.n_bad_points = s.h_small[0];
     ctx->art.n_bad_scalars = s.h_small[1];
     return (s.h_small[0] || s.h_small[1]) ? KZGB_BADARGS : KZGB_OK;
@@ -517,17 +538,26 @@ kzgb_ret kzgb_g1_msm(uint8_t affine_out[96], const uint8_t* points_affine, const
     CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), st));
     launch_points_from_be(st, d_pts, m, s.pts, s.counters);
     launch_scalars_from_be(st, d_sc, m, s.rz, s.counters);
-    MsmPlan plan = msm_make_plan(m, nbits);
-    if ((size_t)plan.W * m > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || plan.total_segs > s.max_segs + 512) {
+    // 255-bit scalars are GLV-split: 2m points (P, phi(P)) with 128-bit scalars (k1, k2)
+    const bool glv = nbits == 255;
+    size_t mm = glv ? 2 * m : m;
+    MsmPlan plan = msm_make_plan(mm, 128);
+    if ((size_t)plan.W * mm > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || plan.total_segs > s.max_segs + 512) {
         cudaFree(d_pts); cudaFree(d_sc);
         return KZGB_BADARGS;
     }
     MsmWorkspace ws = make_ws(s, s.sortZ, s.bucketsC);
     CK(cudaEventRecord(s.ev[0], st));
-    msm_sort_stage(st, plan, s.rz, 8, m, ws);
+    if (glv) {
+        launch_glv_split(st, s.rz, m, s.zs);
+        launch_endo_points(st, s.pts, m, s.pts + 2 * m);
+        msm_sort_stage(st, plan, s.zs, 4, mm, ws);
+    } else {
+        msm_sort_stage(st, plan, s.rz, 8, mm, ws);
+    }
     save_ws(s.sortZ, ws);
     CK(cudaEventRecord(s.ev[1], st));
-    msm_accumulate_stage(st, plan, s.pts, m, ws);
+    msm_accumulate_stage(st, plan, s.pts, mm, ws);
     CK(cudaEventRecord(s.ev[2], st));
     msm_reduce_stage(st, plan, ws, s.sums + 0);
     CK(cudaEventRecord(s.ev[3], st));

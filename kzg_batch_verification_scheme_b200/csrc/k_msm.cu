@@ -19,6 +19,35 @@ __global__ void __launch_bounds__(128) k_msm_digits(const u32* __restrict__ scal
     msm_digits_body(keys, vals, sc, i, m, plan);
 }
 
+// GLV preparation of a 255-bit sum: scalars k -> (k1 | k2) as 2m 128-bit scalars, points P -> phi(P)
+__global__ void __launch_bounds__(128) k_glv_split(const u32* __restrict__ scalars8, size_t m, u32* __restrict__ out4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    u32 sc[8], k1[4], k2[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sc[j] = scalars8[8 * i + j];
+    glv_split(sc, k1, k2);
+    reinterpret_cast<uint4*>(out4)[i] = make_uint4(k1[0], k1[1], k1[2], k1[3]);
+    reinterpret_cast<uint4*>(out4)[m + i] = make_uint4(k2[0], k2[1], k2[2], k2[3]);
+}
+__global__ void __launch_bounds__(128) k_endo_points(const Fp* __restrict__ src, size_t m, Fp* __restrict__ dst) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    G1Aff q = g1_endo(load_point(src, i));
+    dst[2 * i] = q.x;
+    dst[2 * i + 1] = q.y;
+}
+void launch_glv_split(cudaStream_t s, const uint32_t* scalars8, size_t m, uint32_t* out4) {
+    if (!m) return;
+    k_glv_split<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(scalars8, m, out4);
+    KZ_COUNT_LAUNCH();
+}
+void launch_endo_points(cudaStream_t s, const Fp* src, size_t m, Fp* dst) {
+    if (!m) return;
+    k_endo_points<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(src, m, dst);
+    KZ_COUNT_LAUNCH();
+}
+
 // start[b] = first sorted position with key >= b, for b in [0, total_buckets+1]
 __global__ void k_bucket_bounds(const u32* __restrict__ keys, size_t N, u32 total_buckets, u32* __restrict__ start) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

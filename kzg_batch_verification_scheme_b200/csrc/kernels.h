@@ -52,6 +52,9 @@ struct MsmWorkspace {
     size_t max_buckets, max_segs;
 };
 size_t msm_cub_temp_bytes(size_t entries);
+// GLV: 255-bit scalars (8 limbs) -> k1 (m x 4 limbs) | k2 (m x 4 limbs); points P -> phi(P) = (beta^2 x, y)
+void launch_glv_split(cudaStream_t s, const uint32_t* scalars8, size_t m, uint32_t* out4);
+void launch_endo_points(cudaStream_t s, const Fp* src, size_t m, Fp* dst);
 uint32_t msm_chunk_len(size_t N);
 // digits + sort + bucket boundaries for `m` scalars of `nl` limbs each
 void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars, int nl, size_t m, MsmWorkspace& ws);

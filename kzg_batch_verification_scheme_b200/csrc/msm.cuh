@@ -23,9 +23,21 @@ inline MsmPlan msm_make_plan(size_t n, int nbits) {
     MsmPlan p;
     int lg = 0;
     while ((size_t(1) << (lg + 1)) <= n) ++lg;
-    int c = lg - 3;
-    if (c < 3) c = 3;
-    if (c > 16) c = 16;
+    int c0 = lg - 3;
+    if (c0 < 3) c0 = 3;
+    if (c0 > 16) c0 = 16;
+    // The top window holds tb = nbits - c(W-1) bits.  A narrow top window means a handful of giant buckets
+    // (2^(c-1-tb) times the average load), which serialises the accumulation; pick, near c0, the cheapest
+    // width whose top-window buckets are at most 8x heavier than the others.
+    int c = c0;
+    double best = -1;
+    for (int cc = c0 - 3; cc <= c0 + 1; ++cc) {
+        if (cc < 3 || cc > 16) continue;
+        int W = (nbits + cc - 1) / cc, tb = nbits - cc * (W - 1);
+        if (cc - 1 - tb > 3) continue;
+        double cost = (double)W * (10.0 * (double)n + 28.0 * (double)(1u << (cc - 1)));
+        if (best < 0 || cost < best) { best = cost; c = cc; }
+    }
     p.nbits = nbits;
     p.c = c;
     p.W = (nbits + c - 1) / c;
@@ -63,6 +75,62 @@ KZ_HD void msm_digits_body(u32* keys, u32* vals, const u32* sc, size_t i, size_t
         vals[(size_t)w * n + i] = (u32)i | (neg << 31);
     }
 }
+
+// GLV split of a canonical scalar k < r:  k = k1 + k2 * lambda  with  k2 = floor(k / lambda), 0 <= k1 < lambda,
+// both below 2^128 (lambda = x^2 - 1, r = lambda^2 + lambda + 1).  phi(P) = (beta^2 x, y) = [lambda]P, so
+// k*P = k1*P + k2*phi(P): a 255-bit sum over m points becomes a 128-bit sum over 2m points -- the same
+// number of bucket additions, half the windows (bucket reductions, Horner doublings).
+// Barrett quotient with mu = floor(2^384 / lambda): q^ = (k * mu) >> 384 is q or q-1.
+KZ_HD void glv_split(const u32* k, u32* k1, u32* k2) {
+    u32 prod[17];
+    for (int i = 0; i < 17; ++i) prod[i] = 0;
+    for (int i = 0; i < 8; ++i) {
+        u64 c = 0;
+        for (int j = 0; j < 9; ++j) {
+            u64 v = (u64)k[i] * GLV_MU[j] + prod[i + j] + c;
+            prod[i + j] = (u32)v;
+            c = v >> 32;
+        }
+        prod[i + 9] = (u32)c;
+    }
+    u32 q[5];
+    for (int i = 0; i < 5; ++i) q[i] = prod[12 + i];
+    // rem = k - q * lambda  (fits in 5 limbs: < 2 lambda)
+    u32 ql[9];
+    for (int i = 0; i < 9; ++i) ql[i] = 0;
+    for (int i = 0; i < 5; ++i) {
+        u64 c = 0;
+        for (int j = 0; j < 4; ++j) {
+            u64 v = (u64)q[i] * GLV_LAMBDA[j] + ql[i + j] + c;
+            ql[i + j] = (u32)v;
+            c = v >> 32;
+        }
+        ql[i + 4] = (u32)c;
+    }
+    u32 rem[5];
+    u64 bw = 0;
+    for (int i = 0; i < 5; ++i) {
+        u64 v = (u64)k[i] - ql[i] - bw;
+        rem[i] = (u32)v;
+        bw = (v >> 32) & 1;
+    }
+    for (int rep = 0; rep < 2; ++rep) {          // at most one correction is ever needed; two for safety
+        u32 t[5];
+        bw = 0;
+        for (int i = 0; i < 5; ++i) {
+            u64 v = (u64)rem[i] - (i < 4 ? GLV_LAMBDA[i] : 0u) - bw;
+            t[i] = (u32)v;
+            bw = (v >> 32) & 1;
+        }
+        if (!bw) {                                // rem >= lambda
+            for (int i = 0; i < 5; ++i) rem[i] = t[i];
+            u64 c = 1;
+            for (int i = 0; i < 5; ++i) { u64 v = (u64)q[i] + c; q[i] = (u32)v; c = v >> 32; }
+        }
+    }
+    for (int i = 0; i < 4; ++i) { k1[i] = rem[i]; k2[i] = q[i]; }
+}
+KZ_HD G1Aff g1_endo(const G1Aff& p) { return {fp_mul(fp_const(FP_BETA2), p.x), p.y}; }   // (0,0) stays (0,0)
 
 KZ_HD G1Aff load_point(const Fp* pts, size_t idx) { return {pts[2 * idx], pts[2 * idx + 1]}; }
 

@@ -31,6 +31,19 @@ static void words_to_be(u8* out, const u32* w, int nw) {
 
 // emulated MSM pipeline: digits -> sort -> bounds -> accumulate -> segments -> window sums -> combine
 static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nbits) {
+    if (nbits == 255) {      // GLV split exactly as the device pipeline does it
+        std::vector<u32> zs(4 * 2 * m);
+        std::vector<Fp> p2(2 * 2 * m);
+        for (size_t i = 0; i < m; ++i) {
+            u32 sc[8];
+            for (int k = 0; k < 8; ++k) sc[k] = k < nl ? scalars[nl * i + k] : 0;
+            glv_split(sc, &zs[4 * i], &zs[4 * (m + i)]);
+            G1Aff p = load_point(pts, i), q = g1_endo(p);
+            p2[2 * i] = p.x; p2[2 * i + 1] = p.y;
+            p2[2 * (m + i)] = q.x; p2[2 * (m + i) + 1] = q.y;
+        }
+        return emu_msm(p2.data(), zs.data(), 4, 2 * m, 128);
+    }
     MsmPlan plan = msm_make_plan(m, nbits);
     size_t N = m * (size_t)plan.W;
     std::vector<u32> keys(N), vals(N);

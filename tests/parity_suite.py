@@ -159,3 +159,51 @@ def check_verify(ctx, oracle, oracle_lib, sizes=(1, 2, 9, 64), seed=0x4B5A4701):
     Cd, Zd, Yd, PId = C[:48] * 6, Z[:32] * 6, Y[:32] * 6, PI[:48] * 6
     assert ctx.verify_kzg_proof_batch(Cd, Zd, Yd, PId, 6) == oracle.verify_kzg_proof_batch(Cd, Zd, Yd, PId, 6) == (0, True)
     assert ctx.last_artifacts()["A"] == oracle.last_artifacts()["A"]
+
+
+def check_degenerate(gpu_ctx, oracle_ctx, n=40):
+    """Infinity points, repeated proofs, zero evaluations: exceptional group-law paths on both sides."""
+    inf = b.g1_compress(None)
+    C, Z, Y, PI = oracle_ctx.synth_instance(0x4B5A4720, 0, n)
+    # (1) every proof identical (all bucket additions are doublings / same-point adds)
+    Cd, Zd, Yd, PId = C[:48] * n, Z[:32] * n, Y[:32] * n, PI[:48] * n
+    assert gpu_ctx.verify_kzg_proof_batch(Cd, Zd, Yd, PId, n) == oracle_ctx.verify_kzg_proof_batch(Cd, Zd, Yd, PId, n) == (0, True)
+    assert gpu_ctx.last_artifacts()["A"] == oracle_ctx.last_artifacts()["A"]
+    # (2) all-infinity commitments and proofs with y = 0 (valid: the zero polynomial)
+    Ci, PIi, Yi = inf * n, inf * n, bytes(32) * n
+    assert gpu_ctx.verify_kzg_proof_batch(Ci, Z, Yi, PIi, n) == oracle_ctx.verify_kzg_proof_batch(Ci, Z, Yi, PIi, n) == (0, True)
+    a1, a2 = gpu_ctx.last_artifacts(), oracle_ctx.last_artifacts()
+    assert a1["A"] == a2["A"] == bytes(96) and a1["B"] == a2["B"] == bytes(96)
+    # (3) same but y != 0 somewhere: A = -(r_j y_j) G1 != O -> reject
+    jj = min(7, n - 1)
+    Yj = bytes(32) * jj + (5).to_bytes(32, "big") + bytes(32) * (n - 1 - jj)
+    assert gpu_ctx.verify_kzg_proof_batch(Ci, Z, Yj, PIi, n) == oracle_ctx.verify_kzg_proof_batch(Ci, Z, Yj, PIi, n) == (0, False)
+    assert gpu_ctx.last_artifacts()["A"] == oracle_ctx.last_artifacts()["A"]
+    # (4) a mix of infinity and regular proofs
+    Cm = inf + C[48:]
+    PIm = inf + PI[48:]
+    Ym = bytes(32) + Y[32:]
+    assert gpu_ctx.verify_kzg_proof_batch(Cm, Z, Ym, PIm, n) == oracle_ctx.verify_kzg_proof_batch(Cm, Z, Ym, PIm, n) == (0, True)
+    assert gpu_ctx.last_artifacts()["A"] == oracle_ctx.last_artifacts()["A"]
+    # (5) P and -P in the same batch positions (commitment negated -> wrong proof, still well-formed)
+    negC0 = bytes([C[0] ^ 0x20]) + C[1:48]
+    Cn = negC0 + C[48:]
+    r1 = gpu_ctx.verify_kzg_proof_batch(Cn, Z, Y, PI, n)
+    assert r1 == oracle_ctx.verify_kzg_proof_batch(Cn, Z, Y, PI, n) == (0, False)
+    assert gpu_ctx.last_artifacts()["A"] == oracle_ctx.last_artifacts()["A"]
+
+
+def check_status_classes(gpu_ctx, oracle_ctx, n=64):
+    """Each malformed class planted into an otherwise valid batch gives BADARGS with the same counts."""
+    rnd = random.Random(5)
+    C, Z, Y, PI = oracle_ctx.synth_instance(0x4B5A4721, 0, n)
+    for enc, st in negative_g1_encodings(rnd):
+        if st == 0:
+            continue
+        j = rnd.randrange(n)
+        for which in ("C", "PI"):
+            Cb = C[:48 * j] + enc + C[48 * j + 48:] if which == "C" else C
+            Pb = PI[:48 * j] + enc + PI[48 * j + 48:] if which == "PI" else PI
+            assert gpu_ctx.verify_kzg_proof_batch(Cb, Z, Y, Pb, n) == oracle_ctx.verify_kzg_proof_batch(Cb, Z, Y, Pb, n) == (1, False)
+            a1, a2 = gpu_ctx.last_artifacts(), oracle_ctx.last_artifacts()
+            assert a1["n_bad_points"] == a2["n_bad_points"] == 1 and a1["n_bad_scalars"] == a2["n_bad_scalars"] == 0

@@ -58,3 +58,11 @@ def test_emu_synth(emu_ctx, oracle_ctx):
 
 def test_emu_verify(emu_ctx, oracle_ctx, oracle_lib):
     ps.check_verify(emu_ctx, oracle_ctx, oracle_lib, sizes=(1, 2, 9))
+
+
+def test_emu_degenerate(emu_ctx, oracle_ctx):
+    ps.check_degenerate(emu_ctx, oracle_ctx, n=6)
+
+
+def test_emu_status_classes(emu_ctx, oracle_ctx):
+    ps.check_status_classes(emu_ctx, oracle_ctx, n=4)

@@ -151,3 +151,49 @@ def test_gpu_device_resident_entry_point(gpu_lib):
     assert not ok
     assert ctx.launch_count() > 0
     ctx.close()
+
+
+@pytest.mark.parametrize("n", [3, 63, 64, 65, 1023, 1024, 1025, 2047, 3000])
+def test_gpu_verify_ragged_sizes(gpu_ctx, oracle_ctx, n):
+    """Ragged batch sizes around the window / chunk boundaries: verdict + all artefacts bit-exact."""
+    seed = 0x4B5A4710 + n
+    C, Z, Y, PI = oracle_ctx.synth_instance(seed, 0, n)
+    assert gpu_ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == oracle_ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    a1, a2 = gpu_ctx.last_artifacts(), oracle_ctx.last_artifacts()
+    for key in ("S1", "S2", "S3", "A", "B", "sum_ry", "root"):
+        assert a1[key] == a2[key], (n, key)
+    # swap two proofs: well-formed, must be rejected by both
+    if n >= 2:
+        PI2 = PI[48:96] + PI[:48] + PI[96:]
+        assert gpu_ctx.verify_kzg_proof_batch(C, Z, Y, PI2, n) == oracle_ctx.verify_kzg_proof_batch(C, Z, Y, PI2, n) == (0, False)
+
+
+def test_gpu_degenerate_batches(gpu_ctx, oracle_ctx):
+    ps.check_degenerate(gpu_ctx, oracle_ctx)
+
+
+def test_gpu_every_status_class_in_batch(gpu_ctx, oracle_ctx):
+    ps.check_status_classes(gpu_ctx, oracle_ctx)
+
+
+def test_gpu_msm_large_random_vs_linearity(gpu_lib):
+    """Size-independent property at 2^16 points: MSM(k) + MSM(k') == MSM(k + k') (bit-exact affine bytes
+    compared through a 2-point MSM with unit scalars)."""
+    n = 1 << 16
+    ctx = gpu_lib.context(n_max=n)
+    C, Z, Y, PI = ctx.synth_instance(0x4B5A4722, 0, n)
+    rc, aff, st = ctx.g1_decompress_batch(C)
+    assert rc == 0 and not any(st)
+    rnd = random.Random(9)
+    half = (b.R - 1) // 2
+    k1 = [rnd.randrange(half) for _ in range(n)]
+    k2 = [rnd.randrange(half) for _ in range(n)]
+    enc = lambda ks: b"".join(k.to_bytes(32, "big") for k in ks)
+    rc1, s1 = ctx.g1_msm(aff, enc(k1), 255)
+    rc2, s2 = ctx.g1_msm(aff, enc(k2), 255)
+    rc3, s3 = ctx.g1_msm(aff, enc([x + y for x, y in zip(k1, k2)]), 255)
+    assert rc1 == rc2 == rc3 == 0
+    one = (1).to_bytes(32, "big")
+    rc4, s12 = ctx.g1_msm(s1 + s2, one + one, 255)
+    assert rc4 == 0 and s12 == s3 and s3 != bytes(96)
+    ctx.close()
