@@ -155,21 +155,20 @@ KZ_HD void aff_to_be96(u8* out, const G1Aff& p) {          // canonical x||y; in
 }
 KZ_HD bool aff_from_be96(G1Aff& p, const u8* in) { return fp_from_be(p.x, in) & fp_from_be(p.y, in + 48); }
 
-// ------------------------------------------------------------------ sqrt:  a^((p+1)/4), 4-bit fixed windows
-// 379 squarings + <= 95 table multiplications + 14 to build the table.  The window digit is the same for
-// every thread (fixed exponent), so the table lives in local memory with uniform, coalesced indexing.
+// ------------------------------------------------------------------ sqrt:  a^((p+1)/4), sliding 4-bit windows
+// 376 squarings + 78 table multiplications + 8 products to build the odd-power table (a, a^3, .., a^15).
+// The schedule is a compile-time constant (same for every thread), so the table lives in local memory
+// with uniform, coalesced indexing and all branches are warp-uniform.
 KZ_HD Fp fp_sqrt_candidate(const Fp& a) {
-    Fp tab[16];
-    tab[1] = a;
-    tab[2] = fp_sqr(a);
-    for (int i = 3; i < 16; ++i) tab[i] = fp_mul(tab[i - 1], a);
-    // exponent has 379 bits: top window (bits 376..378) is 3 bits wide
-    u32 top = (EXP_SQRT[11] >> 24) & 0x7;
-    Fp r = tab[top];
-    for (int w = 93; w >= 0; --w) {                        // windows of 4 bits: bits [4w, 4w+4)
-        r = fp_sqr(r); r = fp_sqr(r); r = fp_sqr(r); r = fp_sqr(r);
-        u32 d = (EXP_SQRT[w >> 3] >> ((w & 7) * 4)) & 0xF;
-        if (d) r = fp_mul(r, tab[d]);
+    Fp tab[8];
+    tab[0] = a;
+    Fp a2 = fp_sqr(a);
+    for (int i = 1; i < 8; ++i) tab[i] = fp_mul(tab[i - 1], a2);
+    Fp r = tab[SQRT_SCHED[1]];                       // first step: leading window, no squarings
+    for (int s = 1; s < SQRT_SCHED_STEPS; ++s) {
+        int nsq = SQRT_SCHED[2 * s], idx = SQRT_SCHED[2 * s + 1];
+        for (int k = 0; k < nsq; ++k) r = fp_sqr(r);
+        if (idx != 0xFF) r = fp_mul(r, tab[idx]);
     }
     return r;
 }

@@ -33,6 +33,7 @@ struct DeviceSlot {
     size_t n_max = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;    // high-priority side stream: hashes, challenges and sorts overlap K1
+    cudaStream_t stream3 = nullptr, stream4 = nullptr;   // the three sums accumulate/reduce concurrently
     // staged inputs (host-pointer API)
     uint8_t *dC = nullptr, *dz = nullptr, *dy = nullptr, *dpi = nullptr;
     Fp* pts = nullptr;                 // 3*n_max + 2 affine points: C | pi | G | phi(pi) | phi(G)
@@ -46,7 +47,8 @@ struct DeviceSlot {
     size_t max_bucketsR = 0, max_bucketsZ = 0, max_segs = 0;
     void* cub_temp = nullptr;
     size_t cub_temp_bytes = 0;
-    ChunkRecs recs = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    ChunkRecs recs = {nullptr, nullptr, nullptr, nullptr, nullptr};      // sum S2' (and kzgb_g1_msm)
+    ChunkRecs recsA = {nullptr, nullptr, nullptr, nullptr, nullptr}, recsB = {nullptr, nullptr, nullptr, nullptr, nullptr};
     G1Jac* sums = nullptr;             // [0] S1 [1] S2' [2] S3 [3] A [4] B
     uint8_t* partial_dev = nullptr;    // 320
     uint8_t* partials_in = nullptr;    // 320 * 64
@@ -99,6 +101,8 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
         int lo_pri = 0, hi_pri = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
         CK(cudaStreamCreateWithPriority(&s.stream2, cudaStreamNonBlocking, hi_pri));
+        CK(cudaStreamCreateWithFlags(&s.stream3, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s.stream4, cudaStreamNonBlocking));
     }
     for (auto& e : s.ev) CK(cudaEventCreate(&e));
     CK(dmalloc(s.dC, 48 * (n_max + 1))); CK(dmalloc(s.dz, 32 * (n_max + 1))); CK(dmalloc(s.dy, 32 * (n_max + 1))); CK(dmalloc(s.dpi, 48 * (n_max + 1)));
@@ -131,7 +135,7 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     if (slot_alloc_sort(s.sortZ, capZ, s.max_bucketsZ + 512)) return KZGB_ERROR;
     CK(dmalloc(s.bucketsA, s.max_bucketsR + 512)); CK(dmalloc(s.bucketsB, s.max_bucketsR + 512));
     CK(dmalloc(s.bucketsC, s.max_bucketsZ + 512));
-    CK(dmalloc(s.segsums, 3 * (s.max_segs + 512))); CK(dmalloc(s.winsums, 3 * KZ_MSM_MAX_WINDOWS));
+    CK(dmalloc(s.segsums, 3 * s.max_segs)); CK(dmalloc(s.winsums, 3 * KZ_MSM_MAX_WINDOWS));
     {   // chunk records for the balanced accumulation: worst case over the chunk-length schedule
         auto mn = [](size_t a, size_t b) { return a < b ? a : b; };
         size_t tmax = capZ / msm_chunk_len(capZ) + 1;
@@ -140,6 +144,14 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
         tmax += 64;
         CK(dmalloc(s.recs.head, tmax)); CK(dmalloc(s.recs.tail, tmax));
         CK(dmalloc(s.recs.head_key, tmax)); CK(dmalloc(s.recs.tail_key, tmax)); CK(dmalloc(s.recs.head_flags, tmax));
+        size_t tr = capR / msm_chunk_len(capR) + 1;
+        size_t cr[3] = {mn(capR, (size_t)1 << 21) / 16 + 1, mn(capR, (size_t)1 << 20) / 8 + 1, mn(capR, (size_t)1 << 18) / 4 + 1};
+        for (size_t t : cr) if (t > tr) tr = t;
+        tr += 64;
+        for (ChunkRecs* r : {&s.recsA, &s.recsB}) {
+            CK(dmalloc(r->head, tr)); CK(dmalloc(r->tail, tr));
+            CK(dmalloc(r->head_key, tr)); CK(dmalloc(r->tail_key, tr)); CK(dmalloc(r->head_flags, tr));
+        }
     }
     s.cub_temp_bytes = msm_cub_temp_bytes(capZ) + 256;
     CK(cudaMalloc(&s.cub_temp, s.cub_temp_bytes));
@@ -171,13 +183,17 @@ void slot_free(DeviceSlot& s) {
                    s.sortZ.keys, s.sortZ.vals, s.sortZ.keys_alt, s.sortZ.vals_alt, s.sortZ.bucket_start, s.bucketsA,
                    s.bucketsB, s.bucketsC, s.segsums, s.winsums, s.cub_temp, s.sums, s.partial_dev, s.partials_in,
                    s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb, s.recs.head, s.recs.tail,
-                   s.recs.head_key, s.recs.tail_key, s.recs.head_flags};
+                   s.recs.head_key, s.recs.tail_key, s.recs.head_flags, s.recsA.head, s.recsA.tail, s.recsA.head_key,
+                   s.recsA.tail_key, s.recsA.head_flags, s.recsB.head, s.recsB.tail, s.recsB.head_key, s.recsB.tail_key,
+                   s.recsB.head_flags};
     for (void* p : dev) if (p) cudaFree(p);
     if (s.h_digests) cudaFreeHost(s.h_digests);
     if (s.h_small) cudaFreeHost(s.h_small);
     if (s.h_partial) cudaFreeHost(s.h_partial);
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     if (s.stream2) cudaStreamDestroy(s.stream2);
+    if (s.stream3) cudaStreamDestroy(s.stream3);
+    if (s.stream4) cudaStreamDestroy(s.stream4);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -257,7 +273,7 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     s.planZ = msm_make_plan(2 * (n + 1), 128);
     if ((size_t)s.planR.W * n > s.sortR.capacity || (size_t)s.planZ.W * 2 * (n + 1) > s.sortZ.capacity ||
         s.planR.total_buckets > s.max_bucketsR + 512 || s.planZ.total_buckets > s.max_bucketsZ + 512 ||
-        s.planZ.total_segs > s.max_segs + 512 || s.planR.total_segs > s.max_segs + 512)
+        s.planZ.total_segs > s.max_segs || s.planR.total_segs > s.max_segs)
         return KZGB_BADARGS;
     MsmWorkspace wr = make_ws(s, s.sortR, s.bucketsA), wz = make_ws(s, s.sortZ, s.bucketsC);
     msm_sort_stage(s2, s.planR, s.r, 4, n, wr);
@@ -265,18 +281,30 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     save_ws(s.sortR, wr); save_ws(s.sortZ, wz);
     CK(cudaEventRecord(s.ev[5], s2));
     CK(cudaStreamWaitEvent(st, s.ev[5], 0));
+    // the three sums are independent from here to their per-window totals: run them on three streams
     MsmWorkspace wr2 = wr;
-    wr2.buckets = s.bucketsB;
-    msm_accumulate_stage(st, s.planR, s.pts, n, wr);                 // S1 over C_i
-    msm_accumulate_stage(st, s.planR, s.pts + 2 * n, n, wr2);        // S3 over pi_i
-    msm_accumulate_stage(st, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);     // S2' over pi_i, G and their phi images
+    wr.recs = s.recsA;
+    wr2.buckets = s.bucketsB; wr2.recs = s.recsB;
+    wr2.segsums = s.segsums + s.max_segs; wr2.winsums = s.winsums + KZ_MSM_MAX_WINDOWS;
+    wz.segsums = s.segsums + 2 * s.max_segs; wz.winsums = s.winsums + 2 * KZ_MSM_MAX_WINDOWS;
+    CK(cudaEventRecord(s.ev[11], st));
+    CK(cudaStreamWaitEvent(s.stream3, s.ev[11], 0));
+    CK(cudaStreamWaitEvent(s.stream4, s.ev[11], 0));
+    msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);   // S2' over pi_i, G and their phi images
+    msm_window_sums_stage(s.stream4, s.planZ, wz);
+    CK(cudaEventRecord(s.ev[13], s.stream4));
+    msm_accumulate_stage(s.stream3, s.planR, s.pts + 2 * n, n, wr2);             // S3 over pi_i
+    msm_window_sums_stage(s.stream3, s.planR, wr2);
+    CK(cudaEventRecord(s.ev[12], s.stream3));
+    msm_accumulate_stage(st, s.planR, s.pts, n, wr);                             // S1 over C_i
+    msm_window_sums_stage(st, s.planR, wr);
+    CK(cudaStreamWaitEvent(st, s.ev[12], 0));
+    CK(cudaStreamWaitEvent(st, s.ev[13], 0));
     CK(cudaEventRecord(s.ev[6], st));
-    wr2.segsums = s.segsums + (s.max_segs + 512); wr2.winsums = s.winsums + KZ_MSM_MAX_WINDOWS;
-    wz.segsums = s.segsums + 2 * (s.max_segs + 512); wz.winsums = s.winsums + 2 * KZ_MSM_MAX_WINDOWS;
     const MsmPlan* plans[3] = {&s.planR, &s.planR, &s.planZ};
     MsmWorkspace* wss[3] = {&wr, &wr2, &wz};
     G1Jac* outs[3] = {s.sums + 0, s.sums + 2, s.sums + 1};
-    msm_reduce_stage_multi(st, plans, wss, outs, 3);
+    msm_combine_stage(st, plans, wss, outs, 3);
     launch_make_partial(st, s.sums + 0, s.sums + 1, s.sums + 2, s.sum_ry, s.partial_dev);
     CK(cudaMemcpyAsync(s.h_partial, s.partial_dev, KZGB_PARTIAL_BYTES, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_small, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -542,7 +570,7 @@ kzgb_ret kzgb_g1_msm(uint8_t affine_out[96], const uint8_t* points_affine, const
     const bool glv = nbits == 255;
     size_t mm = glv ? 2 * m : m;
     MsmPlan plan = msm_make_plan(mm, 128);
-    if ((size_t)plan.W * mm > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || plan.total_segs > s.max_segs + 512) {
+    if ((size_t)plan.W * mm > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || plan.total_segs > s.max_segs) {
         cudaFree(d_pts); cudaFree(d_sc);
         return KZGB_BADARGS;
     }

@@ -146,19 +146,25 @@ void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, si
     k_msm_chunk_pass2<<<(T + 127) / 128, 128, 0, s>>>(T, ws.buckets, ws.recs);
     KZ_COUNT_LAUNCH();
 }
-void msm_reduce_stage_multi(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs) {
+// bucket reduction of one sum up to its per-window totals (ws.winsums)
+void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws) {
+    k_msm_segments<<<(plan.total_segs + 127) / 128, 128, 0, s>>>(ws.buckets, ws.segsums, plan);
+    KZ_COUNT_LAUNCH();
+    k_msm_window_sum<<<plan.W, KZ_WIN_THREADS, 0, s>>>(ws.segsums, ws.winsums, plan);
+    KZ_COUNT_LAUNCH();
+}
+// Horner combine of up to 3 sums whose window totals are ready; one block per sum
+void msm_combine_stage(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs) {
     CombineJobs cj;
     for (int j = 0; j < njobs; ++j) {
-        const MsmPlan& plan = *plans[j];
-        MsmWorkspace& ws = *wss[j];
-        k_msm_segments<<<(plan.total_segs + 127) / 128, 128, 0, s>>>(ws.buckets, ws.segsums, plan);
-        KZ_COUNT_LAUNCH();
-        k_msm_window_sum<<<plan.W, KZ_WIN_THREADS, 0, s>>>(ws.segsums, ws.winsums, plan);
-        KZ_COUNT_LAUNCH();
-        cj.winsums[j] = ws.winsums; cj.out[j] = outs[j]; cj.W[j] = plan.W; cj.c[j] = plan.c;
+        cj.winsums[j] = wss[j]->winsums; cj.out[j] = outs[j]; cj.W[j] = plans[j]->W; cj.c[j] = plans[j]->c;
     }
     k_msm_combine<<<njobs, 32, 0, s>>>(cj);
     KZ_COUNT_LAUNCH();
+}
+void msm_reduce_stage_multi(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs) {
+    for (int j = 0; j < njobs; ++j) msm_window_sums_stage(s, *plans[j], *wss[j]);
+    msm_combine_stage(s, plans, wss, outs, njobs);
 }
 void msm_reduce_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, G1Jac* out) {
     const MsmPlan* p = &plan;

@@ -61,6 +61,8 @@ void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars
 // accumulate + reduce + combine over points `pts` (2 Fp each, m points) using the sorted entries in ws
 void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, size_t m, MsmWorkspace& ws);
 void msm_reduce_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, G1Jac* out);
+void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws);
+void msm_combine_stage(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs);
 // up to 3 jobs; each job needs its own buckets / segsums / winsums; the serial Horner chains run concurrently
 void msm_reduce_stage_multi(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs);
 
