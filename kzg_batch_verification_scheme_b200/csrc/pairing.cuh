@@ -167,17 +167,18 @@ struct PairScratch {
 KZ_COLD void coop_mul(PairScratch& S, Fp12& dst, const Fp12& x, const Fp12& y) {
     COOP_FOR(t, 108) {
         int q = t / 3, part = t - 3 * q, i = q / 6, j = q - 6 * i;
-        Fp v;
-        if (part == 0) v = fp_mul(x.c[i].c0, y.c[j].c0);
-        else if (part == 1) v = fp_mul(x.c[i].c1, y.c[j].c1);
-        else v = fp_mul(fp_add(x.c[i].c0, x.c[i].c1), fp_add(y.c[j].c0, y.c[j].c1));
-        S.kar[q][part] = v;
+        // select the operands first so that the warp executes ONE convergent Fp product
+        Fp A, B;
+        if (part == 0) { A = x.c[i].c0; B = y.c[j].c0; }
+        else if (part == 1) { A = x.c[i].c1; B = y.c[j].c1; }
+        else { A = fp_add(x.c[i].c0, x.c[i].c1); B = fp_add(y.c[j].c0, y.c[j].c1); }
+        S.kar[q][part] = fp_mul(A, B);
     }
     COOP_SYNC();
     COOP_FOR(t, 72) {
         int q = t >> 1;
-        if ((t & 1) == 0) S.prod[q].c0 = fp_sub(S.kar[q][0], S.kar[q][1]);
-        else S.prod[q].c1 = fp_sub(fp_sub(S.kar[q][2], S.kar[q][0]), S.kar[q][1]);
+        Fp d = fp_sub((t & 1) ? S.kar[q][2] : S.kar[q][0], (t & 1) ? S.kar[q][0] : S.kar[q][1]);
+        if (t & 1) S.prod[q].c1 = fp_sub(d, S.kar[q][1]); else S.prod[q].c0 = d;
     }
     COOP_SYNC();
     COOP_FOR(t, 36) {
@@ -224,7 +225,9 @@ KZ_COLD void coop_frob1(Fp12& dst, const Fp12& src) {         // c_k = conj(a_k)
         int k = t >> 1;
         Fp a0 = src.c[k].c0, a1 = src.c[k].c1;
         Fp g0 = fp_const(FROB1_GAMMA + 24 * k), g1 = fp_const(FROB1_GAMMA + 24 * k + 12);
-        Fp v = (t & 1) ? fp_sub(fp_mul(a0, g1), fp_mul(a1, g0)) : fp_add(fp_mul(a0, g0), fp_mul(a1, g1));
+        // (a0 - a1 u)(g0 + g1 u): real = a0 g0 + a1 g1, imaginary = a0 g1 - a1 g0; products issued convergently
+        Fp m0 = fp_mul(a0, (t & 1) ? g1 : g0), m1 = fp_mul(a1, (t & 1) ? g0 : g1);
+        Fp v = (t & 1) ? fp_sub(m0, m1) : fp_add(m0, m1);
         if (t & 1) dst.c[k].c1 = v; else dst.c[k].c0 = v;
     }
     COOP_SYNC();
@@ -263,7 +266,8 @@ KZ_COLD void coop_inv(PairScratch& S, Fp12& dst, const Fp12& x) {
     COOP_FOR(t, 12) {                        // dst = a * n2^-1
         int k = t >> 1;
         Fp s0 = S.b.c[0].c0, s1 = S.b.c[0].c1, a0 = S.a.c[k].c0, a1 = S.a.c[k].c1;
-        Fp v = (t & 1) ? fp_add(fp_mul(a0, s1), fp_mul(a1, s0)) : fp_sub(fp_mul(a0, s0), fp_mul(a1, s1));
+        Fp m0 = fp_mul(a0, (t & 1) ? s1 : s0), m1 = fp_mul(a1, (t & 1) ? s0 : s1);
+        Fp v = (t & 1) ? fp_add(m0, m1) : fp_sub(m0, m1);
         if (t & 1) dst.c[k].c1 = v; else dst.c[k].c0 = v;
     }
     COOP_SYNC();
