@@ -223,30 +223,41 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
                 bool on_device, uint8_t* digests_out) {
     if (n == 0 || n > s.n_max) return KZGB_BADARGS;
     CK(cudaSetDevice(s.device));
-    cudaStream_t st = s.stream;
+    cudaStream_t st = s.stream, s2 = s.stream2;        // s2: high priority side stream
     CK(cudaEventRecord(s.ev[0], st));
+    CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), st));
+    CK(cudaEventRecord(s.ev[14], st));
+    CK(cudaStreamWaitEvent(s2, s.ev[14], 0));
     if (!on_device) {
+        // commitments first on the main stream; pi, z, y copy on the side stream while K1 already runs on the C half
         CK(cudaMemcpyAsync(s.dC, C, 48 * n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(s.dz, z, 32 * n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(s.dy, y, 32 * n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(s.dpi, pi, 48 * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.dpi, pi, 48 * n, cudaMemcpyHostToDevice, s2));
+        CK(cudaMemcpyAsync(s.dz, z, 32 * n, cudaMemcpyHostToDevice, s2));
+        CK(cudaMemcpyAsync(s.dy, y, 32 * n, cudaMemcpyHostToDevice, s2));
         s.cur_C = s.dC; s.cur_z = s.dz; s.cur_y = s.dy; s.cur_pi = s.dpi;
     } else {
         s.cur_C = C; s.cur_z = z; s.cur_y = y; s.cur_pi = pi;
     }
     s.cur_n = n;
     s.have_sums = false;
-    CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), st));
-    CK(cudaEventRecord(s.ev[1], st));
-    // side stream (high priority): hashes first, so they start before K1 fills the SMs
-    cudaStream_t s2 = s.stream2;
+    CK(cudaEventRecord(s.ev[1], st));                   // C resident
+    CK(cudaEventRecord(s.ev[13], s2));                  // pi, z, y resident
+    // side stream: hashes (need all four arrays) start before K1 fills the SMs
     CK(cudaStreamWaitEvent(s2, s.ev[1], 0));
     launch_leaf_hash(s2, s.cur_C, s.cur_z, s.cur_y, s.cur_pi, n, s.leaves, s.counters);
     launch_chunk_hash(s2, s.leaves, n, s.digests);
     size_t nch = (n + KZGB_CHUNK - 1) / KZGB_CHUNK;
     CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, s2));
     CK(cudaEventRecord(s.ev[2], s2));
-    launch_decompress(st, s.cur_C, s.cur_pi, n, s.pts, s.k1_tmp, s.status, s.counters);
+    if (!on_device && n >= 32768) {
+        // K1 in two halves: commitments, then (once pi is resident) proofs -- hides most of the H2D copy
+        launch_decompress_points(st, s.cur_C, n, s.pts, s.k1_tmp, s.status, s.counters);
+        CK(cudaStreamWaitEvent(st, s.ev[13], 0));
+        launch_decompress_points(st, s.cur_pi, n, s.pts + 2 * n, s.k1_tmp + 3 * n, s.status + n, s.counters);
+    } else {
+        CK(cudaStreamWaitEvent(st, s.ev[13], 0));
+        launch_decompress(st, s.cur_C, s.cur_pi, n, s.pts, s.k1_tmp, s.status, s.counters);
+    }
     // the setup point G joins the GLV-split sum with scalar -(sum r_i y_i): point slot 2n; then phi(pi_i), phi(G)
     CK(cudaMemcpyAsync(s.pts + 2 * (2 * n), s.g1_pt, 2 * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     launch_endo_points(st, s.pts + 2 * n, n + 1, s.pts + 2 * (2 * n + 1));

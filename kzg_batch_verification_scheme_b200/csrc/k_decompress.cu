@@ -19,10 +19,10 @@ __device__ __forceinline__ u32 ld_be32(u32 x) { return __byte_perm(x, 0, 0x0123)
 // MINB = minimum resident blocks per SM the register allocation must allow (run-time pick: KZGB_K1_MINB).
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_decompress_sqrt(const u8* __restrict__ inC, const u8* __restrict__ inPi, size_t n,
-                                                               Fp* __restrict__ out_pts, u8* __restrict__ status,
+                                                               size_t total, Fp* __restrict__ out_pts, u8* __restrict__ status,
                                                                u32* __restrict__ counters) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * n) return;
+    if (i >= total) return;
     const u8* src = i < n ? inC + 48 * i : inPi + 48 * (i - n);
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4 q0 = __ldg(s4), q1 = __ldg(s4 + 1), q2 = __ldg(s4 + 2);
@@ -40,17 +40,27 @@ __global__ void __launch_bounds__(128, MINB) k_decompress_sqrt(const u8* __restr
     if (st) atomicAdd(counters, 1u);
 }
 // per-kernel occupancy choice "abc" (digits 2..4 for K1a, K1b, K1c), e.g. KZGB_K1_MINB=433
-void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, Fp* out_pts, Fp* tmp, uint8_t* status,
-                       uint32_t* counters) {
-    if (!n) return;
+// points [0, total) with total <= 2n: i < n from inC, the rest from inPi
+static void launch_decompress_impl(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, size_t total, Fp* out_pts,
+                                   Fp* tmp, uint8_t* status, uint32_t* counters) {
+    if (!total) return;
     static const int cfg = [] { const char* e = getenv("KZGB_K1_MINB"); int v = e ? atoi(e) : 322; return (v >= 222 && v <= 444) ? v : 322; }();
     const int ma = cfg / 100, mb = cfg / 10 % 10, mc = cfg % 10;
-    unsigned blocks = (unsigned)((2 * n + 127) / 128);
-    if (ma >= 4) k_decompress_sqrt<4><<<blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
-    else if (ma == 3) k_decompress_sqrt<3><<<blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
-    else k_decompress_sqrt<2><<<blocks, 128, 0, s>>>(inC, inPi, n, out_pts, status, counters);
-    launch_subgroup_chains(s, out_pts, 2 * n, tmp, status, counters, mb, mc);
+    unsigned blocks = (unsigned)((total + 127) / 128);
+    if (ma >= 4) k_decompress_sqrt<4><<<blocks, 128, 0, s>>>(inC, inPi, n, total, out_pts, status, counters);
+    else if (ma == 3) k_decompress_sqrt<3><<<blocks, 128, 0, s>>>(inC, inPi, n, total, out_pts, status, counters);
+    else k_decompress_sqrt<2><<<blocks, 128, 0, s>>>(inC, inPi, n, total, out_pts, status, counters);
+    launch_subgroup_chains(s, out_pts, total, tmp, status, counters, mb, mc);
     KZ_COUNT_LAUNCH(); KZ_COUNT_LAUNCH(); KZ_COUNT_LAUNCH();
+}
+void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, Fp* out_pts, Fp* tmp, uint8_t* status,
+                       uint32_t* counters) {
+    launch_decompress_impl(s, inC, inPi, n, 2 * n, out_pts, tmp, status, counters);
+}
+// m points of ONE input array (used per half so that K1 on the commitments starts while pi, z, y still copy)
+void launch_decompress_points(cudaStream_t s, const uint8_t* in, size_t m, Fp* out_pts, Fp* tmp, uint8_t* status,
+                              uint32_t* counters) {
+    launch_decompress_impl(s, in, in, m, m, out_pts, tmp, status, counters);
 }
 
 // ---- conversions between device Montgomery affine and canonical big-endian bytes

@@ -109,7 +109,7 @@ struct CombineJobs {
 __global__ void k_msm_combine(CombineJobs jobs) {
     if (threadIdx.x) return;
     int j = blockIdx.x;
-    *jobs.out[j] = xyzz_to_jac(msm_combine_body(jobs.winsums[j], jobs.W[j], jobs.c[j]));
+    *jobs.out[j] = msm_combine_body(jobs.winsums[j], jobs.W[j], jobs.c[j]);
 }
 
 size_t msm_cub_temp_bytes(size_t entries) {

@@ -20,6 +20,8 @@ void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, 
                        uint32_t* counters);
 // k_subgroup.cu
 void launch_subgroup_chains(cudaStream_t s, Fp* pts, size_t m, Fp* tmp, uint8_t* status, uint32_t* counters, int mb, int mc);
+void launch_decompress_points(cudaStream_t s, const uint8_t* in, size_t m, Fp* out_pts, Fp* tmp, uint8_t* status,
+                              uint32_t* counters);
 void launch_points_to_be(cudaStream_t s, const Fp* pts, size_t m, uint8_t* out96);           // canonical x||y
 void launch_points_from_be(cudaStream_t s, const uint8_t* in96, size_t m, Fp* pts, uint32_t* counters);
 void launch_debug_op(cudaStream_t s, int op, const uint8_t* in, uint8_t* out, size_t count);

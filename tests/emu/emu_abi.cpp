@@ -87,7 +87,7 @@ static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nb
         for (u32 s = plan.seg_off[w]; s < plan.seg_off[w + 1]; ++s) acc = xyzz_add(acc, segs[s]);
         wins[w] = acc;
     }
-    return xyzz_to_jac(msm_combine_body(wins.data(), plan.W, plan.c));
+    return msm_combine_body(wins.data(), plan.W, plan.c);
 }
 
 extern "C" {
