@@ -26,11 +26,11 @@ sys.path.insert(0, str(ROOT))
 
 # algorithmic work model (DESIGN.md "Work model").  Unit = one 32x32->64 multiply-add.
 # Generic Montgomery product: 2N^2+N = 300 (N = 12); dedicated squaring: N(N-1)/2 + N + N^2 + N = 234.
-# K1 per point: sqrt a^((p+1)/4) = 379 S + 103 M (4-bit windows), on-curve check 2 S + 1 M, two |x| chains =
+# K1 per point: sqrt a^((p+1)/4) = 377 S + 85 M (sliding 4-bit windows), on-curve check 2 S + 1 M, two |x| chains =
 # 126 doublings (2M+5S) + 5 mixed additions (8M+3S) + 5 full additions (12M+4S) + compare (3M+1S):
 IMAD_PER_FPMUL, IMAD_PER_FPSQR = 300, 234
-K1_M_PER_POINT = 103 + 1 + 126 * 2 + 5 * 8 + 5 * 12 + 3 + 2          # + to/from Montgomery
-K1_S_PER_POINT = 379 + 2 + 126 * 5 + 5 * 3 + 5 * 4 + 1
+K1_M_PER_POINT = 85 + 1 + 126 * 2 + 5 * 8 + 5 * 12 + 3 + 2           # + to/from Montgomery
+K1_S_PER_POINT = 377 + 2 + 126 * 5 + 5 * 3 + 5 * 4 + 1
 K1_IMAD_PER_POINT = K1_M_PER_POINT * IMAD_PER_FPMUL + K1_S_PER_POINT * IMAD_PER_FPSQR
 K1_IMAD_PER_POINT_SURVEY = (471 + 1021) * 300                          # SURVEY.md 8(d) model, M = S = 300
 MSM_FPMUL_PER_PROOF = 370                                              # SURVEY.md App. C, n = 2^20
