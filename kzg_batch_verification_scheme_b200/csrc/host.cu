@@ -600,10 +600,7 @@ kzgb_ret kzgb_g1_msm(uint8_t affine_out[96], const uint8_t* points_affine, const
     CK(cudaEventRecord(s.ev[2], st));
     msm_reduce_stage(st, plan, ws, s.sums + 0);
     CK(cudaEventRecord(s.ev[3], st));
-    // affine conversion through the artefact kernel's path: reuse k_artifacts slot 0 (S1)
-    CK(cudaMemsetAsync(s.sums + 1, 0, 2 * sizeof(G1Jac), st));
-    CK(cudaMemsetAsync(s.sum_ry, 0, 8 * sizeof(uint32_t), st));
-    launch_artifacts(st, s.sums + 0, s.sums + 1, s.sums + 2, s.sum_ry, s.g1_pt, s.scratch);
+    launch_jac_to_affine_be(st, s.sums + 0, 1, s.scratch);
     CK(cudaMemcpyAsync(s.h_partial, s.scratch, 96, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_small, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

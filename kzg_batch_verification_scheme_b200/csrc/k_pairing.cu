@@ -99,6 +99,17 @@ void launch_points_jac_from_be(cudaStream_t s, const uint8_t* in96, int m, G1Jac
     KZ_COUNT_LAUNCH();
 }
 
+// Jacobian -> canonical affine bytes (one inversion per point; cold: stage exports only)
+__global__ void k_jac_to_affine_be(const G1Jac* __restrict__ in, int m, u8* __restrict__ out) {
+    int t = threadIdx.x;
+    if (t >= m) return;
+    aff_to_be96(out + 96 * t, d_jac_to_aff(in[t]));
+}
+void launch_jac_to_affine_be(cudaStream_t s, const G1Jac* in, int m, uint8_t* out96) {
+    k_jac_to_affine_be<<<1, 32, 0, s>>>(in, m, out96);
+    KZ_COUNT_LAUNCH();
+}
+
 // ---- the pairing kernel
 __device__ __noinline__ void d_pairing(PairScratch& S, const G2Lines* lines, const G1Jac* P) { coop_pairing_check(S, lines, P); }
 

@@ -84,4 +84,5 @@ void launch_points_jac_from_be(cudaStream_t s, const uint8_t* in96, int m, G1Jac
 // artefacts: S1,S2,S3,A,B affine canonical from the Jacobian sums (S2 = S2' + sum_ry * G)
 void launch_artifacts(cudaStream_t s, const G1Jac* s1, const G1Jac* s2p, const G1Jac* s3, const uint32_t* sum_ry,
                       const Fp* g1_pt, uint8_t* out /*5*96 + 32*/);
+void launch_jac_to_affine_be(cudaStream_t s, const G1Jac* in, int m, uint8_t* out96);   // m <= 32
 void launch_pairing_debug(cudaStream_t s, int op, const G2Lines* lines, const uint8_t* in, uint8_t* out);

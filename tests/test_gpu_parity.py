@@ -197,3 +197,18 @@ def test_gpu_msm_large_random_vs_linearity(gpu_lib):
     rc4, s12 = ctx.g1_msm(s1 + s2, one + one, 255)
     assert rc4 == 0 and s12 == s3 and s3 != bytes(96)
     ctx.close()
+
+
+def test_gpu_config0_real_polynomials_n64(gpu_ctx, oracle_ctx, oracle_lib):
+    """BASELINE.json config[0] inputs (64 proofs from real degree-4095 polynomials, generated by the oracle)
+    through the CUDA library: same verdicts and artefacts."""
+    n, ncoef, seed = 64, 4096, 0x4B5A4700
+    bufs = [ctypes.create_string_buffer(s_ * n) for s_ in (48, 32, 32, 48)]
+    assert oracle_lib.lib.kzgb_oracle_synth_instance_poly(ctypes.c_uint64(seed), ctypes.c_size_t(n), ctypes.c_size_t(ncoef), *bufs, 0) == 0
+    C, Z, Y, PI = (x.raw for x in bufs)
+    assert gpu_ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == oracle_ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    a1, a2 = gpu_ctx.last_artifacts(), oracle_ctx.last_artifacts()
+    for key in ("S1", "S2", "S3", "A", "B", "sum_ry", "root"):
+        assert a1[key] == a2[key], key
+    Ybad = Y[:32 * 5] + ((int.from_bytes(Y[32 * 5:32 * 6], "big") + 1) % b.R).to_bytes(32, "big") + Y[32 * 6:]
+    assert gpu_ctx.verify_kzg_proof_batch(C, Z, Ybad, PI, n) == oracle_ctx.verify_kzg_proof_batch(C, Z, Ybad, PI, n) == (0, False)

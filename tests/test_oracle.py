@@ -202,3 +202,20 @@ def test_sharded_equals_single(oracle_lib):
         art = ctx.last_artifacts()
         assert art["A"] == ref["A"] and art["B"] == ref["B"] and art["sum_ry"] == ref["sum_ry"]
     ctx.close()
+
+
+def test_config0_real_polynomials_n64(oracle_lib, oracle_ctx):
+    """BASELINE.json config[0]: 64 synthetic proofs from real degree-4095 polynomials (known test tau) on host cores."""
+    import ctypes
+    n, ncoef, seed = 64, 4096, 0x4B5A4700
+    bufs = [ctypes.create_string_buffer(s_ * n) for s_ in (48, 32, 32, 48)]
+    assert oracle_lib.lib.kzgb_oracle_synth_instance_poly(ctypes.c_uint64(seed), ctypes.c_size_t(n), ctypes.c_size_t(ncoef), *bufs, 0) == 0
+    C, Z, Y, PI = (x.raw for x in bufs)
+    assert oracle_ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    art = oracle_ctx.last_artifacts()
+    assert oracle_lib.lib.kzgb_oracle_tau_shortcut(art["A"], art["B"]) == 1
+    # y_j tampered: f_j(z_j) + 1 is not the evaluation
+    Ybad = Y[:32 * 5] + ((int.from_bytes(Y[32 * 5:32 * 6], "big") + 1) % R).to_bytes(32, "big") + Y[32 * 6:]
+    assert oracle_ctx.verify_kzg_proof_batch(C, Z, Ybad, PI, n) == (0, False)
+    for i in (0, 63):
+        assert oracle_ctx.verify_kzg_proof(C[48 * i:48 * i + 48], Z[32 * i:32 * i + 32], Y[32 * i:32 * i + 32], PI[48 * i:48 * i + 48]) == (0, True)
