@@ -155,3 +155,109 @@ def verdict_tau_shortcut(art) -> bool:
 
 def verdict_pairing(art, g2_tau) -> bool:
     return bls.pairing_product_is_one([(art["A"], bls.G2), (art["B"], g2_tau)])
+
+
+# ============================================================================= cell batch (BASELINE.json config[4])
+# PeerDAS-shaped multi-point openings.  SPEC (DESIGN.md "Cell batch"): extended domain of 8192 points,
+# omega = 7^((r-1)/8192); cell c (0..127) holds the 64 evaluations f(h_c * omega_64^j), j = 0..63 in natural
+# order, omega_64 = omega^128, coset shift h_c = omega^brp7(c).  A proof pi opens f on the whole coset:
+#   pi = [(f(tau) - I(tau)) / (tau^64 - h_c^64)] G1,   I = interpolation polynomial of the cell (deg < 64)
+# Universal check for openings k with challenges r_k:
+#   e(sum r_k C_{i_k} - [sum r_k I_k(tau)] G1 + sum r_k h_k^64 pi_k, G2) * e(-sum r_k pi_k, [tau^64] G2) = 1
+N_EXT, N_CELLS, CELL_LEN = 8192, 128, 64
+OMEGA = pow(7, (R - 1) // N_EXT, R)
+OMEGA64 = pow(OMEGA, N_EXT // CELL_LEN, R)
+assert pow(OMEGA, N_EXT, R) == 1 and pow(OMEGA, N_EXT // 2, R) != 1
+TAG_CELL = b"KZGB200/cell_v1_"
+TAG_COMM = b"KZGB200/comm_v1_"
+TAG_CROOT = b"KZGB200/croot_v1"
+STREAM_BLOB = 11
+
+
+def brp7(c):
+    return int(f"{c:07b}"[::-1], 2)
+
+
+def coset_shift(c):
+    return pow(OMEGA, brp7(c), R)
+
+
+def cell_points(c):
+    h = coset_shift(c)
+    return [h * pow(OMEGA64, j, R) % R for j in range(CELL_LEN)]
+
+
+def interp_coeffs(c, ys):
+    """Coefficients a_0..a_63 of the degree-<64 polynomial with I(h_c w^j) = ys[j] (naive inverse DFT)."""
+    h_inv = pow(coset_shift(c), R - 2, R)
+    n_inv = pow(CELL_LEN, R - 2, R)
+    w_inv = pow(OMEGA64, R - 2, R)
+    out = []
+    for i in range(CELL_LEN):
+        s = sum(ys[j] * pow(w_inv, i * j, R) for j in range(CELL_LEN)) % R
+        out.append(s * n_inv % R * pow(h_inv, i, R) % R)
+    return out
+
+
+def gen_cells(seed, n_blobs, cells_per_blob, ncoef=64 * 3):
+    """n_blobs random polynomials with `ncoef` coefficients (any count <= 4096 is a valid blob polynomial);
+    for each blob the first `cells_per_blob` cells (cell index = brp-free natural 0..).  Returns
+    (commitments bytes, commitment_indices, cell_indices, cells bytes, proofs bytes)."""
+    comms, ci, xi, cells, proofs = [], [], [], [], []
+    for bi in range(n_blobs):
+        coef = [prng_fr(seed, STREAM_BLOB, bi * 4096 + j) for j in range(ncoef)]
+        ev = lambda x: sum(cf * pow(x, j, R) for j, cf in enumerate(coef)) % R   # noqa: E731
+        ft = ev(TAU)
+        comms.append(bls.g1_compress(bls.g1_mul(ft, bls.G1)))
+        for c in range(cells_per_blob):
+            ys = [ev(x) for x in cell_points(c)]
+            a = interp_coeffs(c, ys)
+            it = sum(cf * pow(TAU, j, R) for j, cf in enumerate(a)) % R
+            den = (pow(TAU, CELL_LEN, R) - pow(coset_shift(c), CELL_LEN, R)) % R
+            q = (ft - it) * pow(den, R - 2, R) % R
+            ci.append(bi); xi.append(c)
+            cells.append(b"".join(y.to_bytes(32, "big") for y in ys))
+            proofs.append(bls.g1_compress(bls.g1_mul(q, bls.G1)))
+    return b"".join(comms), ci, xi, b"".join(cells), b"".join(proofs)
+
+
+def cell_challenges(comms, ci, xi, cells, proofs):
+    m, nc = len(ci), len(comms) // 48
+    leaves = [sha(TAG_CELL + struct.pack(">QQ", ci[k], xi[k]) + cells[2048 * k:2048 * k + 2048] + proofs[48 * k:48 * k + 48])
+              for k in range(m)]
+    cdig = sha(TAG_COMM + comms)
+    root = sha(TAG_CROOT + struct.pack(">QQ", nc, m) + cdig + b"".join(fs_chunk_digests(leaves)))
+    return root, [fs_r(root, k) for k in range(m)]
+
+
+def cell_batch_artifacts(comms, ci, xi, cells, proofs):
+    m, nc = len(ci), len(comms) // 48
+    out = {"ret": KZGB_OK}
+    cs = [bls.g1_decompress(comms[48 * i:48 * i + 48]) for i in range(nc)]
+    ps = [bls.g1_decompress(proofs[48 * k:48 * k + 48]) for k in range(m)]
+    ys = [[int.from_bytes(cells[2048 * k + 32 * j:2048 * k + 32 * j + 32], "big") for j in range(CELL_LEN)] for k in range(m)]
+    if (any(s for s, _ in cs) or any(s for s, _ in ps) or any(v >= R for row in ys for v in row)
+            or any(c >= N_CELLS for c in xi) or any(i >= nc for i in ci) or m == 0):
+        out["ret"] = KZGB_BADARGS
+        return out
+    root, r = cell_challenges(comms, ci, xi, cells, proofs)
+    rlc = rlp = rpi = None
+    s_coef = [0] * CELL_LEN
+    for k in range(m):
+        rlc = bls.g1_add(rlc, bls.g1_mul(r[k], cs[ci[k]][1]))
+        h64 = pow(coset_shift(xi[k]), CELL_LEN, R)
+        rlp = bls.g1_add(rlp, bls.g1_mul(r[k] * h64 % R, ps[k][1]))
+        rpi = bls.g1_add(rpi, bls.g1_mul(r[k], ps[k][1]))
+        a = interp_coeffs(xi[k], ys[k])
+        for i in range(CELL_LEN):
+            s_coef[i] = (s_coef[i] + r[k] * a[i]) % R
+    rli = None
+    for i in range(CELL_LEN):
+        rli = bls.g1_add(rli, bls.g1_mul(s_coef[i] * pow(TAU, i, R) % R, bls.G1))     # [tau^i]G1 from the setup
+    a_pt = bls.g1_add(bls.g1_add(rlc, bls.g1_neg(rli)), rlp)
+    out.update(root=root, r=r, A=a_pt, B=bls.g1_neg(rpi), S=s_coef)
+    return out
+
+
+def cell_verdict_tau_shortcut(art) -> bool:
+    return bls.g1_add(art["A"], bls.g1_mul(pow(TAU, CELL_LEN, R), art["B"])) is None
