@@ -64,6 +64,14 @@ kzgb_ret verify_kzg_proof(bool *ok, const uint8_t C[48], const uint8_t z[32], co
 kzgb_ret verify_kzg_proof_batch(bool *ok, const uint8_t *C /*48n*/, const uint8_t *z /*32n*/, const uint8_t *y /*32n*/,
                                 const uint8_t *pi /*48n*/, size_t n, kzgb_ctx *ctx);
 
+/* ---- cell batch (BASELINE.json config[4]): m multi-point openings on cosets of 64 points
+ * (PeerDAS-shaped; conventions in DESIGN.md "Cell batch").  commitments: nc unique 48-byte G1; opening k refers to
+ * commitments[commitment_indices[k]] and cell cell_indices[k] (< 128), carries 64 evaluations (32 B big-endian each,
+ * < r) and one proof.  Needs a context created with n1 >= 64 ([tau^j]G1) and n2 >= 65 ([tau^64]G2). */
+kzgb_ret verify_cell_kzg_proof_batch(bool *ok, const uint8_t *commitments /*48 nc*/, size_t nc,
+                                     const uint32_t *commitment_indices /*m*/, const uint32_t *cell_indices /*m*/,
+                                     const uint8_t *cells /*2048 m*/, const uint8_t *proofs /*48 m*/, size_t m, kzgb_ctx *ctx);
+
 /* ---- same batch check with inputs already resident in device memory of ctx device 0 (used for the
  * device-resident throughput figure; `stream` is a cudaStream_t or NULL).  Oracle: host pointers. */
 kzgb_ret verify_kzg_proof_batch_device(bool *ok, const uint8_t *dC, const uint8_t *dz, const uint8_t *dy,

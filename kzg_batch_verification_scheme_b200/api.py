@@ -71,6 +71,7 @@ class KzgLib:
             "verify_kzg_proof": [C.POINTER(C.c_bool), vp, vp, vp, vp, vp],
             "verify_kzg_proof_batch": [C.POINTER(C.c_bool), vp, vp, vp, vp, sz, vp],
             "verify_kzg_proof_batch_device": [C.POINTER(C.c_bool), vp, vp, vp, vp, sz, vp, vp],
+            "verify_cell_kzg_proof_batch": [C.POINTER(C.c_bool), vp, sz, vp, vp, vp, vp, sz, vp],
             "kzgb_shard_phase1": [vp, i32, vp, vp, vp, vp, sz, i32, vp, vp, C.POINTER(C.c_uint32)],
             "kzgb_fs_root": [vp, vp, sz, u64],
             "kzgb_shard_phase2": [vp, i32, vp, u64, vp, vp],
@@ -97,7 +98,7 @@ class KzgLib:
         lib.kzgb_version.argtypes, lib.kzgb_version.restype = [], C.c_char_p
 
     EXPORTS = ["kzgb_ctx_create", "kzgb_ctx_free", "verify_kzg_proof", "verify_kzg_proof_batch",
-               "verify_kzg_proof_batch_device", "kzgb_shard_phase1", "kzgb_fs_root", "kzgb_shard_phase2",
+               "verify_kzg_proof_batch_device", "verify_cell_kzg_proof_batch", "kzgb_shard_phase1", "kzgb_fs_root", "kzgb_shard_phase2",
                "kzgb_combine_verify", "kzgb_g1_decompress_batch", "kzgb_fs_challenges", "kzgb_g1_msm",
                "kzgb_g1_msm_times", "kzgb_pairing_check", "kzgb_last_artifacts", "kzgb_synth_instance",
                "kzgb_synth_setup", "kzgb_debug_op", "kzgb_imad_peak", "kzgb_imad32_peak", "kzgb_last_stage_ms", "kzgb_launch_count", "kzgb_set_threads",
@@ -163,6 +164,16 @@ class Context:
         ok = C.c_bool(False)
         rc = self.lib.verify_kzg_proof_batch_device(C.byref(ok), _ptr(dC), _ptr(dz), _ptr(dy), _ptr(dpi), n, self.h,
                                                     C.c_void_p(stream))
+        return rc, bool(ok.value)
+
+    def verify_cell_kzg_proof_batch(self, commitments: bytes, commitment_indices, cell_indices, cells: bytes, proofs: bytes):
+        """Cell batch (PeerDAS-shaped): index lists are sequences of ints; returns (rc, ok)."""
+        m = len(commitment_indices)
+        ci = (C.c_uint32 * m)(*commitment_indices)
+        xi = (C.c_uint32 * m)(*cell_indices)
+        ok = C.c_bool(False)
+        rc = self.lib.verify_cell_kzg_proof_batch(C.byref(ok), _ptr(commitments), len(commitments) // 48, C.cast(ci, C.c_void_p),
+                                                  C.cast(xi, C.c_void_p), _ptr(cells), _ptr(proofs), m, self.h)
         return rc, bool(ok.value)
 
     # ---- shard level

@@ -7,13 +7,16 @@
 #include <chrono>
 #include <new>
 
-#include "kzg.hpp"
+#include <mutex>
+
+#include "cells.hpp"
 #include "../include/kzgb200.h"
 
 using namespace orc;
 
 struct kzgb_ctx {
     Setup setup;
+    CellSetup cells;
     int threads;
     std::vector<Shard> shards;
     Artifacts art;
@@ -42,6 +45,15 @@ kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const ui
     c->threads = (int)std::thread::hardware_concurrency();
     if (c->threads < 1) c->threads = 1;
     c->shards.resize(n_devices > 0 ? n_devices : 1);
+    if (n1 >= CELL_LEN && n2 >= CELL_LEN + 1) {          // cell batch needs [tau^j]G1, j < 64 and [tau^64]G2
+        c->cells.g1.resize(CELL_LEN);
+        bool okc = true;
+        for (size_t j = 0; j < CELL_LEN; ++j) okc = okc && g1_decompress(c->cells.g1[j], g1m + 48 * j) == ST_OK;
+        okc = okc && g2_decompress(c->cells.g2_64, g2m + 96 * CELL_LEN);
+        if (!okc) { delete c; return KZGB_BADARGS; }
+        c->cells.g2_0 = c->setup.g2_0;
+        c->cells.ready = true;
+    }
     *out = c;
     return KZGB_OK;
 }
@@ -150,6 +162,25 @@ kzgb_ret kzgb_combine_verify(kzgb_ctx* c, const uint8_t* parts, int np, bool* ok
     G1A P[2] = {c->art.A, c->art.B};
     G2A Q[2] = {c->setup.g2_0, c->setup.g2_1};
     *ok = pairing_product_is_one(P, Q, 2);
+    return KZGB_OK;
+}
+
+kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, const uint32_t* ci, const uint32_t* xi,
+                                     const uint8_t* cells, const uint8_t* proofs, size_t m, kzgb_ctx* c) {
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!c || !comms || !ci || !xi || !cells || !proofs) return KZGB_BADARGS;
+    bool v = false;
+    int rc = verify_cells(v, c->art, c->cells, comms, nc, ci, xi, cells, proofs, m, c->threads);
+    *ok = v;
+    return rc ? KZGB_BADARGS : KZGB_OK;
+}
+// oracle-only: synthetic cells (n_blobs * cells_per_blob openings)
+kzgb_ret kzgb_oracle_synth_cells(uint64_t seed, size_t n_blobs, size_t cells_per_blob, size_t ncoef, uint8_t* comms, uint32_t* ci,
+                                 uint32_t* xi, uint8_t* cells, uint8_t* proofs, int threads) {
+    if (ncoef > 4096 || cells_per_blob > N_CELLS) return KZGB_BADARGS;
+    synth_cells(seed, n_blobs, cells_per_blob, ncoef, comms, ci, xi, cells, proofs,
+                threads > 0 ? threads : (int)std::thread::hardware_concurrency());
     return KZGB_OK;
 }
 

@@ -371,6 +371,7 @@ kzgb_ret kzgb_debug_op(kzgb_ctx* c, int op, const uint8_t* in, uint8_t* out, siz
 }
 
 // entry points of kzgb200.h that the emulation does not model
+kzgb_ret verify_cell_kzg_proof_batch(bool*, const uint8_t*, size_t, const uint32_t*, const uint32_t*, const uint8_t*, const uint8_t*, size_t, kzgb_ctx*) { return KZGB_ERROR; }
 kzgb_ret verify_kzg_proof_batch_device(bool*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, kzgb_ctx*, void*) { return KZGB_ERROR; }
 kzgb_ret kzgb_shard_phase1(kzgb_ctx*, int, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, int, void*, uint8_t*, uint32_t*) { return KZGB_ERROR; }
 kzgb_ret kzgb_fs_root(uint8_t*, const uint8_t*, size_t, uint64_t) { return KZGB_ERROR; }
