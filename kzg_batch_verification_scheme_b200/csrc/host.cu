@@ -59,6 +59,16 @@ struct DeviceSlot {
     int* setup_status = nullptr;
     Fp* comb = nullptr;
     bool comb_built = false;
+    // cell batch (config[4]): [tau^j]G1 j<64, lines of G2 and [tau^64]G2, twiddles omega^-t, per-call workspace
+    bool cell_ready = false;
+    Fp* cell_g1 = nullptr;
+    G2Lines* lines_cell = nullptr;
+    Fr* cell_W = nullptr;
+    uint8_t* d_cells = nullptr;
+    uint32_t *d_ci = nullptr, *d_xi = nullptr;
+    Fr* cell_coefs = nullptr;
+    size_t cell_cap = 0;
+    bool have_ab = false;              // sums[3], sums[4] hold the pairing inputs of the last call
     // pinned mailboxes
     uint8_t* h_digests = nullptr;      // 32 * ceil(n_max/1024)
     uint32_t* h_small = nullptr;       // 64 words: [0..1] counters, [8..15] root words, [16] result
@@ -92,7 +102,7 @@ kzgb_ret slot_alloc_sort(SortBuf& b, size_t cap, size_t buckets) {
     return KZGB_OK;
 }
 
-kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, const uint8_t* g2m) {
+kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, size_t n1, const uint8_t* g2m, size_t n2) {
     s.device = device;
     s.n_max = n_max;
     CK(cudaSetDevice(device));
@@ -171,6 +181,27 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     CK(cudaStreamSynchronize(s.stream));
     CK(cudaGetLastError());
     if (!(st[0] && st[1] && st[2])) return KZGB_BADARGS;
+    if (n1 >= 64 && n2 >= 65) {
+        // cell batch setup: 64 G1 monomials through K1 (decompress + subgroup), lines for (G2, [tau^64]G2), twiddles
+        CK(dmalloc(s.cell_g1, 2 * 64)); CK(dmalloc(s.lines_cell, 2)); CK(dmalloc(s.cell_W, 8192));
+        CK(cudaMemcpyAsync(s.scratch, g1m, 48 * 64, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.scratch + 4096, g2m, 96, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.scratch + 4096 + 96, g2m + 96 * 64, 96, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), s.stream));
+        CK(cudaMemsetAsync(s.setup_status, 0, 4 * sizeof(int), s.stream));
+        launch_decompress_points(s.stream, s.scratch, 64, s.cell_g1, s.k1_tmp, s.status, s.counters);
+        launch_g2_setup(s.stream, s.scratch + 4096, s.lines_cell, s.setup_status);
+        launch_cell_twiddles(s.stream, s.cell_W);
+        uint32_t cnt[2];
+        uint8_t stat[64];
+        CK(cudaMemcpyAsync(st, s.setup_status, sizeof st, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(cnt, s.counters, sizeof cnt, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(stat, s.status, 64, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+        if (!(st[0] && st[1]) || cnt[0]) return KZGB_BADARGS;
+        s.cell_ready = true;
+    }
     return KZGB_OK;
 }
 
@@ -185,7 +216,7 @@ void slot_free(DeviceSlot& s) {
                    s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb, s.recs.head, s.recs.tail,
                    s.recs.head_key, s.recs.tail_key, s.recs.head_flags, s.recsA.head, s.recsA.tail, s.recsA.head_key,
                    s.recsA.tail_key, s.recsA.head_flags, s.recsB.head, s.recsB.tail, s.recsB.head_key, s.recsB.tail_key,
-                   s.recsB.head_flags};
+                   s.recsB.head_flags, s.cell_g1, s.lines_cell, s.cell_W, s.d_cells, s.d_ci, s.d_xi, s.cell_coefs};
     for (void* p : dev) if (p) cudaFree(p);
     if (s.h_digests) cudaFreeHost(s.h_digests);
     if (s.h_small) cudaFreeHost(s.h_small);
@@ -240,6 +271,7 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
     }
     s.cur_n = n;
     s.have_sums = false;
+    s.have_ab = false;
     CK(cudaEventRecord(s.ev[1], st));                   // C resident
     CK(cudaEventRecord(s.ev[13], s2));                  // pi, z, y resident
     // side stream: hashes (need all four arrays) start before K1 fills the SMs
@@ -337,6 +369,7 @@ kzgb_ret combine(DeviceSlot& s, const uint8_t* partials, int np, bool* ok) {
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     *ok = s.h_small[16] == 1;
+    s.have_ab = true;
     return KZGB_OK;
 }
 
@@ -440,7 +473,7 @@ kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const ui
     for (int i = 0; i < nd; ++i) {
         int dev = (n_devices > 0 && devices) ? devices[i] : 0;
         if (dev < 0 || dev >= ndev) { kzgb_ctx_free(c); return KZGB_BADARGS; }
-        kzgb_ret rc = slot_init(c->slots[i], dev, n_max, g1m, g2m);
+        kzgb_ret rc = slot_init(c->slots[i], dev, n_max, g1m, n1, g2m, n2);
         if (rc) { kzgb_ctx_free(c); return rc; }
     }
     memset(&c->art, 0, sizeof c->art);
@@ -626,6 +659,98 @@ kzgb_ret kzgb_g1_msm_times(float ms_out[4], kzgb_ctx* ctx) {
     return KZGB_OK;
 }
 
+// Cell batch (BASELINE.json config[4]).  Single device (slot 0): 2^14 openings are ~2 ms of work.
+kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, const uint32_t* ci, const uint32_t* xi,
+                                     const uint8_t* cells, const uint8_t* proofs, size_t m, kzgb_ctx* ctx) {
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!ctx || !comms || !ci || !xi || !cells || !proofs || m == 0 || nc == 0) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    const size_t M = m + nc + 64;                      // points of the A-side sum: proofs | commitments | [tau^j]G1
+    if (!s.cell_ready || M > s.n_max || nc > 0xFFFFFFFFull) return KZGB_BADARGS;
+    CK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
+    if (m > s.cell_cap) {
+        for (void* p : {(void*)s.d_cells, (void*)s.d_ci, (void*)s.d_xi, (void*)s.cell_coefs}) if (p) cudaFree(p);
+        s.d_cells = nullptr; s.d_ci = s.d_xi = nullptr; s.cell_coefs = nullptr; s.cell_cap = 0;
+        CK(dmalloc(s.d_cells, 2048 * m)); CK(dmalloc(s.d_ci, m)); CK(dmalloc(s.d_xi, m)); CK(dmalloc(s.cell_coefs, 64 * m));
+        s.cell_cap = m;
+    }
+    s.have_sums = false; s.have_ab = false; s.cur_n = 0;
+    kzgb_artifacts& art = ctx->art;
+    memset(&art, 0, sizeof art);
+    art.n = m;
+    CK(cudaEventRecord(s.ev[0], st));
+    CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), st));
+    CK(cudaMemcpyAsync(s.dC, comms, 48 * nc, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.dpi, proofs, 48 * m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_ci, ci, 4 * m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_xi, xi, 4 * m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_cells, cells, 2048 * m, cudaMemcpyHostToDevice, st));
+    // Fiat-Shamir: cell leaves -> chunk digests -> host root (binds the commitments as well)
+    launch_cell_leaf_hash(st, s.d_ci, s.d_xi, s.d_cells, s.dpi, m, s.leaves);
+    launch_chunk_hash(st, s.leaves, m, s.digests);
+    size_t nch = (m + KZGB_CHUNK - 1) / KZGB_CHUNK;
+    CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(s.ev[2], st));
+    // K1 on proofs and commitments; the 64 setup monomials follow them in the point array
+    launch_decompress_points(st, s.dpi, m, s.pts, s.k1_tmp, s.status, s.counters);
+    launch_decompress_points(st, s.dC, nc, s.pts + 2 * m, s.k1_tmp + 3 * m, s.status + m, s.counters);
+    CK(cudaMemcpyAsync(s.pts + 2 * (m + nc), s.cell_g1, 2 * 64 * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    CK(cudaEventSynchronize(s.ev[2]));
+    std::vector<uint8_t> dig(32 * nch);
+    words_to_be(dig.data(), (const uint32_t*)s.h_digests, 8 * nch);
+    uint8_t root[32];
+    host_sha256_cell_root(root, comms, nc, dig.data(), nch, m);
+    memcpy(art.root, root, 32);
+    be_to_words(s.h_small + 8, root, 8);
+    CK(cudaMemcpyAsync(s.root_words, s.h_small + 8, 32, cudaMemcpyHostToDevice, st));
+    // per opening: r_k, r_k h^64, r_k * interpolation coefficients; then column sums and commitment weights
+    launch_cell_scalars(st, s.cell_W, s.root_words, s.d_ci, s.d_xi, (uint32_t)nc, s.d_cells, m, s.cell_coefs, s.r, s.rz, s.counters);
+    launch_cell_reductions(st, s.cell_coefs, s.d_ci, s.r, m, (uint32_t)nc, s.rz + 8 * m, s.rz + 8 * (m + nc));
+    CK(cudaMemsetAsync(s.sum_ry, 0, 8 * sizeof(uint32_t), st));
+    // A-side: sum (r_k h^64) pi_k + sum w_i C_i - sum S_j [tau^j]G1, 255-bit scalars, GLV-split
+    {
+        size_t mm = 2 * M;
+        MsmPlan plan = msm_make_plan(mm, 128);
+        if ((size_t)plan.W * mm > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || plan.total_segs > s.max_segs)
+            return KZGB_BADARGS;
+        MsmWorkspace ws = make_ws(s, s.sortZ, s.bucketsC);
+        launch_glv_split(st, s.rz, M, s.zs);
+        launch_endo_points(st, s.pts, M, s.pts + 2 * M);
+        msm_sort_stage(st, plan, s.zs, 4, mm, ws);
+        save_ws(s.sortZ, ws);
+        msm_accumulate_stage(st, plan, s.pts, mm, ws);
+        msm_reduce_stage(st, plan, ws, s.sums + 0);
+    }
+    // B-side: sum r_k pi_k, 128-bit scalars
+    {
+        MsmPlan plan = msm_make_plan(m, 128);
+        if ((size_t)plan.W * m > s.sortR.capacity || plan.total_buckets > s.max_bucketsR + 512 || plan.total_segs > s.max_segs)
+            return KZGB_BADARGS;
+        MsmWorkspace ws = make_ws(s, s.sortR, s.bucketsA);
+        ws.recs = s.recsA;
+        msm_sort_stage(st, plan, s.r, 4, m, ws);
+        save_ws(s.sortR, ws);
+        msm_accumulate_stage(st, plan, s.pts, m, ws);
+        msm_reduce_stage(st, plan, ws, s.sums + 2);
+    }
+    launch_set_ab(st, s.sums + 0, s.sums + 2, s.sums + 3);
+    launch_pairing(st, s.lines_cell, s.sums + 3, s.result_dev);
+    CK(cudaMemcpyAsync(s.h_small + 16, s.result_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_small, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(s.ev[8], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    art.n_bad_points = s.h_small[0];
+    art.n_bad_scalars = s.h_small[1];
+    art.stage_ms[9] = ev_ms(s.ev[0], s.ev[8]);
+    if (s.h_small[0] || s.h_small[1]) return KZGB_BADARGS;
+    s.have_ab = true;
+    *ok = s.h_small[16] == 1;
+    return KZGB_OK;
+}
+
 kzgb_ret kzgb_pairing_check(bool* ok, const uint8_t A_affine[96], const uint8_t B_affine[96], kzgb_ctx* ctx) {
     if (!ok || !A_affine || !B_affine || !ctx) return KZGB_BADARGS;
     *ok = false;
@@ -661,6 +786,17 @@ kzgb_ret kzgb_last_artifacts(kzgb_ctx* ctx, kzgb_artifacts* out) {
         memcpy(ctx->art.S1, s.h_partial, 96); memcpy(ctx->art.S2, s.h_partial + 96, 96);
         memcpy(ctx->art.S3, s.h_partial + 192, 96); memcpy(ctx->art.A, s.h_partial + 288, 96);
         memcpy(ctx->art.B, s.h_partial + 384, 96); memcpy(ctx->art.sum_ry, s.h_partial + 480, 32);
+    } else if (s.have_ab) {
+        // several shards or a cell batch: only the pairing inputs (and the total sum r_i y_i) exist on this device
+        CK(cudaSetDevice(s.device));
+        launch_jac_to_affine_be(s.stream, s.sums + 3, 2, s.scratch);
+        launch_fr_to_be(s.stream, s.sum_ry, s.scratch + 192);
+        CK(cudaMemcpyAsync(s.h_partial, s.scratch, 224, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+        memset(ctx->art.S1, 0, 96); memset(ctx->art.S2, 0, 96); memset(ctx->art.S3, 0, 96);
+        memcpy(ctx->art.A, s.h_partial, 96); memcpy(ctx->art.B, s.h_partial + 96, 96);
+        memcpy(ctx->art.sum_ry, s.h_partial + 192, 32);
     }
     *out = ctx->art;
     return KZGB_OK;

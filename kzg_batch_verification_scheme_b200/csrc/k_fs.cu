@@ -303,3 +303,21 @@ void host_sha256_root(uint8_t out[32], const uint8_t* digests, size_t n_chunks, 
     s.update(digests, 32 * n_chunks);
     s.final(out);
 }
+
+// cell batch root: SHA256("KZGB200/croot_v1" | u64be(nc) | u64be(m) | SHA256("KZGB200/comm_v1_" | commitments) | chunk digests)
+void host_sha256_cell_root(uint8_t out[32], const uint8_t* comms, size_t nc, const uint8_t* digests, size_t n_chunks, uint64_t m) {
+    uint8_t cdig[32];
+    HostSha c;
+    c.update((const uint8_t*)"KZGB200/comm_v1_", 16);
+    c.update(comms, 48 * nc);
+    c.final(cdig);
+    HostSha s;
+    s.update((const uint8_t*)"KZGB200/croot_v1", 16);
+    uint8_t be[16];
+    uint64_t a = nc;
+    for (int i = 0; i < 8; ++i) { be[i] = (uint8_t)(a >> (56 - 8 * i)); be[8 + i] = (uint8_t)(m >> (56 - 8 * i)); }
+    s.update(be, 16);
+    s.update(cdig, 32);
+    s.update(digests, 32 * n_chunks);
+    s.final(out);
+}

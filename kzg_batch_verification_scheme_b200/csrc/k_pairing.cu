@@ -99,6 +99,27 @@ void launch_points_jac_from_be(cudaStream_t s, const uint8_t* in96, int m, G1Jac
     KZ_COUNT_LAUNCH();
 }
 
+// cell batch: AB[0] = A, AB[1] = -B
+__global__ void k_set_ab(const G1Jac* a, const G1Jac* b, G1Jac* AB) {
+    if (threadIdx.x == 0) AB[0] = *a;
+    if (threadIdx.x == 1) AB[1] = jac_neg(*b);
+}
+void launch_set_ab(cudaStream_t s, const G1Jac* a, const G1Jac* b, G1Jac* AB) {
+    k_set_ab<<<1, 32, 0, s>>>(a, b, AB);
+    KZ_COUNT_LAUNCH();
+}
+// sum_ry (8 canonical limbs) -> 32 big-endian bytes
+__global__ void k_fr_to_be(const u32* in, u8* out) {
+    if (threadIdx.x) return;
+    Fr v;
+    for (int k = 0; k < 8; ++k) v.v[k] = in[k];
+    fr_raw_to_be(out, v);
+}
+void launch_fr_to_be(cudaStream_t s, const uint32_t* in, uint8_t* out32) {
+    k_fr_to_be<<<1, 32, 0, s>>>(in, out32);
+    KZ_COUNT_LAUNCH();
+}
+
 // Jacobian -> canonical affine bytes (one inversion per point; cold: stage exports only)
 __global__ void k_jac_to_affine_be(const G1Jac* __restrict__ in, int m, u8* __restrict__ out) {
     int t = threadIdx.x;

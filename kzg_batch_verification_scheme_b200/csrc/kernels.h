@@ -84,5 +84,17 @@ void launch_points_jac_from_be(cudaStream_t s, const uint8_t* in96, int m, G1Jac
 // artefacts: S1,S2,S3,A,B affine canonical from the Jacobian sums (S2 = S2' + sum_ry * G)
 void launch_artifacts(cudaStream_t s, const G1Jac* s1, const G1Jac* s2p, const G1Jac* s3, const uint32_t* sum_ry,
                       const Fp* g1_pt, uint8_t* out /*5*96 + 32*/);
+void launch_set_ab(cudaStream_t s, const G1Jac* a, const G1Jac* b, G1Jac* AB);
+void launch_fr_to_be(cudaStream_t s, const uint32_t* in, uint8_t* out32);
 void launch_jac_to_affine_be(cudaStream_t s, const G1Jac* in, int m, uint8_t* out96);   // m <= 32
 void launch_pairing_debug(cudaStream_t s, int op, const G2Lines* lines, const uint8_t* in, uint8_t* out);
+
+// ---- k_cells.cu (cell batch, BASELINE.json config[4])
+void launch_cell_twiddles(cudaStream_t s, Fr* W /*8192*/);
+void launch_cell_leaf_hash(cudaStream_t s, const uint32_t* ci, const uint32_t* xi, const uint8_t* cells, const uint8_t* proofs, size_t m,
+                           uint32_t* leaves);
+void launch_cell_scalars(cudaStream_t s, const Fr* W, const uint32_t* root_words, const uint32_t* ci, const uint32_t* xi, uint32_t nc,
+                         const uint8_t* cells, size_t m, Fr* coefs, uint32_t* r_out, uint32_t* rh_out, uint32_t* counters);
+void launch_cell_reductions(cudaStream_t s, const Fr* coefs, const uint32_t* ci, const uint32_t* r, size_t m, uint32_t nc,
+                            uint32_t* w_out, uint32_t* negS_out);
+void host_sha256_cell_root(uint8_t out[32], const uint8_t* comms, size_t nc, const uint8_t* digests, size_t n_chunks, uint64_t m);

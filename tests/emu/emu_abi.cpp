@@ -12,9 +12,16 @@
 #include "../../kzg_batch_verification_scheme_b200/csrc/msm.cuh"
 #include "../../kzg_batch_verification_scheme_b200/csrc/pairing.cuh"
 #include "../../kzg_batch_verification_scheme_b200/csrc/sha256.cuh"
+#include "../../kzg_batch_verification_scheme_b200/csrc/cells.cuh"
 
 struct kzgb_ctx {
     G2Lines lines[2];
+    G2Lines lines_cell[2];
+    std::vector<G1Aff> cell_g1;
+    std::vector<Fr> W;
+    bool cell_ready = false;
+    G1Jac ab[2];
+    bool have_ab = false;
     G1Aff g1;
     kzgb_artifacts art;
     G1Jac sums[3];
@@ -102,6 +109,20 @@ kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const ui
     bool ok = g1_decompress_validate(c->g1, w) == ST_OK && !aff_is_inf(c->g1);
     ok = ok && g2_setup_point(c->lines[0], g2m) && g2_setup_point(c->lines[1], g2m + 96);
     if (!ok) { delete c; return KZGB_BADARGS; }
+    if (n1 >= 64 && n2 >= 65) {
+        c->cell_g1.resize(64);
+        for (int j = 0; j < 64 && ok; ++j) {
+            words_from_be(w, g1m + 48 * j, 12);
+            ok = g1_decompress_validate(c->cell_g1[j], w) == ST_OK;
+        }
+        c->lines_cell[0] = c->lines[0];
+        ok = ok && g2_setup_point(c->lines_cell[1], g2m + 96 * 64);
+        if (!ok) { delete c; return KZGB_BADARGS; }
+        c->W.resize(KZ_N_EXT);
+        Fr acc = fr_const(FR_ONE);
+        for (u32 t = 0; t < KZ_N_EXT; ++t) { c->W[t] = acc; acc = fr_mul(acc, fr_const(FR_OMEGA_INV)); }
+        c->cell_ready = true;
+    }
     *out = c;
     return KZGB_OK;
 }
@@ -230,6 +251,10 @@ kzgb_ret verify_kzg_proof_batch(bool* ok, const uint8_t* C, const uint8_t* z, co
     return emu_verify(ok, C, z, y, pi, n, c, false);
 }
 kzgb_ret kzgb_last_artifacts(kzgb_ctx* c, kzgb_artifacts* out) {
+    if (c->have_ab) {
+        aff_to_be96(c->art.A, jac_to_aff(c->ab[0]));
+        aff_to_be96(c->art.B, jac_to_aff(c->ab[1]));
+    }
     if (c->have_sums) {
         u32 k[8];
         for (int i = 0; i < 8; ++i) k[i] = c->sum_ry.v[i];
@@ -370,8 +395,97 @@ kzgb_ret kzgb_debug_op(kzgb_ctx* c, int op, const uint8_t* in, uint8_t* out, siz
     return KZGB_OK;
 }
 
+// cell batch through the device bodies (cells.cuh), one "block" per opening
+kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, const uint32_t* ci, const uint32_t* xi,
+                                     const uint8_t* cells, const uint8_t* proofs, size_t m, kzgb_ctx* c) {
+    *ok = false;
+    if (!c->cell_ready || !m || !nc) return KZGB_BADARGS;
+    memset(&c->art, 0, sizeof c->art);
+    c->art.n = m;
+    c->have_sums = false; c->have_ab = false;
+    const size_t M = m + nc + 64;
+    std::vector<Fp> pts(2 * M);
+    u32 badp = 0, bads = 0;
+    for (size_t i = 0; i < m + nc; ++i) {
+        u32 w[12];
+        words_from_be(w, i < m ? proofs + 48 * i : comms + 48 * (i - m), 12);
+        G1Aff p;
+        badp += g1_decompress_validate(p, w) != ST_OK;
+        pts[2 * i] = p.x; pts[2 * i + 1] = p.y;
+    }
+    for (int j = 0; j < 64; ++j) { pts[2 * (m + nc + j)] = c->cell_g1[j].x; pts[2 * (m + nc + j) + 1] = c->cell_g1[j].y; }
+    // leaves -> chunk digests -> root
+    std::vector<u32> leaves(8 * m);
+    for (size_t k = 0; k < m; ++k)
+        fs_cell_leaf_words(&leaves[8 * k], ci[k], xi[k], reinterpret_cast<const u32*>(cells + 2048 * k), reinterpret_cast<const u32*>(proofs + 48 * k));
+    size_t nch = (m + 1023) / 1024;
+    std::vector<u8> dig(32 * nch);
+    for (size_t j = 0; j < nch; ++j) {
+        u32 h[8];
+        fs_chunk_words(h, &leaves[8 * j * 1024], (u32)std::min<size_t>(1024, m - j * 1024));
+        words_to_be(&dig[32 * j], h, 8);
+    }
+    auto sha_msg = [](std::vector<u8> msg, u8 out[32]) {
+        u64 bits = msg.size() * 8;
+        msg.push_back(0x80);
+        while (msg.size() % 64 != 56) msg.push_back(0);
+        for (int i = 0; i < 8; ++i) msg.push_back((u8)(bits >> (56 - 8 * i)));
+        u32 h[8];
+        sha256_init(h);
+        for (size_t b = 0; b < msg.size(); b += 64) { u32 w[16]; words_from_be(w, &msg[b], 16); sha256_compress(h, w); }
+        words_to_be(out, h, 8);
+    };
+    u8 cdig[32], root[32];
+    {
+        std::vector<u8> msg;
+        const char* tag = "KZGB200/comm_v1_";
+        msg.insert(msg.end(), tag, tag + 16);
+        msg.insert(msg.end(), comms, comms + 48 * nc);
+        sha_msg(msg, cdig);
+        std::vector<u8> r;
+        const char* tag2 = "KZGB200/croot_v1";
+        r.insert(r.end(), tag2, tag2 + 16);
+        for (int i = 0; i < 8; ++i) r.push_back((u8)((u64)nc >> (56 - 8 * i)));
+        for (int i = 0; i < 8; ++i) r.push_back((u8)((u64)m >> (56 - 8 * i)));
+        r.insert(r.end(), cdig, cdig + 32);
+        r.insert(r.end(), dig.begin(), dig.end());
+        sha_msg(r, root);
+    }
+    memcpy(c->art.root, root, 32);
+    u32 rw[8];
+    words_from_be(rw, root, 8);
+    std::vector<Fr> coefs(64 * m);
+    std::vector<u32> r(4 * m), rz(8 * M);
+    for (size_t k = 0; k < m; ++k) {
+        CellScratch S;
+        coop_cell_body(S, c->W.data(), rw, (u64)k, ci[k], xi[k], (u32)nc, cells + 2048 * k, &coefs[64 * k], &r[4 * k], &rz[8 * k]);
+        bads += S.bad;
+    }
+    c->art.n_bad_points = badp; c->art.n_bad_scalars = bads;
+    if (badp || bads) return KZGB_BADARGS;
+    for (size_t i = 0; i < nc; ++i) {            // w_i
+        Fr acc = fr_zero();
+        for (size_t k = 0; k < m; ++k) if (ci[k] == i) { Fr v = fr_zero(); for (int j = 0; j < 4; ++j) v.v[j] = r[4 * k + j]; acc = fr_add(acc, v); }
+        for (int j = 0; j < 8; ++j) rz[8 * (m + i) + j] = acc.v[j];
+    }
+    for (int i = 0; i < 64; ++i) {               // -S_i
+        Fr acc = fr_zero();
+        for (size_t k = 0; k < m; ++k) acc = fr_add(acc, coefs[64 * k + i]);
+        Fr neg = fr_from_mont(fr_neg(acc));
+        for (int j = 0; j < 8; ++j) rz[8 * (m + nc + i) + j] = neg.v[j];
+    }
+    G1Jac a = emu_msm(pts.data(), rz.data(), 8, M, 255);
+    G1Jac bsum = emu_msm(pts.data(), r.data(), 4, m, 128);
+    c->ab[0] = a; c->ab[1] = jac_neg(bsum);
+    c->have_ab = true;
+    PairScratch S;
+    coop_pairing_check(S, c->lines_cell, c->ab);
+    *ok = S.result == 1;
+    return KZGB_OK;
+}
+
 // entry points of kzgb200.h that the emulation does not model
-kzgb_ret verify_cell_kzg_proof_batch(bool*, const uint8_t*, size_t, const uint32_t*, const uint32_t*, const uint8_t*, const uint8_t*, size_t, kzgb_ctx*) { return KZGB_ERROR; }
+
 kzgb_ret verify_kzg_proof_batch_device(bool*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, kzgb_ctx*, void*) { return KZGB_ERROR; }
 kzgb_ret kzgb_shard_phase1(kzgb_ctx*, int, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, int, void*, uint8_t*, uint32_t*) { return KZGB_ERROR; }
 kzgb_ret kzgb_fs_root(uint8_t*, const uint8_t*, size_t, uint64_t) { return KZGB_ERROR; }

@@ -207,3 +207,30 @@ def check_status_classes(gpu_ctx, oracle_ctx, n=64):
             assert gpu_ctx.verify_kzg_proof_batch(Cb, Z, Y, Pb, n) == oracle_ctx.verify_kzg_proof_batch(Cb, Z, Y, Pb, n) == (1, False)
             a1, a2 = gpu_ctx.last_artifacts(), oracle_ctx.last_artifacts()
             assert a1["n_bad_points"] == a2["n_bad_points"] == 1 and a1["n_bad_scalars"] == a2["n_bad_scalars"] == 0
+
+
+def check_cell_batch(ctx, oracle, inst):
+    """inst = (commitments, commitment_indices, cell_indices, cells, proofs) from the oracle generator."""
+    comms, ci, xi, cells, proofs = inst
+    m = len(ci)
+    assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, cells, proofs) == oracle.verify_cell_kzg_proof_batch(comms, ci, xi, cells, proofs) == (0, True)
+    a1, a2 = ctx.last_artifacts(), oracle.last_artifacts()
+    assert a1["A"] == a2["A"] and a1["B"] == a2["B"] and a1["root"] == a2["root"]
+    bad = bytearray(cells); bad[2048 * (m - 1) + 32 * 7 + 31] ^= 1                 # one evaluation tampered
+    assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, bytes(bad), proofs) == oracle.verify_cell_kzg_proof_batch(comms, ci, xi, bytes(bad), proofs) == (0, False)
+    a1, a2 = ctx.last_artifacts(), oracle.last_artifacts()
+    assert a1["A"] == a2["A"] and a1["B"] == a2["B"]
+    xi2 = list(xi); xi2[0] = (xi2[0] + 5) % 128                                      # wrong coset
+    assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi2, cells, proofs) == oracle.verify_cell_kzg_proof_batch(comms, ci, xi2, cells, proofs) == (0, False)
+    if m >= 2:
+        pr2 = proofs[48:96] + proofs[:48] + proofs[96:]
+        assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, cells, pr2) == oracle.verify_cell_kzg_proof_batch(comms, ci, xi, cells, pr2) == (0, False)
+    # malformed inputs
+    bad = bytearray(cells); bad[32:64] = b"\xff" * 32
+    assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, bytes(bad), proofs) == oracle.verify_cell_kzg_proof_batch(comms, ci, xi, bytes(bad), proofs) == (1, False)
+    xi3 = list(xi); xi3[-1] = 128
+    assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi3, cells, proofs) == (1, False)
+    ci3 = list(ci); ci3[-1] = len(comms) // 48
+    assert ctx.verify_cell_kzg_proof_batch(comms, ci3, xi, cells, proofs) == (1, False)
+    assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, cells, b.g1_compress((0, 2)) + proofs[48:]) == (1, False)
+    assert ctx.verify_cell_kzg_proof_batch(b.g1_compress((0, 2)) + comms[48:], ci, xi, cells, proofs) == (1, False)

@@ -66,3 +66,14 @@ def test_emu_degenerate(emu_ctx, oracle_ctx):
 
 def test_emu_status_classes(emu_ctx, oracle_ctx):
     ps.check_status_classes(emu_ctx, oracle_ctx, n=4)
+
+
+def test_emu_cell_batch(oracle_lib):
+    """Cell batch (config[4]) through the device bodies vs the oracle: verdicts and pairing inputs."""
+    from kzg_batch_verification_scheme_b200.api import KzgLib
+    from tests.test_cells_oracle import synth_cells
+    lib = KzgLib(ROOT / "tests" / "emu" / "libkzgb_emu.so")
+    g1, g2 = oracle_lib.synth_setup(64, 65)
+    ctx, octx = lib.context(g1, g2), oracle_lib.context(g1, g2)
+    ps.check_cell_batch(ctx, octx, synth_cells(oracle_lib, 0x4B5A4724, 2, 3, 200))
+    ctx.close(); octx.close()

@@ -212,3 +212,43 @@ def test_gpu_config0_real_polynomials_n64(gpu_ctx, oracle_ctx, oracle_lib):
         assert a1[key] == a2[key], key
     Ybad = Y[:32 * 5] + ((int.from_bytes(Y[32 * 5:32 * 6], "big") + 1) % b.R).to_bytes(32, "big") + Y[32 * 6:]
     assert gpu_ctx.verify_kzg_proof_batch(C, Z, Ybad, PI, n) == oracle_ctx.verify_kzg_proof_batch(C, Z, Ybad, PI, n) == (0, False)
+
+
+def test_gpu_cell_batch_small(gpu_lib, oracle_lib):
+    from tests.test_cells_oracle import synth_cells
+    g1, g2 = oracle_lib.synth_setup(64, 65)
+    ctx, octx = gpu_lib.context(g1, g2, n_max=4096), oracle_lib.context(g1, g2)
+    ps.check_cell_batch(ctx, octx, synth_cells(oracle_lib, 0x4B5A4724, 2, 3, 200))
+    ps.check_cell_batch(ctx, octx, synth_cells(oracle_lib, 0x4B5A4725, 5, 40, 4096))
+    # the plain batch entry points keep working on an extended-setup context
+    C, Z, Y, PI = octx.synth_instance(0x4B5A4726, 0, 33)
+    assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, 33) == octx.verify_kzg_proof_batch(C, Z, Y, PI, 33) == (0, True)
+    # and a context without the extended setup refuses the cell batch
+    plain = gpu_lib.context(n_max=4096)
+    inst = synth_cells(oracle_lib, 1, 1, 1, 64)
+    assert plain.verify_cell_kzg_proof_batch(*inst) == (1, False)
+    plain.close(); ctx.close(); octx.close()
+
+
+def test_gpu_config4_cell_batch_128x128(gpu_lib, oracle_lib):
+    """BASELINE.json config[4]: 128 blobs x 128 cells = 2^14 multi-point openings (one GPU; the work is ~ms)."""
+    import time
+    from tests.test_cells_oracle import synth_cells
+    g1, g2 = oracle_lib.synth_setup(64, 65)
+    ctx, octx = gpu_lib.context(g1, g2, n_max=1 << 15), oracle_lib.context(g1, g2)
+    comms, ci, xi, cells, proofs = synth_cells(oracle_lib, 0x4B5A4704, 128, 128, 4096)
+    assert len(ci) == 1 << 14
+    assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, cells, proofs) == (0, True)
+    t0 = time.perf_counter()
+    assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, cells, proofs) == (0, True)
+    gpu_s = time.perf_counter() - t0
+    a1 = ctx.last_artifacts()
+    t0 = time.perf_counter()
+    assert octx.verify_cell_kzg_proof_batch(comms, ci, xi, cells, proofs) == (0, True)
+    cpu_s = time.perf_counter() - t0
+    a2 = octx.last_artifacts()
+    assert a1["A"] == a2["A"] and a1["B"] == a2["B"] and a1["root"] == a2["root"]
+    print(f"cell batch 2^14 openings: gpu {gpu_s * 1e3:.1f} ms (host buffers, device ms {a1['stage_ms']['total']:.2f}), cpu oracle {cpu_s * 1e3:.0f} ms")
+    bad = bytearray(cells); bad[2048 * 7777 + 32 * 13 + 30] ^= 4
+    assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, bytes(bad), proofs) == (0, False)
+    ctx.close(); octx.close()
