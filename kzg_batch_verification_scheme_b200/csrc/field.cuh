@@ -116,7 +116,43 @@ KZ_HD Fp fp_pow_const(const Fp& a, const u32* e, int nbits) {
     }
     return r;
 }
-KZ_COLD Fp fp_inv(const Fp& a) { return fp_pow_const(a, EXP_PM2, 381); }   // inv(0) = 0
+// Inversion by the binary extended Euclidean algorithm on the canonical limbs (variable time: nothing here
+// is secret).  ~760 shift/subtract steps instead of the ~570 Montgomery products of a Fermat power -- the
+// inversion sits on latency-critical single-thread paths (pairing, Jacobian -> affine).  inv(0) = 0.
+// Input a*R (Montgomery); the Euclid result (a R)^-1 is brought back with one product by R^3.
+KZ_COLD Fp fp_inv(const Fp& a) {
+    u32 orv = 0;
+    for (int i = 0; i < 12; ++i) orv |= a.v[i];
+    if (!orv) return fp_zero();
+    u32 u[12], v[12], x1[12], x2[12], p[12];
+    for (int i = 0; i < 12; ++i) { u[i] = a.v[i]; p[i] = FP_P[i]; v[i] = p[i]; x1[i] = 0; x2[i] = 0; }
+    x1[0] = 1;
+    auto is_one = [](const u32* w) { u32 o = w[0] ^ 1u; for (int i = 1; i < 12; ++i) o |= w[i]; return o == 0; };
+    auto shr1 = [](u32* w) { for (int i = 0; i < 11; ++i) w[i] = (w[i] >> 1) | (w[i + 1] << 31); w[11] >>= 1; };
+    auto half_mod = [&](u32* w) {              // w <- w / 2 mod p
+        if (w[0] & 1u) { u64 c = 0; for (int i = 0; i < 12; ++i) { u64 s = (u64)w[i] + p[i] + c; w[i] = (u32)s; c = s >> 32; } }
+        for (int i = 0; i < 11; ++i) w[i] = (w[i] >> 1) | (w[i + 1] << 31);
+        w[11] >>= 1;
+    };
+    auto sub_to = [](u32* w, const u32* y) {   // w <- w - y, returns borrow
+        u64 bw = 0;
+        for (int i = 0; i < 12; ++i) { u64 s = (u64)w[i] - y[i] - bw; w[i] = (u32)s; bw = (s >> 32) & 1; }
+        return (u32)bw;
+    };
+    auto sub_mod = [&](u32* w, const u32* y) { // w <- w - y mod p
+        if (sub_to(w, y)) { u64 c = 0; for (int i = 0; i < 12; ++i) { u64 s = (u64)w[i] + p[i] + c; w[i] = (u32)s; c = s >> 32; } }
+    };
+    for (int guard = 0; guard < 2000 && !is_one(u) && !is_one(v); ++guard) {
+        while (!(u[0] & 1u)) { shr1(u); half_mod(x1); }
+        while (!(v[0] & 1u)) { shr1(v); half_mod(x2); }
+        if (limbs_ge12(u, v)) { sub_to(u, v); sub_mod(x1, x2); }
+        else { sub_to(v, u); sub_mod(x2, x1); }
+    }
+    Fp r;
+    const u32* res = is_one(u) ? x1 : x2;
+    for (int i = 0; i < 12; ++i) r.v[i] = res[i];
+    return fp_mul(r, fp_const(FP_R3));
+}
 // big-endian 48 bytes <-> raw limbs
 KZ_HD void fp_raw_from_be(Fp& r, const u8* b) {
     KZ_UNROLL for (int i = 0; i < 12; ++i) {

@@ -234,3 +234,50 @@ def check_cell_batch(ctx, oracle, inst):
     assert ctx.verify_cell_kzg_proof_batch(comms, ci3, xi, cells, proofs) == (1, False)
     assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, cells, b.g1_compress((0, 2)) + proofs[48:]) == (1, False)
     assert ctx.verify_cell_kzg_proof_batch(b.g1_compress((0, 2)) + comms[48:], ci, xi, cells, proofs) == (1, False)
+
+
+def check_random_differential(gpu_ctx, oracle_ctx, sizes=(1, 2, 3, 17, 64, 255, 256, 1000, 1024, 1025, 2049, 3000), trials=40, pool=3000):
+    """Randomised differential test: random batch sizes and random single-byte / structural corruptions;
+    return code, verdict and (when well-formed) the pairing inputs must equal the oracle's."""
+    rnd = random.Random(20261018)
+    C0, Z0, Y0, PI0 = oracle_ctx.synth_instance(0x4B5A4730, 0, pool)
+    specials = [b.g1_compress(None), b.g1_compress((0, 2)), bytes(48), b"\xff" * 48, b.g1_compress(b.G1), b.g1_compress(b.g1_neg(b.G1))]
+    outcomes = {}
+    for trial in range(trials):
+        n = rnd.choice(list(sizes))
+        off = rnd.randrange(0, pool - n + 1)
+        arrs = [bytearray(C0[48 * off:48 * (off + n)]), bytearray(Z0[32 * off:32 * (off + n)]), bytearray(Y0[32 * off:32 * (off + n)]),
+                bytearray(PI0[48 * off:48 * (off + n)])]
+        widths = [48, 32, 32, 48]
+        kind = rnd.choice(["none", "flip", "flip", "special", "swap", "dup", "highbit"])
+        if kind == "flip":
+            a = rnd.randrange(4)
+            arrs[a][rnd.randrange(len(arrs[a]))] ^= 1 << rnd.randrange(8)
+        elif kind == "special":
+            a = rnd.choice([0, 3])
+            j = rnd.randrange(n)
+            arrs[a][48 * j:48 * j + 48] = rnd.choice(specials)
+        elif kind == "swap" and n >= 2:
+            a = rnd.randrange(4)
+            w = widths[a]
+            i, j = rnd.sample(range(n), 2)
+            arrs[a][w * i:w * i + w], arrs[a][w * j:w * j + w] = arrs[a][w * j:w * j + w], arrs[a][w * i:w * i + w]
+        elif kind == "dup" and n >= 2:
+            i, j = rnd.sample(range(n), 2)
+            for a, w in enumerate(widths):
+                arrs[a][w * j:w * j + w] = arrs[a][w * i:w * i + w]
+        elif kind == "highbit":
+            a = rnd.choice([1, 2])
+            j = rnd.randrange(n)
+            arrs[a][32 * j] |= 0x80                       # scalar >= r
+        args = [bytes(x) for x in arrs] + [n]
+        r1 = gpu_ctx.verify_kzg_proof_batch(*args)
+        r2 = oracle_ctx.verify_kzg_proof_batch(*args)
+        assert r1 == r2, (trial, kind, n, r1, r2)
+        outcomes[r1] = outcomes.get(r1, 0) + 1
+        a1, a2 = gpu_ctx.last_artifacts(), oracle_ctx.last_artifacts()
+        assert a1["n_bad_points"] == a2["n_bad_points"] and a1["n_bad_scalars"] == a2["n_bad_scalars"], (trial, kind)
+        if r1[0] == 0:
+            for key in ("S1", "S2", "S3", "A", "B", "sum_ry", "root"):
+                assert a1[key] == a2[key], (trial, kind, key)
+    assert len(outcomes) >= 2, outcomes          # at least two of accepted / rejected / malformed were exercised

@@ -77,3 +77,7 @@ def test_emu_cell_batch(oracle_lib):
     ctx, octx = lib.context(g1, g2), oracle_lib.context(g1, g2)
     ps.check_cell_batch(ctx, octx, synth_cells(oracle_lib, 0x4B5A4724, 2, 3, 200))
     ctx.close(); octx.close()
+
+
+def test_emu_random_differential(emu_ctx, oracle_ctx):
+    ps.check_random_differential(emu_ctx, oracle_ctx, sizes=(1, 2, 3, 9), trials=14, pool=12)

@@ -252,3 +252,7 @@ def test_gpu_config4_cell_batch_128x128(gpu_lib, oracle_lib):
     bad = bytearray(cells); bad[2048 * 7777 + 32 * 13 + 30] ^= 4
     assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, bytes(bad), proofs) == (0, False)
     ctx.close(); octx.close()
+
+
+def test_gpu_random_differential(gpu_ctx, oracle_ctx):
+    ps.check_random_differential(gpu_ctx, oracle_ctx)
