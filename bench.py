@@ -269,7 +269,9 @@ def main():
             ach = k1_imad / (k1_ms * 1e-3)
             roofline = {"bound": "imad", "kernel": "K1 = k_decompress_sqrt + k_subgroup_chain1 + k_subgroup_chain2 (one stage, 3 launches)",
                         "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T wide-IMAD/s", "frac": ach / imad_peak,
-                        "traffic": None,
+                        # dram__bytes_read+write per launch from the ncu --set full captures of the three K1 kernels at
+                        # n = 65536 (profiles/r1_k1[abc]_*: 22.2 + 12.7 + 31.6 MB for 131072 points = 507 B/point), scaled to this n
+                        "traffic": 2 * n_local * 507,
                         "peak_source": peak_src + ": carry-chained mad.lo.cc/madc.hi.cc (SASS IMAD.WIDE.U32.X) on all SMs, measured in this "
                                        "run; 32 lanes/clk/SM on B200 (148 x 32 x 1.965 GHz = 9.31 T/s nominal)",
                         "imad32_issue_peak": imad32_peak / 1e12,
