@@ -25,6 +25,7 @@ namespace {
 
 struct SortBuf {
     uint32_t *keys = nullptr, *vals = nullptr, *keys_alt = nullptr, *vals_alt = nullptr, *bucket_start = nullptr;
+    uint32_t *count = nullptr, *cursor = nullptr;
     size_t capacity = 0;
 };
 
@@ -45,8 +46,6 @@ struct DeviceSlot {
     SortBuf sortR, sortZ;
     G1Xyzz *bucketsA = nullptr, *bucketsB = nullptr, *bucketsC = nullptr, *segsums = nullptr, *winsums = nullptr;
     size_t max_bucketsR = 0, max_bucketsZ = 0, max_segs = 0;
-    void* cub_temp = nullptr;
-    size_t cub_temp_bytes = 0;
     ChunkRecs recs = {nullptr, nullptr, nullptr, nullptr, nullptr};      // sum S2' (and kzgb_g1_msm)
     ChunkRecs recsA = {nullptr, nullptr, nullptr, nullptr, nullptr}, recsB = {nullptr, nullptr, nullptr, nullptr, nullptr};
     G1Jac* sums = nullptr;             // [0] S1 [1] S2' [2] S3 [3] A [4] B
@@ -98,7 +97,7 @@ cudaError_t dmalloc(T*& p, size_t count) { return cudaMalloc((void**)&p, count *
 kzgb_ret slot_alloc_sort(SortBuf& b, size_t cap, size_t buckets) {
     b.capacity = cap;
     CK(dmalloc(b.keys, cap)); CK(dmalloc(b.vals, cap)); CK(dmalloc(b.keys_alt, cap)); CK(dmalloc(b.vals_alt, cap));
-    CK(dmalloc(b.bucket_start, buckets + 2));
+    CK(dmalloc(b.bucket_start, buckets + 2)); CK(dmalloc(b.count, buckets + 2)); CK(dmalloc(b.cursor, buckets + 2));
     return KZGB_OK;
 }
 
@@ -163,8 +162,6 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
             CK(dmalloc(r->head_key, tr)); CK(dmalloc(r->tail_key, tr)); CK(dmalloc(r->head_flags, tr));
         }
     }
-    s.cub_temp_bytes = msm_cub_temp_bytes(capZ) + 256;
-    CK(cudaMalloc(&s.cub_temp, s.cub_temp_bytes));
     CK(dmalloc(s.sums, 5)); CK(dmalloc(s.partial_dev, KZGB_PARTIAL_BYTES)); CK(dmalloc(s.partials_in, KZGB_PARTIAL_BYTES * 64));
     CK(dmalloc(s.scratch, 1 << 20));
     CK(dmalloc(s.result_dev, 4)); CK(dmalloc(s.lines, 2)); CK(dmalloc(s.g1_pt, 2)); CK(dmalloc(s.setup_status, 4));
@@ -210,9 +207,10 @@ void slot_free(DeviceSlot& s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     if (s.stream2) cudaStreamSynchronize(s.stream2);
     void* dev[] = {s.dC, s.dz, s.dy, s.dpi, s.pts, s.k1_tmp, s.status, s.counters, s.leaves, s.digests, s.root_words, s.r, s.rz,
-                   s.partials, s.sum_ry, s.zs, s.sortR.keys, s.sortR.vals, s.sortR.keys_alt, s.sortR.vals_alt, s.sortR.bucket_start,
+                   s.partials, s.sum_ry, s.zs, s.sortR.keys, s.sortR.vals, s.sortR.keys_alt, s.sortR.vals_alt, s.sortR.bucket_start, s.sortR.count, s.sortR.cursor,
+                   s.sortZ.count, s.sortZ.cursor,
                    s.sortZ.keys, s.sortZ.vals, s.sortZ.keys_alt, s.sortZ.vals_alt, s.sortZ.bucket_start, s.bucketsA,
-                   s.bucketsB, s.bucketsC, s.segsums, s.winsums, s.cub_temp, s.sums, s.partial_dev, s.partials_in,
+                   s.bucketsB, s.bucketsC, s.segsums, s.winsums, s.sums, s.partial_dev, s.partials_in,
                    s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb, s.recs.head, s.recs.tail,
                    s.recs.head_key, s.recs.tail_key, s.recs.head_flags, s.recsA.head, s.recsA.tail, s.recsA.head_key,
                    s.recsA.tail_key, s.recsA.head_flags, s.recsB.head, s.recsB.tail, s.recsB.head_key, s.recsB.tail_key,
@@ -231,8 +229,9 @@ void slot_free(DeviceSlot& s) {
 MsmWorkspace make_ws(DeviceSlot& s, SortBuf& b, G1Xyzz* buckets) {
     MsmWorkspace ws;
     ws.keys = b.keys; ws.vals = b.vals; ws.keys_alt = b.keys_alt; ws.vals_alt = b.vals_alt;
-    ws.capacity = b.capacity; ws.bucket_start = b.bucket_start; ws.buckets = buckets; ws.segsums = s.segsums;
-    ws.winsums = s.winsums; ws.recs = s.recs; ws.cub_temp = s.cub_temp; ws.cub_temp_bytes = s.cub_temp_bytes;
+    ws.capacity = b.capacity; ws.bucket_start = b.bucket_start; ws.count = b.count; ws.cursor = b.cursor;
+    ws.buckets = buckets; ws.segsums = s.segsums;
+    ws.winsums = s.winsums; ws.recs = s.recs;
     ws.max_buckets = 0; ws.max_segs = s.max_segs;
     return ws;
 }

@@ -1,15 +1,15 @@
 // K4-K7: Pippenger MSM kernels (BASELINE.json:5 item (d)).
 //   K4 digits     one thread per scalar: signed-window recoding -> (bucket key, point|sign) pairs
-//   K5 sort       radix sort of the pairs by bucket key (CUB DeviceRadixSort, first cut -- SURVEY 2.2 S5)
-//                 + bucket boundary detection
+//   K5 sort       hand-written counting sort of the pairs by bucket key: the key space is the bucket table itself
+//                 (<= 2^19 keys), so one histogram pass (fused into K4), one exclusive scan -- which IS the bucket
+//                 boundary table -- and one scatter pass replace a multi-pass radix sort.  The order inside a
+//                 bucket is arbitrary; bucket sums are group elements, so every canonical output is unchanged.
 //   K6 accumulate bucket sums in XYZZ (mixed additions with the affine points)
 //   K7 reduce     per-segment running sums, per-window block reduction, Horner combine over windows
-#include <cub/device/device_radix_sort.cuh>
-
 #include "kernels.h"
 
 __global__ void __launch_bounds__(128) k_msm_digits(const u32* __restrict__ scalars, int nl, size_t m,
-                                                    u32* __restrict__ keys, u32* __restrict__ vals,
+                                                    u32* __restrict__ keys, u32* __restrict__ vals, u32* __restrict__ count,
                                                     const __grid_constant__ MsmPlan plan) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
@@ -17,6 +17,44 @@ __global__ void __launch_bounds__(128) k_msm_digits(const u32* __restrict__ scal
 #pragma unroll
     for (int k = 0; k < 8; ++k) sc[k] = k < nl ? scalars[(size_t)nl * i + k] : 0u;
     msm_digits_body(keys, vals, sc, i, m, plan);
+    // histogram of the keys just written (total_buckets + 1 counters; the last one collects zero digits)
+    for (int w = 0; w < plan.W; ++w) atomicAdd(&count[keys[(size_t)w * m + i]], 1u);
+}
+
+// exclusive scan of count[0 .. nkeys) into start[0 .. nkeys] (start[nkeys] = N) and a working copy `cursor`.
+// One block: each thread owns a contiguous slice, block-level scan of the slice totals in shared memory.
+#define KZ_SCAN_THREADS 1024
+__global__ void __launch_bounds__(KZ_SCAN_THREADS) k_bucket_scan(const u32* __restrict__ count, u32 nkeys, u32* __restrict__ start,
+                                                                 u32* __restrict__ cursor) {
+    __shared__ u32 part[KZ_SCAN_THREADS];
+    u32 per = (nkeys + KZ_SCAN_THREADS - 1) / KZ_SCAN_THREADS;
+    u32 lo = threadIdx.x * per, hi = lo + per < nkeys ? lo + per : nkeys;
+    u32 sum = 0;
+    for (u32 k = lo; k < hi; ++k) sum += count[k];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < KZ_SCAN_THREADS; off <<= 1) {          // Hillis-Steele inclusive scan
+        u32 v = (int)threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    u32 run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+    for (u32 k = lo; k < hi; ++k) {
+        start[k] = run;
+        cursor[k] = run;
+        run += count[k];
+    }
+    if (threadIdx.x == KZ_SCAN_THREADS - 1) start[nkeys] = part[KZ_SCAN_THREADS - 1];
+}
+__global__ void __launch_bounds__(256) k_bucket_scatter(const u32* __restrict__ keys, const u32* __restrict__ vals, size_t N,
+                                                        u32* __restrict__ cursor, u32* __restrict__ skeys, u32* __restrict__ svals) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    u32 k = keys[i];
+    u32 pos = atomicAdd(&cursor[k], 1u);
+    skeys[pos] = k;
+    svals[pos] = vals[i];
 }
 
 // GLV preparation of a 255-bit sum: scalars k -> (k1 | k2) as 2m 128-bit scalars, points P -> phi(P)
@@ -46,17 +84,6 @@ void launch_endo_points(cudaStream_t s, const Fp* src, size_t m, Fp* dst) {
     if (!m) return;
     k_endo_points<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(src, m, dst);
     KZ_COUNT_LAUNCH();
-}
-
-// start[b] = first sorted position with key >= b, for b in [0, total_buckets+1]
-__global__ void k_bucket_bounds(const u32* __restrict__ keys, size_t N, u32 total_buckets, u32* __restrict__ start) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    u32 k = keys[i];
-    u32 kp = i ? keys[i - 1] : 0xFFFFFFFFu;      // treat "before the first" as key -1
-    if (i == 0) { for (u32 b = 0; b <= k; ++b) start[b] = 0; }
-    else if (k != kp) { for (u32 b = kp + 1; b <= k; ++b) start[b] = (u32)i; }
-    if (i == N - 1) { for (u32 b = k + 1; b <= total_buckets + 1; ++b) start[b] = (u32)N; }
 }
 
 __global__ void __launch_bounds__(128) k_msm_chunk_pass1(const Fp* __restrict__ pts, const u32* __restrict__ keys,
@@ -112,25 +139,15 @@ __global__ void k_msm_combine(CombineJobs jobs) {
     *jobs.out[j] = msm_combine_body(jobs.winsums[j], jobs.W[j], jobs.c[j]);
 }
 
-size_t msm_cub_temp_bytes(size_t entries) {
-    size_t bytes = 0;
-    cub::DoubleBuffer<u32> k(nullptr, nullptr), v(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int)entries, 0, 32, (cudaStream_t)0);
-    return bytes;
-}
-
 void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars, int nl, size_t m, MsmWorkspace& ws) {
     size_t N = m * (size_t)plan.W;
-    k_msm_digits<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(scalars, nl, m, ws.keys, ws.vals, plan);
+    u32 nkeys = plan.total_buckets + 1;                  // + the "zero digit" key
+    cudaMemsetAsync(ws.count, 0, sizeof(u32) * (nkeys + 1), s);
+    k_msm_digits<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(scalars, nl, m, ws.keys_alt, ws.vals_alt, ws.count, plan);
     KZ_COUNT_LAUNCH();
-    int end_bit = 1;
-    while ((1u << end_bit) <= plan.total_buckets) ++end_bit;
-    cub::DoubleBuffer<u32> k(ws.keys, ws.keys_alt), v(ws.vals, ws.vals_alt);
-    size_t bytes = ws.cub_temp_bytes;
-    cub::DeviceRadixSort::SortPairs(ws.cub_temp, bytes, k, v, (int)N, 0, end_bit, s);
+    k_bucket_scan<<<1, KZ_SCAN_THREADS, 0, s>>>(ws.count, nkeys, ws.bucket_start, ws.cursor);
     KZ_COUNT_LAUNCH();
-    if (k.Current() != ws.keys) { std::swap(ws.keys, ws.keys_alt); std::swap(ws.vals, ws.vals_alt); }
-    k_bucket_bounds<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(ws.keys, N, plan.total_buckets, ws.bucket_start);
+    k_bucket_scatter<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(ws.keys_alt, ws.vals_alt, N, ws.cursor, ws.keys, ws.vals);
     KZ_COUNT_LAUNCH();
 }
 u32 msm_chunk_len(size_t N) { return N >= (1u << 21) ? 32u : N >= (1u << 20) ? 16u : N >= (1u << 18) ? 8u : 4u; }

@@ -46,21 +46,19 @@ void host_sha256_root(uint8_t out[32], const uint8_t* digests, size_t n_chunks, 
 struct MsmWorkspace {
     uint32_t *keys, *vals, *keys_alt, *vals_alt;   // capacity entries each
     size_t capacity;
-    uint32_t* bucket_start;                        // total_buckets + 2
+    uint32_t* bucket_start;                        // total_buckets + 2: exclusive scan of the key histogram
+    uint32_t *count, *cursor;                      // total_buckets + 2 each: histogram, scatter cursors
     G1Xyzz* buckets;                               // max total buckets
     G1Xyzz* segsums;                               // max total segs
     G1Xyzz* winsums;                               // KZ_MSM_MAX_WINDOWS
     ChunkRecs recs;                                // partial records, capacity/4 + 1 chunks
-    void* cub_temp;
-    size_t cub_temp_bytes;
     size_t max_buckets, max_segs;
 };
-size_t msm_cub_temp_bytes(size_t entries);
 // GLV: 255-bit scalars (8 limbs) -> k1 (m x 4 limbs) | k2 (m x 4 limbs); points P -> phi(P) = (beta^2 x, y)
 void launch_glv_split(cudaStream_t s, const uint32_t* scalars8, size_t m, uint32_t* out4);
 void launch_endo_points(cudaStream_t s, const Fp* src, size_t m, Fp* dst);
 uint32_t msm_chunk_len(size_t N);
-// digits + sort + bucket boundaries for `m` scalars of `nl` limbs each
+// digits + histogram + scan (= bucket boundaries) + scatter for `m` scalars of `nl` limbs each
 void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars, int nl, size_t m, MsmWorkspace& ws);
 // accumulate + reduce + combine over points `pts` (2 Fp each, m points) using the sorted entries in ws
 void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, size_t m, MsmWorkspace& ws);
