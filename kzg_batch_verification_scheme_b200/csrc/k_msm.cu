@@ -6,6 +6,8 @@
 //                 bucket is arbitrary; bucket sums are group elements, so every canonical output is unchanged.
 //   K6 accumulate bucket sums in XYZZ (mixed additions with the affine points)
 //   K7 reduce     per-segment running sums, per-window block reduction, Horner combine over windows
+#include <cstdlib>
+
 #include "kernels.h"
 
 __global__ void __launch_bounds__(128) k_msm_digits(const u32* __restrict__ scalars, int nl, size_t m,
@@ -94,6 +96,92 @@ __global__ void __launch_bounds__(128) k_msm_chunk_pass1(const Fp* __restrict__ 
     if (t >= T) return;
     msm_chunk_pass1(pts, keys, vals, start[total_buckets], L, t, buckets, R);
 }
+// Warp-cooperative variant of pass 1 (BASELINE.json:5 item (d): "points staged through shared memory and read
+// with coalesced 128-bit loads").  All 32 lanes walk their runs in lock step; for every step the warp gathers
+// its 32 affine points together: lane l loads 16-byte piece (q*32 + l) % 6 of point (q*32 + l) / 6, so six
+// consecutive lanes read one contiguous 96-byte point and every load instruction touches fully used sectors
+// (the per-lane version reads each 32-byte sector twice).  The pieces go to a per-warp shared-memory tile and
+// each lane reads its own point back with six 128-bit shared loads.  The gather for step s+1 is issued
+// before the mixed addition of step s (registers), written to the tile afterwards.
+#define KZ_ACC_WARPS 4
+__global__ void __launch_bounds__(32 * KZ_ACC_WARPS) k_msm_chunk_pass1_staged(const Fp* __restrict__ pts, const u32* __restrict__ keys,
+                                                                              const u32* __restrict__ vals, const u32* __restrict__ start,
+                                                                              u32 total_buckets, u32 L, u32 T,
+                                                                              G1Xyzz* __restrict__ buckets, ChunkRecs R) {
+    __shared__ uint4 tile[KZ_ACC_WARPS][32 * 6];
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint4* my_tile = tile[wid];
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 n_valid = start[total_buckets];
+    const bool active = t < T && t * L < n_valid;
+    if (t < T) { R.head_key[t] = KZ_KEY_NONE; R.tail_key[t] = KZ_KEY_NONE; }
+    const u32 lo = t * L;
+    const u32 hi = active ? (lo + L < n_valid ? lo + L : n_valid) : lo;
+    const u32 prev_key = (active && lo) ? keys[lo - 1] : KZ_KEY_NONE;
+    const u32 next_key = (active && hi < n_valid) ? keys[hi] : KZ_KEY_NONE;
+    u32 cur = active ? keys[lo] : KZ_KEY_NONE;
+    bool is_head = true, done = !active;
+    G1Xyzz acc = xyzz_inf();
+    const uint4* base = reinterpret_cast<const uint4*>(pts);
+    // gather of one step into registers: 6 pieces per lane, point index fetched from the owning lane
+    uint4 piece[6];
+    auto gather = [&](u32 v_mine, bool have_mine) {
+        u32 idx_mine = have_mine ? (v_mine & 0x7FFFFFFFu) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            u32 g = (u32)q * 32u + lane, owner = g / 6u, part = g - owner * 6u;
+            u32 idx = __shfl_sync(0xFFFFFFFFu, idx_mine, owner);
+            piece[q] = idx != 0xFFFFFFFFu ? __ldg(base + (size_t)idx * 6 + part) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    auto publish = [&]() {
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 6; ++q) my_tile[q * 32 + lane] = piece[q];
+        __syncwarp();
+    };
+    u32 v_next = active ? vals[lo] : 0u;
+    gather(v_next, active);
+    publish();
+    for (u32 step = 0; step <= L; ++step) {                    // warp-uniform trip count
+        const u32 j = lo + step;
+        const bool have = !done && j < hi;
+        const u32 k = have ? keys[j] : KZ_KEY_NONE;
+        const u32 v = v_next;
+        // my point of this step from the tile
+        G1Aff p;
+        {
+            const uint4* mine = my_tile + lane * 6;
+            uint4 a = mine[0], b = mine[1], c = mine[2], d = mine[3], e = mine[4], f = mine[5];
+            p.x.v[0] = a.x; p.x.v[1] = a.y; p.x.v[2] = a.z; p.x.v[3] = a.w; p.x.v[4] = b.x; p.x.v[5] = b.y; p.x.v[6] = b.z; p.x.v[7] = b.w;
+            p.x.v[8] = c.x; p.x.v[9] = c.y; p.x.v[10] = c.z; p.x.v[11] = c.w;
+            p.y.v[0] = d.x; p.y.v[1] = d.y; p.y.v[2] = d.z; p.y.v[3] = d.w; p.y.v[4] = e.x; p.y.v[5] = e.y; p.y.v[6] = e.z; p.y.v[7] = e.w;
+            p.y.v[8] = f.x; p.y.v[9] = f.y; p.y.v[10] = f.z; p.y.v[11] = f.w;
+        }
+        // issue the gather of the next step before the arithmetic of this one
+        const bool have_next = !done && j + 1 < hi;
+        v_next = have_next ? vals[j + 1] : 0u;
+        if (step < L) gather(v_next, have_next);
+        if (!done && k != cur) {                               // flush the finished run (k == NONE at j == hi)
+            const bool is_tail = j == hi;
+            const bool starts = is_head ? prev_key != cur : true;
+            const bool ends = is_tail ? next_key != cur : true;
+            if (starts && ends) buckets[cur] = acc;
+            else if (is_head) { R.head[t] = acc; R.head_key[t] = cur; R.head_flags[t] = (starts ? 1u : 0u) | (ends ? 2u : 0u) | (is_tail ? 4u : 0u); }
+            else { R.tail[t] = acc; R.tail_key[t] = cur; }
+            if (is_tail) done = true;
+            cur = k;
+            is_head = false;
+            acc = xyzz_inf();
+        }
+        if (have && !aff_is_inf(p)) {
+            if (v >> 31) p.y = fp_neg(p.y);
+            acc = xyzz_madd(acc, p);
+        }
+        if (step < L) publish();
+    }
+}
+
 __global__ void __launch_bounds__(128) k_msm_chunk_pass2(u32 T, G1Xyzz* __restrict__ buckets, ChunkRecs R) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
@@ -157,8 +245,15 @@ void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, si
     u32 L = msm_chunk_len(N);
     u32 T = (u32)((N + L - 1) / L);
     cudaMemsetAsync(ws.buckets, 0, sizeof(G1Xyzz) * (size_t)plan.total_buckets, s);      // empty buckets = infinity
-    k_msm_chunk_pass1<<<(T + 127) / 128, 128, 0, s>>>(pts, ws.keys, ws.vals, ws.bucket_start, plan.total_buckets, L, T,
-                                                      ws.buckets, ws.recs);
+    static const int staged = [] { const char* e = getenv("KZGB_ACC_STAGED"); return e ? atoi(e) : 1; }();
+    if (staged) {
+        const u32 bt = 32 * KZ_ACC_WARPS;
+        k_msm_chunk_pass1_staged<<<(T + bt - 1) / bt, bt, 0, s>>>(pts, ws.keys, ws.vals, ws.bucket_start, plan.total_buckets, L, T,
+                                                                   ws.buckets, ws.recs);
+    } else {
+        k_msm_chunk_pass1<<<(T + 127) / 128, 128, 0, s>>>(pts, ws.keys, ws.vals, ws.bucket_start, plan.total_buckets, L, T,
+                                                          ws.buckets, ws.recs);
+    }
     KZ_COUNT_LAUNCH();
     k_msm_chunk_pass2<<<(T + 127) / 128, 128, 0, s>>>(T, ws.buckets, ws.recs);
     KZ_COUNT_LAUNCH();
