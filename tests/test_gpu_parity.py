@@ -256,3 +256,50 @@ def test_gpu_config4_cell_batch_128x128(gpu_lib, oracle_lib):
 
 def test_gpu_random_differential(gpu_ctx, oracle_ctx):
     ps.check_random_differential(gpu_ctx, oracle_ctx)
+
+
+def test_gpu_full_size_2p20_properties(gpu_lib, oracle_lib):
+    """BASELINE.json config[3] size (n = 2^20) through size-independent properties: a valid batch is accepted and
+    its pairing inputs satisfy A + tau*B = O (pairing-free check with the known test tau); one swapped
+    pair of proofs is rejected and breaks that relation; two virtual shards give byte-identical A, B, root."""
+    n, seed = 1 << 20, 0x4B5A4703
+    ctx = gpu_lib.context(devices=[0, 0], n_max=n)
+    C, Z, Y, PI = ctx.synth_instance(seed, 0, n)
+    assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)            # two slots on device 0
+    a2 = ctx.last_artifacts()
+    assert oracle_lib.lib.kzgb_oracle_tau_shortcut(a2["A"], a2["B"]) == 1
+    one = gpu_lib.context(n_max=n)
+    assert one.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)            # one slot
+    a1 = one.last_artifacts()
+    assert a1["A"] == a2["A"] and a1["B"] == a2["B"] and a1["root"] == a2["root"] and a1["sum_ry"] == a2["sum_ry"]
+    i, j = 123456, 987654
+    PIb = bytearray(PI)
+    PIb[48 * i:48 * i + 48], PIb[48 * j:48 * j + 48] = PI[48 * j:48 * j + 48], PI[48 * i:48 * i + 48]
+    assert one.verify_kzg_proof_batch(C, Z, Y, bytes(PIb), n) == (0, False)
+    ab = one.last_artifacts()
+    assert oracle_lib.lib.kzgb_oracle_tau_shortcut(ab["A"], ab["B"]) == 0
+    # a slice of the device generator's stream equals the oracle generator's bytes
+    octx = oracle_lib.context()
+    assert octx.synth_instance(seed, 777777, 32) == tuple(x[w * 777777:w * (777777 + 32)] for x, w in ((C, 48), (Z, 32), (Y, 32), (PI, 48)))
+    # MSM linearity at full size: MSM(k) + MSM(k') == MSM(k + k') over 2^20 points
+    rc, aff, st = one.g1_decompress_batch(C)
+    assert rc == 0 and not any(st)
+    import numpy as np
+    rng = np.random.default_rng(3)
+    k1 = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); k1[:, 0] &= 0x1F
+    k2 = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); k2[:, 0] &= 0x1F
+    s_ = k1.astype(np.uint16)[:, ::-1] + k2.astype(np.uint16)[:, ::-1]          # little-endian byte order for the carry walk
+    carry = np.zeros(n, dtype=np.uint16)
+    out = np.zeros((n, 32), dtype=np.uint8)
+    for b_ in range(32):
+        v = s_[:, b_] + carry
+        out[:, b_] = (v & 0xFF).astype(np.uint8)
+        carry = v >> 8
+    ksum = out[:, ::-1].copy()
+    r1 = one.g1_msm(aff, k1.tobytes(), 255)
+    r2 = one.g1_msm(aff, k2.tobytes(), 255)
+    r3 = one.g1_msm(aff, ksum.tobytes(), 255)
+    assert r1[0] == r2[0] == r3[0] == 0
+    unit = (1).to_bytes(32, "big")
+    assert one.g1_msm(r1[1] + r2[1], unit + unit, 255) == (0, r3[1]) and r3[1] != bytes(96)
+    one.close(); ctx.close(); octx.close()
