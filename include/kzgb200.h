@@ -133,7 +133,9 @@ enum {
     KZGB_OP_FP12_INV = 16,   /* in 576 out 576 */
     KZGB_OP_FINAL_EXP = 17,  /* in 576 out 576 : f^(3(p^12-1)/r) */
     KZGB_OP_MILLER_FE = 18,  /* in 192 (A|B affine) out 576 : final_exp(miller(A,G2) miller(B,[tau]G2)) */
-    KZGB_OP_SHA256_64 = 19   /* in 64 out 32 : SHA-256 of a 64-byte message */
+    KZGB_OP_SHA256_64 = 19,  /* in 64 out 32 : SHA-256 of a 64-byte message */
+    KZGB_OP_FPD_MUL = 20,    /* in 96 (a|b) out 48 : a*b through the FP64-limb multiplier (fpd.cuh); equals FP_MUL */
+    KZGB_OP_FPD_SQR_CHAIN = 21 /* in 48 out 48 : a^(2^64) by 64 lazy FP64-limb squarings, reduced once at the end */
 };
 kzgb_ret kzgb_debug_op(kzgb_ctx *ctx, int op, const uint8_t *in, uint8_t *out, size_t count);
 

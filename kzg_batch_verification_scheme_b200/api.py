@@ -21,10 +21,10 @@ STAGE_NAMES = ["h2d", "decompress", "hash", "root_host", "challenges", "msm_sort
 
 OP = dict(FP_MUL=1, FP_SQR=2, FP_ADD=3, FP_SUB=4, FP_INV=5, FP_SQRT_CAND=6, FR_MUL=7, FR_ADD=8, G1_ADD=9,
           G1_DBL=10, G1_MUL=11, G1_MUL_XSQ=12, FP12_MUL=13, FP12_FROB1=14, FP12_FROB2=15, FP12_INV=16,
-          FINAL_EXP=17, MILLER_FE=18, SHA256_64=19)
+          FINAL_EXP=17, MILLER_FE=18, SHA256_64=19, FPD_MUL=20, FPD_SQR_CHAIN=21)
 OP_SIZES = {1: (96, 48), 2: (48, 48), 3: (96, 48), 4: (96, 48), 5: (48, 48), 6: (48, 48), 7: (64, 32), 8: (64, 32),
             9: (192, 96), 10: (96, 96), 11: (128, 96), 12: (96, 96), 13: (1152, 576), 14: (576, 576),
-            15: (576, 576), 16: (576, 576), 17: (576, 576), 18: (192, 576), 19: (64, 32)}
+            15: (576, 576), 16: (576, 576), 17: (576, 576), 18: (192, 576), 19: (64, 32), 20: (96, 48), 21: (48, 48)}
 
 
 class Artifacts(C.Structure):

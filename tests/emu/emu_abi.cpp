@@ -4,6 +4,7 @@
 // indices) so the no-GPU CI can exercise the SAME decompression / subgroup / SHA / MSM / pairing logic
 // that runs on the B200 and diff it against the oracle.  Nothing in the product library links this.
 #include <algorithm>
+#include <cfenv>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "../../kzg_batch_verification_scheme_b200/csrc/pairing.cuh"
 #include "../../kzg_batch_verification_scheme_b200/csrc/sha256.cuh"
 #include "../../kzg_batch_verification_scheme_b200/csrc/cells.cuh"
+#include "../../kzg_batch_verification_scheme_b200/csrc/fpd.cuh"
 
 struct kzgb_ctx {
     G2Lines lines[2];
@@ -387,6 +389,24 @@ kzgb_ret kzgb_debug_op(kzgb_ctx* c, int op, const uint8_t* in, uint8_t* out, siz
                 w[0] = 0x80000000u; w[14] = 0; w[15] = 512;
                 sha256_compress(h, w);
                 words_to_be(out + 32 * i, h, 8);
+                break;
+            }
+            case 20: case 21: {
+                // FP64-limb field: the h chains need round-toward-zero; every other operation is exact
+                const int old = fegetround();
+                fesetround(FE_TOWARDZERO);
+                Fp a, b;
+                if (op == 20) {
+                    fp_from_be(a, in + 96 * i); fp_from_be(b, in + 96 * i + 48);
+                    a = fpd_to_fp(fpd_mul(fpd_from_fp(a), fpd_from_fp(b)));
+                } else {
+                    fp_from_be(a, in + 48 * i);
+                    FpD x = fpd_from_fp(a);
+                    for (int k = 0; k < 64; ++k) x = fpd_sqr(x);
+                    a = fpd_to_fp(x);
+                }
+                fesetround(old);
+                fp_to_be(out + 48 * i, a);
                 break;
             }
             default: return KZGB_BADARGS;

@@ -36,6 +36,19 @@ def check_field_ops(ctx, oracle, n_random=200):
         _same(ctx, oracle, op, data)
 
 
+def check_fpd_ops(ctx, oracle):
+    """FP64-limb multiplier (csrc/fpd.cuh): same bits as the integer Montgomery product, lazy [0, 2p) chains included."""
+    rnd = random.Random(131)
+    vals = edge_fps() + [(1 << 48) - 1, 1 << 48, (1 << 96) - 1, (1 << 336) - 1, P - (1 << 48)] + [rnd.randrange(P) for _ in range(60)]
+    pairs = [(x, y) for x in vals[:18] for y in vals[:18]] + [(rnd.randrange(P), rnd.randrange(P)) for _ in range(400)]
+    data = b"".join(fp_bytes(x) + fp_bytes(y) for x, y in pairs)
+    rc, got = ctx.debug_op("FPD_MUL", data)
+    rc2, want = oracle.debug_op("FP_MUL", data)
+    assert rc == 0 and rc2 == 0 and got == want
+    rc, got = ctx.debug_op("FPD_SQR_CHAIN", b"".join(fp_bytes(x) for x in vals))
+    assert rc == 0 and got == b"".join(fp_bytes(pow(x, 1 << 64, P)) for x in vals)
+
+
 def check_g1_ops(ctx, oracle):
     rnd = random.Random(102)
     pts = [rand_g1(rnd) for _ in range(5)] + [None, rand_curve_point(rnd), (0, 2)]

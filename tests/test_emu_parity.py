@@ -25,6 +25,10 @@ def test_emu_field_ops(emu_ctx, oracle_ctx):
     ps.check_field_ops(emu_ctx, oracle_ctx)
 
 
+def test_emu_fpd_ops(emu_ctx, oracle_ctx):
+    ps.check_fpd_ops(emu_ctx, oracle_ctx)
+
+
 def test_emu_sha_single_block(emu_ctx, oracle_ctx):
     import random
     rnd = random.Random(1)

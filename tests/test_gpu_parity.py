@@ -20,6 +20,10 @@ def test_gpu_field_ops(gpu_ctx, oracle_ctx):
     ps.check_field_ops(gpu_ctx, oracle_ctx, n_random=2000)
 
 
+def test_gpu_fpd_ops(gpu_ctx, oracle_ctx):
+    ps.check_fpd_ops(gpu_ctx, oracle_ctx)
+
+
 def test_gpu_g1_ops(gpu_ctx, oracle_ctx):
     ps.check_g1_ops(gpu_ctx, oracle_ctx)
 
