@@ -152,6 +152,11 @@ kzgb_ret kzgb_last_stage_ms(kzgb_ctx *ctx, float ms_out[KZGB_N_STAGES]);
 uint64_t kzgb_launch_count(const kzgb_ctx *ctx);
 /* threads the oracle uses (oracle library only; product returns 0) */
 int kzgb_set_threads(kzgb_ctx *ctx, int n_threads);
+/* Batches (shards) of at least n_min proofs establish subgroup membership of all 2n points through 128 slice
+ * sums per MSM of the bucket tables that sum r_i C_i and sum r_i pi_i fill anyway (soundness 2^-127 per point,
+ * DESIGN.md "Batched subgroup check"); smaller ones, and any batch in which a slice sum fails, run the
+ * deterministic per-point check.  0 = always per point.  Default 32768 (env KZGB_SG_BATCH_MIN). */
+kzgb_ret kzgb_set_subgroup_batch_min(kzgb_ctx *ctx, size_t n_min);
 const char *kzgb_version(void);
 
 #ifdef __cplusplus

@@ -88,6 +88,7 @@ class KzgLib:
             "kzgb_imad_peak": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
             "kzgb_imad32_peak": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
             "kzgb_last_stage_ms": [vp, C.POINTER(C.c_float * N_STAGES)],
+            "kzgb_set_subgroup_batch_min": [vp, sz],
         }
         for name, args in sig.items():
             f = getattr(lib, name)
@@ -102,7 +103,7 @@ class KzgLib:
                "kzgb_combine_verify", "kzgb_g1_decompress_batch", "kzgb_fs_challenges", "kzgb_g1_msm",
                "kzgb_g1_msm_times", "kzgb_pairing_check", "kzgb_last_artifacts", "kzgb_synth_instance",
                "kzgb_synth_setup", "kzgb_debug_op", "kzgb_imad_peak", "kzgb_imad32_peak", "kzgb_last_stage_ms", "kzgb_launch_count", "kzgb_set_threads",
-               "kzgb_version"]
+               "kzgb_set_subgroup_batch_min", "kzgb_version"]
 
     def version(self) -> str:
         return self.lib.kzgb_version().decode()
@@ -279,6 +280,10 @@ class Context:
 
     def set_threads(self, n: int) -> int:
         return int(self.lib.kzgb_set_threads(self.h, n))
+
+    def set_subgroup_batch_min(self, n_min: int) -> int:
+        """Batches of >= n_min proofs use the batched subgroup check (0: always the per-point check)."""
+        return int(self.lib.kzgb_set_subgroup_batch_min(self.h, n_min))
 
 
 PKG_DIR = Path(__file__).resolve().parent

@@ -35,12 +35,14 @@ struct DeviceSlot {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;    // high-priority side stream: hashes, challenges and sorts overlap K1
     cudaStream_t stream3 = nullptr, stream4 = nullptr;   // the three sums accumulate/reduce concurrently
+    cudaStream_t stream5 = nullptr;    // high priority like stream3: S1 and S3 finish first so that their bucket slices
+                                       // (batched subgroup check) overlap the longer GLV sum on stream4
     // staged inputs (host-pointer API)
     uint8_t *dC = nullptr, *dz = nullptr, *dy = nullptr, *dpi = nullptr;
     Fp* pts = nullptr;                 // 3*n_max + 2 affine points: C | pi | G | phi(pi) | phi(G)
     Fp* k1_tmp = nullptr;              // 3 Fp per point: [|x|]P between the subgroup-check kernels
     uint8_t* status = nullptr;         // 2*n_max
-    uint32_t* counters = nullptr;      // [0] bad points [1] bad scalars
+    uint32_t* counters = nullptr;      // [0] bad points [1] bad scalars [2] slice sums outside G1 (batched check)
     uint32_t *leaves = nullptr, *digests = nullptr, *root_words = nullptr;
     uint32_t *r = nullptr, *rz = nullptr, *zs = nullptr, *partials = nullptr, *sum_ry = nullptr;   // zs: GLV halves of rz
     SortBuf sortR, sortZ;
@@ -48,6 +50,10 @@ struct DeviceSlot {
     size_t max_bucketsR = 0, max_bucketsZ = 0, max_segs = 0;
     ChunkRecs recs = {nullptr, nullptr, nullptr, nullptr, nullptr};      // sum S2' (and kzgb_g1_msm)
     ChunkRecs recsA = {nullptr, nullptr, nullptr, nullptr, nullptr}, recsB = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    G1Xyzz* sg_partial = nullptr;      // batched subgroup check: row/column partials and totals, two sums
+    size_t sg_cap = 0;                 // entries per sum
+    size_t sg_min = 32768;             // batches of at least this many proofs use the batched subgroup check (0 = never)
+    bool sg_batch = false;             // current shard: K1 ran without the per-point chains
     G1Jac* sums = nullptr;             // [0] S1 [1] S2' [2] S3 [3] A [4] B
     uint8_t* partial_dev = nullptr;    // 320
     uint8_t* partials_in = nullptr;    // 320 * 64
@@ -70,9 +76,9 @@ struct DeviceSlot {
     bool have_ab = false;              // sums[3], sums[4] hold the pairing inputs of the last call
     // pinned mailboxes
     uint8_t* h_digests = nullptr;      // 32 * ceil(n_max/1024)
-    uint32_t* h_small = nullptr;       // 64 words: [0..1] counters, [8..15] root words, [16] result
+    uint32_t* h_small = nullptr;       // 64 words: [0..2] counters, [8..15] root words, [16] result
     uint8_t* h_partial = nullptr;      // 320 * 64
-    cudaEvent_t ev[16] = {};
+    cudaEvent_t ev[20] = {};
     // current shard (between phase 1 and phase 2)
     const uint8_t *cur_C = nullptr, *cur_z = nullptr, *cur_y = nullptr, *cur_pi = nullptr;
     size_t cur_n = 0;
@@ -110,8 +116,9 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
         int lo_pri = 0, hi_pri = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
         CK(cudaStreamCreateWithPriority(&s.stream2, cudaStreamNonBlocking, hi_pri));
-        CK(cudaStreamCreateWithFlags(&s.stream3, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&s.stream3, cudaStreamNonBlocking, hi_pri));
         CK(cudaStreamCreateWithFlags(&s.stream4, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&s.stream5, cudaStreamNonBlocking, hi_pri));
     }
     for (auto& e : s.ev) CK(cudaEventCreate(&e));
     CK(dmalloc(s.dC, 48 * (n_max + 1))); CK(dmalloc(s.dz, 32 * (n_max + 1))); CK(dmalloc(s.dy, 32 * (n_max + 1))); CK(dmalloc(s.dpi, 48 * (n_max + 1)));
@@ -143,6 +150,20 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     if (slot_alloc_sort(s.sortR, capR, s.max_bucketsR + 512)) return KZGB_ERROR;
     if (slot_alloc_sort(s.sortZ, capZ, s.max_bucketsZ + 512)) return KZGB_ERROR;
     CK(dmalloc(s.bucketsA, s.max_bucketsR + 512)); CK(dmalloc(s.bucketsB, s.max_bucketsR + 512));
+    {
+        // scratch of the batched subgroup check: worst case over every window width msm_make_plan can pick
+        s.sg_cap = 0;
+        for (int c = 3; c <= 16; ++c) {
+            MsmPlan p;
+            p.nbits = 128; p.c = c; p.W = (128 + c - 1) / c;
+            s.sg_cap = std::max(s.sg_cap, sg_work_entries(p));
+        }
+        CK(dmalloc(s.sg_partial, 2 * s.sg_cap));
+    }
+    {
+        const char* e = getenv("KZGB_SG_BATCH_MIN");
+        if (e) s.sg_min = (size_t)strtoull(e, nullptr, 10);
+    }
     CK(dmalloc(s.bucketsC, s.max_bucketsZ + 512));
     CK(dmalloc(s.segsums, 3 * s.max_segs)); CK(dmalloc(s.winsums, 3 * KZ_MSM_MAX_WINDOWS));
     {   // chunk records for the balanced accumulation: worst case over the chunk-length schedule
@@ -214,7 +235,7 @@ void slot_free(DeviceSlot& s) {
                    s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb, s.recs.head, s.recs.tail,
                    s.recs.head_key, s.recs.tail_key, s.recs.head_flags, s.recsA.head, s.recsA.tail, s.recsA.head_key,
                    s.recsA.tail_key, s.recsA.head_flags, s.recsB.head, s.recsB.tail, s.recsB.head_key, s.recsB.tail_key,
-                   s.recsB.head_flags, s.cell_g1, s.lines_cell, s.cell_W, s.d_cells, s.d_ci, s.d_xi, s.cell_coefs};
+                   s.recsB.head_flags, s.sg_partial, s.cell_g1, s.lines_cell, s.cell_W, s.d_cells, s.d_ci, s.d_xi, s.cell_coefs};
     for (void* p : dev) if (p) cudaFree(p);
     if (s.h_digests) cudaFreeHost(s.h_digests);
     if (s.h_small) cudaFreeHost(s.h_small);
@@ -223,6 +244,7 @@ void slot_free(DeviceSlot& s) {
     if (s.stream2) cudaStreamDestroy(s.stream2);
     if (s.stream3) cudaStreamDestroy(s.stream3);
     if (s.stream4) cudaStreamDestroy(s.stream4);
+    if (s.stream5) cudaStreamDestroy(s.stream5);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -271,6 +293,7 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
     s.cur_n = n;
     s.have_sums = false;
     s.have_ab = false;
+    s.sg_batch = s.sg_min && n >= s.sg_min && n >= 2;             // subgroup membership through the bucket slices of S1 and S3
     CK(cudaEventRecord(s.ev[1], st));                   // C resident
     CK(cudaEventRecord(s.ev[13], s2));                  // pi, z, y resident
     // side stream: hashes (need all four arrays) start before K1 fills the SMs
@@ -280,7 +303,12 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
     size_t nch = (n + KZGB_CHUNK - 1) / KZGB_CHUNK;
     CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, s2));
     CK(cudaEventRecord(s.ev[2], s2));
-    if (!on_device && n >= 32768) {
+    if (s.sg_batch) {
+        // K1a only; commitments first, then (once pi is resident) proofs -- hides most of the H2D copy
+        launch_decompress_sqrt_points(st, s.cur_C, n, s.pts, s.status, s.counters);
+        CK(cudaStreamWaitEvent(st, s.ev[13], 0));
+        launch_decompress_sqrt_points(st, s.cur_pi, n, s.pts + 2 * n, s.status + n, s.counters);
+    } else if (!on_device && n >= 32768) {
         // K1 in two halves: commitments, then (once pi is resident) proofs -- hides most of the H2D copy
         launch_decompress_points(st, s.cur_C, n, s.pts, s.k1_tmp, s.status, s.counters);
         CK(cudaStreamWaitEvent(st, s.ev[13], 0));
@@ -315,7 +343,7 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     s.planZ = msm_make_plan(2 * (n + 1), 128);
     if ((size_t)s.planR.W * n > s.sortR.capacity || (size_t)s.planZ.W * 2 * (n + 1) > s.sortZ.capacity ||
         s.planR.total_buckets > s.max_bucketsR + 512 || s.planZ.total_buckets > s.max_bucketsZ + 512 ||
-        s.planZ.total_segs > s.max_segs || s.planR.total_segs > s.max_segs)
+        s.planZ.total_segs > s.max_segs || s.planR.total_segs > s.max_segs || sg_work_entries(s.planR) > s.sg_cap)
         return KZGB_BADARGS;
     MsmWorkspace wr = make_ws(s, s.sortR, s.bucketsA), wz = make_ws(s, s.sortZ, s.bucketsC);
     msm_sort_stage(s2, s.planR, s.r, 4, n, wr);
@@ -332,16 +360,30 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     CK(cudaEventRecord(s.ev[11], st));
     CK(cudaStreamWaitEvent(s.stream3, s.ev[11], 0));
     CK(cudaStreamWaitEvent(s.stream4, s.ev[11], 0));
-    msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);   // S2' over pi_i, G and their phi images
-    msm_window_sums_stage(s.stream4, s.planZ, wz);
-    CK(cudaEventRecord(s.ev[13], s.stream4));
+    CK(cudaStreamWaitEvent(s.stream5, s.ev[11], 0));
     msm_accumulate_stage(s.stream3, s.planR, s.pts + 2 * n, n, wr2);             // S3 over pi_i
     msm_window_sums_stage(s.stream3, s.planR, wr2);
     CK(cudaEventRecord(s.ev[12], s.stream3));
-    msm_accumulate_stage(st, s.planR, s.pts, n, wr);                             // S1 over C_i
-    msm_window_sums_stage(st, s.planR, wr);
+    msm_accumulate_stage(s.stream5, s.planR, s.pts, n, wr);                      // S1 over C_i
+    CK(cudaEventRecord(s.ev[10], s.stream5));                                    // buckets of S1 complete
+    msm_window_sums_stage(s.stream5, s.planR, wr);
+    CK(cudaEventRecord(s.ev[16], s.stream5));
+    msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);   // S2' over pi_i, G and their phi images
+    msm_window_sums_stage(s.stream4, s.planZ, wz);
+    CK(cudaEventRecord(s.ev[13], s.stream4));
+    if (s.sg_batch) {
+        // batched subgroup check: 128 slice sums of the S3 buckets (all pi_i) and of the S1 buckets (all C_i).
+        // S1 and S3 run at high priority, so this work overlaps the GLV sum (twice the points) on stream4
+        launch_sg_batch_check(s.stream3, s.planR, wr2.buckets, s.sg_partial, s.counters);
+        CK(cudaStreamWaitEvent(s.stream3, s.ev[10], 0));
+        launch_sg_batch_check(s.stream3, s.planR, wr.buckets, s.sg_partial + s.sg_cap, s.counters);
+        // the verdict of the check travels on this stream: the main stream goes on to the pairing without it
+        CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream3));
+        CK(cudaEventRecord(s.ev[9], s.stream3));
+    }
     CK(cudaStreamWaitEvent(st, s.ev[12], 0));
     CK(cudaStreamWaitEvent(st, s.ev[13], 0));
+    CK(cudaStreamWaitEvent(st, s.ev[16], 0));
     CK(cudaEventRecord(s.ev[6], st));
     const MsmPlan* plans[3] = {&s.planR, &s.planR, &s.planZ};
     MsmWorkspace* wss[3] = {&wr, &wr2, &wz};
@@ -349,9 +391,24 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     msm_combine_stage(st, plans, wss, outs, 3);
     launch_make_partial(st, s.sums + 0, s.sums + 1, s.sums + 2, s.sum_ry, s.partial_dev);
     CK(cudaMemcpyAsync(s.h_partial, s.partial_dev, KZGB_PARTIAL_BYTES, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(s.h_small, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[7], st));
+    if (!s.sg_batch) CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     s.have_sums = true;
+    return KZGB_OK;
+}
+
+// After the main stream has been synchronised: if a slice sum of the batched subgroup check fell outside G1,
+// find the offending points with the per-point chains (status bytes, counters[0]) -- the rare path.
+kzgb_ret finish_subgroup(DeviceSlot& s) {
+    if (!s.sg_batch) return KZGB_OK;
+    CK(cudaEventSynchronize(s.ev[9]));                  // counters (incl. the check's verdict) are on the host
+    if (!s.h_small[2]) return KZGB_OK;
+    cudaStream_t st = s.stream;
+    launch_subgroup_points(st, s.pts, 2 * s.cur_n, s.k1_tmp, s.status, s.counters);
+    CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    s.have_sums = false;
     return KZGB_OK;
 }
 
@@ -422,27 +479,42 @@ kzgb_ret verify_common(bool* ok, const uint8_t* C, const uint8_t* z, const uint8
     }
     std::vector<uint8_t> parts(KZGB_PARTIAL_BYTES * G);
     uint32_t badp = 0, bads = 0;
+    // One slot with the batched subgroup check: the pairing does not wait for the check's verdict (its serial
+    // |x|^2 chains finish while the Miller loop runs); the counters are read after both.
+    const bool speculate = G == 1 && ctx->slots[0].sg_batch;
     for (size_t g = 0; g < G; ++g) {
         DeviceSlot& s = ctx->slots[g];
         CK(cudaSetDevice(s.device));
         CK(cudaStreamSynchronize(s.stream));
         CK(cudaGetLastError());
+        if (!speculate) {
+            kzgb_ret frc = finish_subgroup(s);
+            if (frc) return frc;
+            badp += s.h_small[0];
+            bads += s.h_small[1];
+        }
         memcpy(parts.data() + KZGB_PARTIAL_BYTES * g, s.h_partial, KZGB_PARTIAL_BYTES);
-        badp += s.h_small[0];
-        bads += s.h_small[1];
     }
     kzgb_artifacts& art = ctx->art;
     memset(&art, 0, sizeof art);
     art.n = n;
+    memcpy(art.root, root, 32);
+    DeviceSlot& s0 = ctx->slots[0];
+    kzgb_ret rc = KZGB_OK;
+    if (!(badp || bads)) rc = combine(s0, parts.data(), (int)G, ok);
+    if (speculate) {
+        kzgb_ret frc = finish_subgroup(s0);
+        if (frc) return frc;
+        badp = s0.h_small[0];
+        bads = s0.h_small[1];
+    }
     art.n_bad_points = badp;
     art.n_bad_scalars = bads;
-    memcpy(art.root, root, 32);
     if (badp || bads) {
-        for (auto& s : ctx->slots) s.have_sums = false;
+        *ok = false;
+        for (auto& s : ctx->slots) { s.have_sums = false; s.have_ab = false; }
         return KZGB_BADARGS;
     }
-    DeviceSlot& s0 = ctx->slots[0];
-    kzgb_ret rc = combine(s0, parts.data(), (int)G, ok);
     if (rc) return rc;
     if (G > 1) s0.have_sums = false;
     fill_stage_ms(art, s0, root_ms);
@@ -532,6 +604,8 @@ kzgb_ret kzgb_shard_phase2(kzgb_ctx* ctx, int slot, const uint8_t root[32], uint
     if (rc) return rc;
     CK(cudaStreamSynchronize(s.stream));
     CK(cudaGetLastError());
+    rc = finish_subgroup(s);
+    if (rc) return rc;
     memcpy(partial_out, s.h_partial, KZGB_PARTIAL_BYTES);
     fill_stage_ms(ctx->art, s, 0.0f);
     ctx->art.n_bad_points = s.h_small[0];
@@ -837,15 +911,15 @@ kzgb_ret kzgb_synth_setup(uint8_t*, size_t, uint8_t*, size_t) { return KZGB_ERRO
 
 kzgb_ret kzgb_debug_op(kzgb_ctx* ctx, int op, const uint8_t* in, uint8_t* out, size_t count) {
     if (!ctx || !in || !out) return KZGB_BADARGS;
-    static const int isz[] = {0, 96, 48, 96, 96, 48, 48, 64, 64, 192, 96, 128, 96, 1152, 576, 576, 576, 576, 192, 64};
-    static const int osz[] = {0, 48, 48, 48, 48, 48, 48, 32, 32, 96, 96, 96, 96, 576, 576, 576, 576, 576, 576, 32};
-    if (op < 1 || op > 18) return KZGB_BADARGS;      // SHA256_64 is exercised through the FS stage exports
+    static const int isz[] = {0, 96, 48, 96, 96, 48, 48, 64, 64, 192, 96, 128, 96, 1152, 576, 576, 576, 576, 192, 64, 96, 48};
+    static const int osz[] = {0, 48, 48, 48, 48, 48, 48, 32, 32, 96, 96, 96, 96, 576, 576, 576, 576, 576, 576, 32, 48, 48};
+    if (op < 1 || op > 21 || op == 19) return KZGB_BADARGS;      // SHA256_64 is exercised through the FS stage exports
     DeviceSlot& s = ctx->slots[0];
     CK(cudaSetDevice(s.device));
     uint8_t *d_in = nullptr, *d_out = nullptr;
     CK(cudaMalloc((void**)&d_in, (size_t)isz[op] * count + 16)); CK(cudaMalloc((void**)&d_out, (size_t)osz[op] * count + 16));
     CK(cudaMemcpyAsync(d_in, in, (size_t)isz[op] * count, cudaMemcpyHostToDevice, s.stream));
-    if (op <= 12) launch_debug_op(s.stream, op, d_in, d_out, count);
+    if (op <= 12 || op >= 20) launch_debug_op(s.stream, op, d_in, d_out, count);
     else for (size_t i = 0; i < count; ++i) launch_pairing_debug(s.stream, op, s.lines, d_in + (size_t)isz[op] * i, d_out + (size_t)osz[op] * i);
     CK(cudaMemcpyAsync(out, d_out, (size_t)osz[op] * count, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));
@@ -889,5 +963,10 @@ kzgb_ret kzgb_last_stage_ms(kzgb_ctx* ctx, float ms_out[KZGB_N_STAGES]) {
 }
 uint64_t kzgb_launch_count(const kzgb_ctx*) { return g_kzgb_launches.load(); }
 int kzgb_set_threads(kzgb_ctx*, int) { return 0; }
+kzgb_ret kzgb_set_subgroup_batch_min(kzgb_ctx* ctx, size_t n_min) {
+    if (!ctx) return KZGB_BADARGS;
+    for (auto& s : ctx->slots) s.sg_min = n_min;
+    return KZGB_OK;
+}
 
 }  // extern "C"

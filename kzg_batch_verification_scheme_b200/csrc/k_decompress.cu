@@ -42,17 +42,34 @@ __global__ void __launch_bounds__(128, MINB) k_decompress_sqrt(const u8* __restr
 }
 // per-kernel occupancy choice "abc" (digits 2..4 for K1a, K1b, K1c), e.g. KZGB_K1_MINB=433
 // points [0, total) with total <= 2n: i < n from inC, the rest from inPi
-static void launch_decompress_impl(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, size_t total, Fp* out_pts,
-                                   Fp* tmp, uint8_t* status, uint32_t* counters) {
-    if (!total) return;
+static int k1_minb_cfg() {
     static const int cfg = [] { const char* e = getenv("KZGB_K1_MINB"); int v = e ? atoi(e) : 322; return (v >= 222 && v <= 444) ? v : 322; }();
+    return cfg;
+}
+// with_subgroup = false: K1a only (flags, x < p, on-curve, y); the caller runs the batched subgroup check
+static void launch_decompress_impl(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, size_t total, Fp* out_pts,
+                                   Fp* tmp, uint8_t* status, uint32_t* counters, bool with_subgroup = true) {
+    if (!total) return;
+    const int cfg = k1_minb_cfg();
     const int ma = cfg / 100, mb = cfg / 10 % 10, mc = cfg % 10;
     unsigned blocks = (unsigned)((total + 127) / 128);
     if (ma >= 4) k_decompress_sqrt<4><<<blocks, 128, 0, s>>>(inC, inPi, n, total, out_pts, status, counters);
     else if (ma == 3) k_decompress_sqrt<3><<<blocks, 128, 0, s>>>(inC, inPi, n, total, out_pts, status, counters);
     else k_decompress_sqrt<2><<<blocks, 128, 0, s>>>(inC, inPi, n, total, out_pts, status, counters);
+    KZ_COUNT_LAUNCH();
+    if (!with_subgroup) return;
     launch_subgroup_chains(s, out_pts, total, tmp, status, counters, mb, mc);
-    KZ_COUNT_LAUNCH(); KZ_COUNT_LAUNCH(); KZ_COUNT_LAUNCH();
+    KZ_COUNT_LAUNCH(); KZ_COUNT_LAUNCH();
+}
+// per-point subgroup check of already decompressed points (the fallback of the batched check)
+void launch_subgroup_points(cudaStream_t s, Fp* pts, size_t m, Fp* tmp, uint8_t* status, uint32_t* counters) {
+    if (!m) return;
+    const int cfg = k1_minb_cfg();
+    launch_subgroup_chains(s, pts, m, tmp, status, counters, cfg / 10 % 10, cfg % 10);
+    KZ_COUNT_LAUNCH(); KZ_COUNT_LAUNCH();
+}
+void launch_decompress_sqrt_points(cudaStream_t s, const uint8_t* in, size_t m, Fp* out_pts, uint8_t* status, uint32_t* counters) {
+    launch_decompress_impl(s, in, in, m, m, out_pts, nullptr, status, counters, false);
 }
 void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, Fp* out_pts, Fp* tmp, uint8_t* status,
                        uint32_t* counters) {

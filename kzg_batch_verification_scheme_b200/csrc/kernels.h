@@ -22,6 +22,12 @@ void launch_decompress(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, 
 void launch_subgroup_chains(cudaStream_t s, Fp* pts, size_t m, Fp* tmp, uint8_t* status, uint32_t* counters, int mb, int mc);
 void launch_decompress_points(cudaStream_t s, const uint8_t* in, size_t m, Fp* out_pts, Fp* tmp, uint8_t* status,
                               uint32_t* counters);
+// K1a only / per-point subgroup check only (batched subgroup check and its fallback)
+void launch_decompress_sqrt_points(cudaStream_t s, const uint8_t* in, size_t m, Fp* out_pts, uint8_t* status, uint32_t* counters);
+void launch_subgroup_points(cudaStream_t s, Fp* pts, size_t m, Fp* tmp, uint8_t* status, uint32_t* counters);
+// batched subgroup check on the buckets of a 128-bit sum: counters[2] += slice sums outside G1
+size_t sg_work_entries(const MsmPlan& plan);          // G1Xyzz entries of scratch one call needs
+void launch_sg_batch_check(cudaStream_t s, const MsmPlan& plan, const G1Xyzz* buckets, G1Xyzz* work, uint32_t* counters);
 void launch_points_to_be(cudaStream_t s, const Fp* pts, size_t m, uint8_t* out96);           // canonical x||y
 void launch_points_from_be(cudaStream_t s, const uint8_t* in96, size_t m, Fp* pts, uint32_t* counters);
 void launch_debug_op(cudaStream_t s, int op, const uint8_t* in, uint8_t* out, size_t count);

@@ -264,3 +264,35 @@ KZ_COLD G1Jac msm_combine_body(const G1Xyzz* win, int W, int c) {
     }
     return acc;
 }
+
+// ---- batched subgroup check on the bucket sums of a 128-bit MSM (DESIGN.md "Batched subgroup check").
+// The signed digits of the challenges r_i are 128 fair, independent coins per point: for a signed window the
+// c-1 magnitude bits and the sign, for the unsigned top window its tb bits (c(W-1) + tb = 128).  Slice (w, b)
+// sums the buckets of window w whose magnitude has bit b set; slice (w, c-1) of a signed window sums all its
+// buckets (coefficient = sign of the digit).  Point P_i enters each slice with a coefficient in {-1, 0, 1}
+// that takes any fixed value with probability <= 1/2 + 2^-c, independently over the 128 slices, so a point with
+// a non-zero cofactor component (odd order >= 3) leaves every one of the 128 slice sums inside G1 with
+// probability <= 2^-127: checking the 128 sums replaces 2n per-point checks.  No extra point additions are
+// needed -- the buckets are the ones the sum  sum r_i P_i  fills anyway.
+struct SgSlice { int w; int b; bool all; u32 count; };
+KZ_HD SgSlice sg_slice(const MsmPlan& P, int sid) {
+    SgSlice s;
+    int signed_slices = P.c * (P.W - 1);
+    if (sid < signed_slices) { s.w = sid / P.c; s.b = sid - s.w * P.c; s.all = s.b == P.c - 1; }
+    else { s.w = P.W - 1; s.b = sid - signed_slices; s.all = false; }
+    s.count = s.all ? P.nb[s.w] : P.nb[s.w] / 2;
+    return s;
+}
+// j-th member (j < count) -> bucket index inside the window (bucket of magnitude m sits at m - 1)
+KZ_HD u32 sg_member_bucket(const SgSlice& s, u32 j) {
+    if (s.all) return j;
+    u32 low = (1u << s.b) - 1u;
+    u32 m = ((j & ~low) << 1) | (1u << s.b) | (j & low);
+    return m - 1u;
+}
+KZ_COLD bool sg_sum_in_g1(const G1Xyzz& t) {
+    if (xyzz_is_inf(t)) return true;
+    G1Aff a = jac_to_aff(xyzz_to_jac(t));
+    return g1_in_subgroup(a);
+}
+

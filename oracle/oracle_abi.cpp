@@ -59,6 +59,9 @@ kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const ui
 }
 void kzgb_ctx_free(kzgb_ctx* c) { delete c; }
 
+// the oracle always checks every point on its own; the knob exists so that both libraries export the same ABI
+kzgb_ret kzgb_set_subgroup_batch_min(kzgb_ctx* c, size_t) { return c ? KZGB_OK : KZGB_BADARGS; }
+
 int kzgb_set_threads(kzgb_ctx* c, int n) {
     if (c && n > 0) c->threads = n;
     return c ? c->threads : 0;

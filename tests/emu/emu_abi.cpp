@@ -29,6 +29,7 @@ struct kzgb_ctx {
     G1Jac sums[3];
     Fr sum_ry;
     bool have_sums = false;
+    size_t sg_min = 0;             // batched subgroup check for batches of at least this many proofs (0 = never)
 };
 
 static void words_from_be(u32* w, const u8* in, int nw) {
@@ -39,7 +40,8 @@ static void words_to_be(u8* out, const u32* w, int nw) {
 }
 
 // emulated MSM pipeline: digits -> sort -> bounds -> accumulate -> segments -> window sums -> combine
-static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nbits) {
+// sg_fail != null: also run the batched subgroup check on this sum's buckets (count of slice sums outside G1)
+static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nbits, u32* sg_fail = nullptr) {
     if (nbits == 255) {      // GLV split exactly as the device pipeline does it
         std::vector<u32> zs(4 * 2 * m);
         std::vector<Fp> p2(2 * 2 * m);
@@ -84,6 +86,14 @@ static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nb
             G1Jac a = xyzz_to_jac(ref), c2 = xyzz_to_jac(buckets[b]);
             bool same = jac_is_inf(a) ? jac_is_inf(c2) : (!jac_is_inf(c2) && aff_is_inf(jac_to_aff(jac_add(a, jac_neg(c2)))));
             if (!same) { fprintf(stderr, "emu: bucket %u differs\n", b); abort(); }
+        }
+    }
+    if (sg_fail) {
+        for (int sid = 0; sid < plan.nbits; ++sid) {
+            SgSlice sl = sg_slice(plan, sid);
+            G1Xyzz acc = xyzz_inf();
+            for (u32 j = 0; j < sl.count; ++j) acc = xyzz_add(acc, buckets[plan.bucket_off[sl.w] + sg_member_bucket(sl, j)]);
+            *sg_fail += !sg_sum_in_g1(acc);
         }
     }
     for (u32 s = 0; s < plan.total_segs; ++s) {
@@ -202,13 +212,14 @@ static kzgb_ret emu_verify(bool* ok, const u8* C, const u8* z, const u8* y, cons
     memset(&c->art, 0, sizeof c->art);
     c->art.n = n;
     c->have_sums = false;
+    const bool sg_batch = !single && c->sg_min && n >= c->sg_min && n >= 2;
     std::vector<Fp> pts(2 * (2 * n + 1));
-    u32 badp = 0, bads = 0;
+    u32 badp = 0, bads = 0, sg_fail = 0;
     for (size_t i = 0; i < 2 * n; ++i) {
         u32 w[12];
         words_from_be(w, i < n ? C + 48 * i : pi + 48 * (i - n), 12);
         G1Aff p;
-        badp += g1_decompress_validate(p, w) != ST_OK;
+        badp += g1_decompress_validate(p, w, !sg_batch) != ST_OK;
         pts[2 * i] = p.x; pts[2 * i + 1] = p.y;
     }
     std::vector<u8> dig;
@@ -235,8 +246,16 @@ static kzgb_ret emu_verify(bool* ok, const u8* C, const u8* z, const u8* y, cons
     Fr neg = fr_neg(sum);
     for (int k = 0; k < 8; ++k) rz[8 * n + k] = neg.v[k];
     pts[2 * 2 * n] = c->g1.x; pts[2 * 2 * n + 1] = c->g1.y;
-    c->sums[0] = emu_msm(pts.data(), r.data(), 4, n, 128);
-    c->sums[2] = emu_msm(pts.data() + 2 * n, r.data(), 4, n, 128);
+    c->sums[0] = emu_msm(pts.data(), r.data(), 4, n, 128, sg_batch ? &sg_fail : nullptr);
+    c->sums[2] = emu_msm(pts.data() + 2 * n, r.data(), 4, n, 128, sg_batch ? &sg_fail : nullptr);
+    if (sg_fail) {           // a slice sum left G1: the per-point check names the offenders
+        for (size_t i = 0; i < 2 * n; ++i) {
+            G1Aff p = load_point(pts.data(), i);
+            badp += !aff_is_inf(p) && !g1_in_subgroup(p);
+        }
+        c->art.n_bad_points = badp;
+        return KZGB_BADARGS;
+    }
     c->sums[1] = emu_msm(pts.data() + 2 * n, rz.data(), 8, n + 1, 255);
     c->sum_ry = sum;
     c->have_sums = true;
@@ -518,4 +537,5 @@ kzgb_ret kzgb_imad32_peak(kzgb_ctx*, double*, double*) { return KZGB_ERROR; }
 kzgb_ret kzgb_last_stage_ms(kzgb_ctx*, float*) { return KZGB_ERROR; }
 uint64_t kzgb_launch_count(const kzgb_ctx*) { return 0; }
 int kzgb_set_threads(kzgb_ctx*, int) { return 0; }
+kzgb_ret kzgb_set_subgroup_batch_min(kzgb_ctx* c, size_t n_min) { if (!c) return KZGB_BADARGS; c->sg_min = n_min; return KZGB_OK; }
 }

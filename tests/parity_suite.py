@@ -222,6 +222,70 @@ def check_status_classes(gpu_ctx, oracle_ctx, n=64):
             assert a1["n_bad_points"] == a2["n_bad_points"] == 1 and a1["n_bad_scalars"] == a2["n_bad_scalars"] == 0
 
 
+def small_order_points(rnd):
+    """Points of E(Fp) of small prime order l | h1 = 3 * 11^2 * 10177^2 * 859267^2 * 52437899^2 (cofactor torsion)."""
+    order = b.H1 * R
+    out = {3: (0, 2)}
+    for ell in (11, 10177, 859267, 52437899):           # l^2 | h1: clear everything but the l-Sylow subgroup
+        while ell not in out:
+            t = b.g1_mul(order // (ell * ell), rand_curve_point(rnd))
+            if t is None:
+                continue
+            t2 = b.g1_mul(ell, t)
+            if t2 is not None:                          # order l^2 (cyclic Sylow): take the order-l multiple
+                t = t2
+            assert b.g1_mul(ell, t) is None
+            out[ell] = t
+    return out
+
+
+def check_subgroup_batch(ctx, oracle, n=24, min_batch=2, ells=(3, 11, 10177, 859267, 52437899)):
+    """Batched subgroup check (slice sums of the S1 / S3 buckets) against the oracle's per-point check: points
+    with a cofactor component of every small prime order, alone, in cancelling pairs and everywhere."""
+    rnd = random.Random(77)
+    assert ctx.set_subgroup_batch_min(min_batch) == 0
+    try:
+        tors = small_order_points(rnd)
+        C, Z, Y, PI = oracle.synth_instance(0x4B5A4731, 0, n)
+        assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == oracle.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+        a1, a2 = ctx.last_artifacts(), oracle.last_artifacts()
+        for key in ("S1", "S2", "S3", "A", "B", "sum_ry", "root"):
+            assert a1[key] == a2[key], key
+
+        def shifted(buf, j, t):
+            st, p = b.g1_decompress(buf[48 * j:48 * j + 48])
+            assert st == 0
+            q = b.g1_add(p, t)
+            return buf[:48 * j] + b.g1_compress(q) + buf[48 * j + 48:]
+
+        def expect_bad(Cb, Pb, count):
+            assert ctx.verify_kzg_proof_batch(Cb, Z, Y, Pb, n) == oracle.verify_kzg_proof_batch(Cb, Z, Y, Pb, n) == (1, False)
+            b1, b2 = ctx.last_artifacts(), oracle.last_artifacts()
+            assert b1["n_bad_points"] == b2["n_bad_points"] == count
+
+        for ell in ells:
+            t = tors[ell]
+            j = rnd.randrange(n)
+            expect_bad(shifted(C, j, t), PI, 1)                       # one commitment with an order-l component
+            expect_bad(C, shifted(PI, j, t), 1)                       # one proof
+            expect_bad(C[:48 * j] + b.g1_compress(t) + C[48 * j + 48:], PI, 1)   # the torsion point itself
+            i2 = (j + 1 + rnd.randrange(n - 1)) % n
+            expect_bad(shifted(shifted(C, j, t), i2, b.g1_neg(t)), PI, 2)        # components cancel in a plain sum
+            expect_bad(shifted(C, j, t), shifted(PI, j, b.g1_neg(t)), 2)
+        if n <= 64:
+            t3 = tors[3]
+            Call, Pall = C, PI
+            for j in range(n):
+                Call, Pall = shifted(Call, j, t3), shifted(Pall, j, t3)
+            expect_bad(Call, Pall, 2 * n)
+        expect_bad(shifted(C, 0, rand_curve_point(rnd)), PI, 1)       # generic off-subgroup point
+        # a wrong proof inside G1 is still only a rejection, not malformed input
+        Pw = PI[48:96] + PI[:48] + PI[96:]
+        assert ctx.verify_kzg_proof_batch(C, Z, Y, Pw, n) == oracle.verify_kzg_proof_batch(C, Z, Y, Pw, n) == (0, False)
+    finally:
+        ctx.set_subgroup_batch_min(32768)
+
+
 def check_cell_batch(ctx, oracle, inst):
     """inst = (commitments, commitment_indices, cell_indices, cells, proofs) from the oracle generator."""
     comms, ci, xi, cells, proofs = inst

@@ -29,6 +29,10 @@ def test_emu_fpd_ops(emu_ctx, oracle_ctx):
     ps.check_fpd_ops(emu_ctx, oracle_ctx)
 
 
+def test_emu_subgroup_batch(emu_ctx, oracle_ctx):
+    ps.check_subgroup_batch(emu_ctx, oracle_ctx, n=6)
+
+
 def test_emu_sha_single_block(emu_ctx, oracle_ctx):
     import random
     rnd = random.Random(1)

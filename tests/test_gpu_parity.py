@@ -20,6 +20,15 @@ def test_gpu_field_ops(gpu_ctx, oracle_ctx):
     ps.check_field_ops(gpu_ctx, oracle_ctx, n_random=2000)
 
 
+def test_gpu_subgroup_batch_small(gpu_ctx, oracle_ctx):
+    ps.check_subgroup_batch(gpu_ctx, oracle_ctx, n=24)
+
+
+def test_gpu_subgroup_batch_default_threshold(gpu_ctx, oracle_ctx):
+    """n = 2^15 proofs: the batched check is the default path; a single order-3 / order-11 component is found."""
+    ps.check_subgroup_batch(gpu_ctx, oracle_ctx, n=1 << 15, min_batch=32768, ells=(3, 11))
+
+
 def test_gpu_fpd_ops(gpu_ctx, oracle_ctx):
     ps.check_fpd_ops(gpu_ctx, oracle_ctx)
 
