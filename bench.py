@@ -32,6 +32,10 @@ IMAD_PER_FPMUL, IMAD_PER_FPSQR = 300, 234
 K1_M_PER_POINT = 85 + 1 + 126 * 2 + 5 * 8 + 5 * 12 + 3 + 2           # + to/from Montgomery
 K1_S_PER_POINT = 377 + 2 + 126 * 5 + 5 * 3 + 5 * 4 + 1
 K1_IMAD_PER_POINT = K1_M_PER_POINT * IMAD_PER_FPMUL + K1_S_PER_POINT * IMAD_PER_FPSQR
+# batches of >= KZGB_SG_BATCH_MIN (default 32768) proofs: the subgroup check is done on 128 bucket-slice sums per MSM,
+# K1 is the decompression kernel alone (sqrt + on-curve + Montgomery conversions)
+K1A_M_PER_POINT, K1A_S_PER_POINT = 85 + 1 + 2, 377 + 2
+K1A_IMAD_PER_POINT = K1A_M_PER_POINT * IMAD_PER_FPMUL + K1A_S_PER_POINT * IMAD_PER_FPSQR
 K1_IMAD_PER_POINT_SURVEY = (471 + 1021) * 300                          # SURVEY.md 8(d) model, M = S = 300
 MSM_FPMUL_PER_PROOF = 370                                              # SURVEY.md App. C, n = 2^20
 SEED = 0x4B5A4703
@@ -264,26 +268,36 @@ def main():
             except Exception:                                   # noqa: BLE001
                 pass
         k1_ms = stages.get("decompress", 0.0)
+        sg_min = int(os.environ.get("KZGB_SG_BATCH_MIN", "32768"))
+        sg_batch = sg_min > 0 and n_local >= sg_min
         if k1_ms > 0:
-            k1_imad = 2 * n_local * K1_IMAD_PER_POINT
+            per_point = K1A_IMAD_PER_POINT if sg_batch else K1_IMAD_PER_POINT
+            k1_imad = 2 * n_local * per_point
             ach = k1_imad / (k1_ms * 1e-3)
-            roofline = {"bound": "imad", "kernel": "K1 = k_decompress_sqrt + k_subgroup_chain1 + k_subgroup_chain2 (one stage, 3 launches)",
+            kernel = ("K1 = k_decompress_sqrt (2 launches: commitments, proofs); subgroup membership is established on 128 bucket-slice "
+                      "sums per MSM (batched check), not per point") if sg_batch else \
+                "K1 = k_decompress_sqrt + k_subgroup_chain1 + k_subgroup_chain2 (one stage, 3 launches)"
+            roofline = {"bound": "imad", "kernel": kernel,
                         "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T wide-IMAD/s", "frac": ach / imad_peak,
                         # dram__bytes_read+write per launch from the ncu --set full captures of the three K1 kernels at
                         # n = 65536 (profiles/r1_k1[abc]_*: 22.2 + 12.7 + 31.6 MB for 131072 points = 507 B/point), scaled to this n
-                        "traffic": 2 * n_local * 507,
+                        "traffic": 2 * n_local * (169 if sg_batch else 507),
                         "peak_source": peak_src + ": carry-chained mad.lo.cc/madc.hi.cc (SASS IMAD.WIDE.U32.X) on all SMs, measured in this "
                                        "run; 32 lanes/clk/SM on B200 (148 x 32 x 1.965 GHz = 9.31 T/s nominal)",
                         "imad32_issue_peak": imad32_peak / 1e12,
                         "algorithmic_per_launch": k1_imad, "launch_ms": k1_ms,
-                        "formula": f"2n x ({K1_M_PER_POINT} M x 300 + {K1_S_PER_POINT} S x 234) wide multiply-adds; stage time from CUDA events on the library's stream",
-                        "frac_survey_model": 2 * n_local * K1_IMAD_PER_POINT_SURVEY / (k1_ms * 1e-3) / imad_peak,
-                        "whole_batch_frac": (n_local * (2 * K1_IMAD_PER_POINT + MSM_FPMUL_PER_PROOF * 300)) / (stages.get("total", ms_dev) * 1e-3) / imad_peak}
-            k1_bytes = 2 * n_local * (48 + 96 + 1 + 2 * 144 + 2 * 96)
+                        "formula": (f"2n x ({K1A_M_PER_POINT} M x 300 + {K1A_S_PER_POINT} S x 234)" if sg_batch else
+                                    f"2n x ({K1_M_PER_POINT} M x 300 + {K1_S_PER_POINT} S x 234)") +
+                                   " wide multiply-adds; stage time from CUDA events on the library's stream",
+                        "subgroup_check": "batched (bucket slices)" if sg_batch else "per point",
+                        "whole_batch_frac": (n_local * (2 * per_point + MSM_FPMUL_PER_PROOF * 300)) / (stages.get("total", ms_dev) * 1e-3) / imad_peak}
+            if not sg_batch:
+                roofline["frac_survey_model"] = 2 * n_local * K1_IMAD_PER_POINT_SURVEY / (k1_ms * 1e-3) / imad_peak
+            k1_bytes = 2 * n_local * ((48 + 96 + 1) if sg_batch else (48 + 96 + 1 + 2 * 144 + 2 * 96))
             roofline_hbm = {"bound": "hbm", "kernel": "K1", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak,
                             "unit": "GB/s", "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                            "note": "K1 is integer-pipe bound by construction (~1500 Fp products per ~625 bytes moved); HBM fraction reported for completeness"}
+                            "note": "K1 is integer-pipe bound by construction (hundreds of Fp products per ~150-625 bytes moved); HBM fraction reported for completeness"}
         if not args.no_extras:
             # CPU baseline: oracle port on the box's host cores, bounded sample (~10-20 s)
             try:
