@@ -394,7 +394,7 @@ def main():
                        "l2": "inputs (160 B/proof) and intermediates exceed the 126 MB L2; no flush needed",
                        "parallelism": f"contiguous shards x{world}, host combine" if multi else "single GPU"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "proofs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 160 * n_local * world,
+            "e2e": {"value": e2e_value, "unit": "proofs/s", "ms_per_step": ms_e2e, "stage_ms": stages_e2e, "h2d_bytes_per_step": 160 * n_local * world,
                     "d2h_bytes_per_step": (32 * nch + PARTIAL_BYTES + 16) * world},
             "gpu_launches": launches,
             "stage_ms": stages,

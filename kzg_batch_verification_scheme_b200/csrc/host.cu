@@ -54,6 +54,7 @@ struct DeviceSlot {
     size_t sg_cap = 0;                 // entries per sum
     size_t sg_min = 32768;             // batches of at least this many proofs use the batched subgroup check (0 = never)
     bool sg_batch = false;             // current shard: K1 ran without the per-point chains
+    bool head_mode = false;            // current shard: K1 started after the first eighth of C was resident (ev[17])
     G1Jac* sums = nullptr;             // [0] S1 [1] S2' [2] S3 [3] A [4] B
     uint8_t* partial_dev = nullptr;    // 320
     uint8_t* partials_in = nullptr;    // 320 * 64
@@ -280,9 +281,25 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
     CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), st));
     CK(cudaEventRecord(s.ev[14], st));
     CK(cudaStreamWaitEvent(s2, s.ev[14], 0));
+    s.sg_batch = s.sg_min && n >= s.sg_min && n >= 2;   // subgroup membership through the bucket slices of S1 and S3
+    // host buffers, large batch: only the first eighth of the commitments is copied ahead of K1; the rest of C,
+    // then pi, z, y follow on the side stream, one transfer at a time, while K1 already runs
+    const size_t head = (!on_device && s.sg_batch && n >= 65536) ? (n / 8) & ~(size_t)127 : 0;
+    s.head_mode = head != 0;
     if (!on_device) {
-        // commitments first on the main stream; pi, z, y copy on the side stream while K1 already runs on the C half
-        CK(cudaMemcpyAsync(s.dC, C, 48 * n, cudaMemcpyHostToDevice, st));
+        if (head) {
+            // all transfers on ONE stream, in the order K1 needs them (copies of the high-priority side stream
+            // overtake a copy queued on the main stream: measured, the head then arrived last)
+            CK(cudaMemcpyAsync(s.dC, C, 48 * head, cudaMemcpyHostToDevice, s2));
+            CK(cudaEventRecord(s.ev[17], s2));
+            CK(cudaStreamWaitEvent(st, s.ev[17], 0));
+            CK(cudaMemcpyAsync(s.dC + 48 * head, C + 48 * head, 48 * (n - head), cudaMemcpyHostToDevice, s2));
+            CK(cudaEventRecord(s.ev[1], s2));               // C resident (together with ev[17])
+        } else {
+            CK(cudaMemcpyAsync(s.dC, C, 48 * n, cudaMemcpyHostToDevice, s2));
+            CK(cudaEventRecord(s.ev[1], s2));               // C resident
+            CK(cudaStreamWaitEvent(st, s.ev[1], 0));
+        }
         CK(cudaMemcpyAsync(s.dpi, pi, 48 * n, cudaMemcpyHostToDevice, s2));
         CK(cudaMemcpyAsync(s.dz, z, 32 * n, cudaMemcpyHostToDevice, s2));
         CK(cudaMemcpyAsync(s.dy, y, 32 * n, cudaMemcpyHostToDevice, s2));
@@ -293,19 +310,24 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
     s.cur_n = n;
     s.have_sums = false;
     s.have_ab = false;
-    s.sg_batch = s.sg_min && n >= s.sg_min && n >= 2;             // subgroup membership through the bucket slices of S1 and S3
-    CK(cudaEventRecord(s.ev[1], st));                   // C resident
+    if (on_device) CK(cudaEventRecord(s.ev[1], st));    // inputs already resident
     CK(cudaEventRecord(s.ev[13], s2));                  // pi, z, y resident
     // side stream: hashes (need all four arrays) start before K1 fills the SMs
-    CK(cudaStreamWaitEvent(s2, s.ev[1], 0));
+    if (on_device) CK(cudaStreamWaitEvent(s2, s.ev[1], 0));
     launch_leaf_hash(s2, s.cur_C, s.cur_z, s.cur_y, s.cur_pi, n, s.leaves, s.counters);
     launch_chunk_hash(s2, s.leaves, n, s.digests);
     size_t nch = (n + KZGB_CHUNK - 1) / KZGB_CHUNK;
     CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, s2));
     CK(cudaEventRecord(s.ev[2], s2));
     if (s.sg_batch) {
-        // K1a only; commitments first, then (once pi is resident) proofs -- hides most of the H2D copy
-        launch_decompress_sqrt_points(st, s.cur_C, n, s.pts, s.status, s.counters);
+        // K1a only; commitments first, then (once pi is resident) proofs -- hides the H2D copy
+        if (head) {
+            launch_decompress_sqrt_points(st, s.cur_C, head, s.pts, s.status, s.counters);
+            CK(cudaStreamWaitEvent(st, s.ev[1], 0));
+            launch_decompress_sqrt_points(st, s.cur_C + 48 * head, n - head, s.pts + 2 * head, s.status + head, s.counters);
+        } else {
+            launch_decompress_sqrt_points(st, s.cur_C, n, s.pts, s.status, s.counters);
+        }
         CK(cudaStreamWaitEvent(st, s.ev[13], 0));
         launch_decompress_sqrt_points(st, s.cur_pi, n, s.pts + 2 * n, s.status + n, s.counters);
     } else if (!on_device && n >= 32768) {
@@ -438,9 +460,10 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 // stages overlap (side stream): hash/challenges/sort are measured on the side stream, decompress and the
 // rest on the main stream; "accumulate" starts when K1 has finished.  Valid after the slot's streams synced.
 void fill_stage_ms(kzgb_artifacts& art, DeviceSlot& s0, float root_ms) {
-    art.stage_ms[0] = ev_ms(s0.ev[0], s0.ev[1]);
+    cudaEvent_t k1_start = s0.head_mode ? s0.ev[17] : s0.ev[1];
+    art.stage_ms[0] = ev_ms(s0.ev[0], k1_start);
     art.stage_ms[2] = ev_ms(s0.ev[1], s0.ev[2]);
-    art.stage_ms[1] = ev_ms(s0.ev[1], s0.ev[3]);
+    art.stage_ms[1] = ev_ms(k1_start, s0.ev[3]);
     art.stage_ms[3] = root_ms;
     art.stage_ms[4] = ev_ms(s0.ev[2], s0.ev[4]);
     art.stage_ms[5] = ev_ms(s0.ev[4], s0.ev[5]);
