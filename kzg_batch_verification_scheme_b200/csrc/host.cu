@@ -35,6 +35,9 @@ struct DeviceSlot {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;    // high-priority side stream: hashes, challenges and sorts overlap K1
     cudaStream_t stream3 = nullptr, stream4 = nullptr;   // the three sums accumulate/reduce concurrently
+    cudaStream_t stream6 = nullptr, stream7 = nullptr;   // normal-priority twins of stream3 / stream5 (small batches)
+    size_t pri_min = ~(size_t)0;       // batch size from which S1 and S3 run at high priority (env KZGB_MSM_PRI_MIN);
+                                       // measured slower at every size (2^20: 51.9 vs 50.2 ms), so off by default
     cudaStream_t stream5 = nullptr;    // high priority like stream3: S1 and S3 finish first so that their bucket slices
                                        // (batched subgroup check) overlap the longer GLV sum on stream4
     // staged inputs (host-pointer API)
@@ -120,6 +123,9 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
         CK(cudaStreamCreateWithPriority(&s.stream3, cudaStreamNonBlocking, hi_pri));
         CK(cudaStreamCreateWithFlags(&s.stream4, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithPriority(&s.stream5, cudaStreamNonBlocking, hi_pri));
+        CK(cudaStreamCreateWithFlags(&s.stream6, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s.stream7, cudaStreamNonBlocking));
+        if (const char* e = getenv("KZGB_MSM_PRI_MIN")) s.pri_min = (size_t)strtoull(e, nullptr, 10);
     }
     for (auto& e : s.ev) CK(cudaEventCreate(&e));
     CK(dmalloc(s.dC, 48 * (n_max + 1))); CK(dmalloc(s.dz, 32 * (n_max + 1))); CK(dmalloc(s.dy, 32 * (n_max + 1))); CK(dmalloc(s.dpi, 48 * (n_max + 1)));
@@ -246,6 +252,8 @@ void slot_free(DeviceSlot& s) {
     if (s.stream3) cudaStreamDestroy(s.stream3);
     if (s.stream4) cudaStreamDestroy(s.stream4);
     if (s.stream5) cudaStreamDestroy(s.stream5);
+    if (s.stream6) cudaStreamDestroy(s.stream6);
+    if (s.stream7) cudaStreamDestroy(s.stream7);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -379,29 +387,40 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     wr2.buckets = s.bucketsB; wr2.recs = s.recsB;
     wr2.segsums = s.segsums + s.max_segs; wr2.winsums = s.winsums + KZ_MSM_MAX_WINDOWS;
     wz.segsums = s.segsums + 2 * s.max_segs; wz.winsums = s.winsums + 2 * KZ_MSM_MAX_WINDOWS;
+    // Longest chain (S2', twice the points) first, all three sums at normal priority.  The alternative -- S1 and S3
+    // at high priority so that the batched subgroup check starts early and overlaps S2' -- is kept behind
+    // KZGB_MSM_PRI_MIN; it was slower at every batch size.
+    const bool pri = n >= s.pri_min;
+    cudaStream_t sS3 = pri ? s.stream3 : s.stream6, sS1 = pri ? s.stream5 : s.stream7;
     CK(cudaEventRecord(s.ev[11], st));
-    CK(cudaStreamWaitEvent(s.stream3, s.ev[11], 0));
+    CK(cudaStreamWaitEvent(sS3, s.ev[11], 0));
     CK(cudaStreamWaitEvent(s.stream4, s.ev[11], 0));
-    CK(cudaStreamWaitEvent(s.stream5, s.ev[11], 0));
-    msm_accumulate_stage(s.stream3, s.planR, s.pts + 2 * n, n, wr2);             // S3 over pi_i
-    msm_window_sums_stage(s.stream3, s.planR, wr2);
-    CK(cudaEventRecord(s.ev[12], s.stream3));
-    msm_accumulate_stage(s.stream5, s.planR, s.pts, n, wr);                      // S1 over C_i
-    CK(cudaEventRecord(s.ev[10], s.stream5));                                    // buckets of S1 complete
-    msm_window_sums_stage(s.stream5, s.planR, wr);
-    CK(cudaEventRecord(s.ev[16], s.stream5));
-    msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);   // S2' over pi_i, G and their phi images
-    msm_window_sums_stage(s.stream4, s.planZ, wz);
-    CK(cudaEventRecord(s.ev[13], s.stream4));
+    CK(cudaStreamWaitEvent(sS1, s.ev[11], 0));
+    if (!pri) {
+        msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);
+        msm_window_sums_stage(s.stream4, s.planZ, wz);
+        CK(cudaEventRecord(s.ev[13], s.stream4));
+    }
+    msm_accumulate_stage(sS3, s.planR, s.pts + 2 * n, n, wr2);                   // S3 over pi_i
+    msm_window_sums_stage(sS3, s.planR, wr2);
+    CK(cudaEventRecord(s.ev[12], sS3));
+    msm_accumulate_stage(sS1, s.planR, s.pts, n, wr);                            // S1 over C_i
+    CK(cudaEventRecord(s.ev[10], sS1));                                          // buckets of S1 complete
+    msm_window_sums_stage(sS1, s.planR, wr);
+    CK(cudaEventRecord(s.ev[16], sS1));
+    if (pri) {
+        msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);   // S2' over pi_i, G and their phi images
+        msm_window_sums_stage(s.stream4, s.planZ, wz);
+        CK(cudaEventRecord(s.ev[13], s.stream4));
+    }
     if (s.sg_batch) {
-        // batched subgroup check: 128 slice sums of the S3 buckets (all pi_i) and of the S1 buckets (all C_i).
-        // S1 and S3 run at high priority, so this work overlaps the GLV sum (twice the points) on stream4
-        launch_sg_batch_check(s.stream3, s.planR, wr2.buckets, s.sg_partial, s.counters);
-        CK(cudaStreamWaitEvent(s.stream3, s.ev[10], 0));
-        launch_sg_batch_check(s.stream3, s.planR, wr.buckets, s.sg_partial + s.sg_cap, s.counters);
+        // batched subgroup check: 128 slice sums of the S3 buckets (all pi_i) and of the S1 buckets (all C_i)
+        launch_sg_batch_check(sS3, s.planR, wr2.buckets, s.sg_partial, s.counters);
+        CK(cudaStreamWaitEvent(sS3, s.ev[10], 0));
+        launch_sg_batch_check(sS3, s.planR, wr.buckets, s.sg_partial + s.sg_cap, s.counters);
         // the verdict of the check travels on this stream: the main stream goes on to the pairing without it
-        CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream3));
-        CK(cudaEventRecord(s.ev[9], s.stream3));
+        CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sS3));
+        CK(cudaEventRecord(s.ev[9], sS3));
     }
     CK(cudaStreamWaitEvent(st, s.ev[12], 0));
     CK(cudaStreamWaitEvent(st, s.ev[13], 0));
