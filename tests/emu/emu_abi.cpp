@@ -241,6 +241,14 @@ static kzgb_ret emu_verify(bool* ok, const u8* C, const u8* z, const u8* y, cons
         for (int k = 0; k < 4; ++k) r[4 * i + k] = ri.v[k];
         for (int k = 0; k < 8; ++k) rz[8 * i + k] = v.v[k];
     }
+    if (sg_batch && (badp || bads)) {
+        // the device still runs the sums and their slice check on the well-formed points; an off-subgroup point
+        // among them fails a slice and the per-point fallback counts it
+        for (size_t i = 0; i < 2 * n; ++i) {
+            G1Aff p = load_point(pts.data(), i);
+            badp += !aff_is_inf(p) && !g1_in_subgroup(p);
+        }
+    }
     c->art.n_bad_points = badp; c->art.n_bad_scalars = bads;
     if (badp || bads) return KZGB_BADARGS;
     Fr neg = fr_neg(sum);

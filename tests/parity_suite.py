@@ -282,6 +282,18 @@ def check_subgroup_batch(ctx, oracle, n=24, min_batch=2, ells=(3, 11, 10177, 859
         # a wrong proof inside G1 is still only a rejection, not malformed input
         Pw = PI[48:96] + PI[:48] + PI[96:]
         assert ctx.verify_kzg_proof_batch(C, Z, Y, Pw, n) == oracle.verify_kzg_proof_batch(C, Z, Y, Pw, n) == (0, False)
+        # malformed encodings (flags, x >= p, off curve) and scalars >= r on the batched path; mixed with an
+        # off-subgroup point the counts still agree
+        if n <= 4096:
+            check_status_classes(ctx, oracle, n=n)
+        for enc, st in negative_g1_encodings(rnd):
+            if st in (1, 2, 3):
+                j = rnd.randrange(1, n)
+                expect_bad(shifted(C, 0, tors[3])[:48 * j] + enc + C[48 * j + 48:], PI, 2)
+                break
+        Zb = Z[:32] + b"\xff" * 32 + Z[64:]
+        assert ctx.verify_kzg_proof_batch(C, Zb, Y, PI, n) == oracle.verify_kzg_proof_batch(C, Zb, Y, PI, n) == (1, False)
+        assert ctx.last_artifacts()["n_bad_scalars"] == oracle.last_artifacts()["n_bad_scalars"] == 1
     finally:
         ctx.set_subgroup_batch_min(32768)
 
