@@ -49,12 +49,12 @@ struct DeviceSlot {
     uint32_t *leaves = nullptr, *digests = nullptr, *root_words = nullptr;
     uint32_t *r = nullptr, *rz = nullptr, *zs = nullptr, *partials = nullptr, *sum_ry = nullptr;   // zs: GLV halves of rz
     SortBuf sortR, sortZ;
-    G1Xyzz *bucketsA = nullptr, *bucketsB = nullptr, *bucketsC = nullptr, *segsums = nullptr, *winsums = nullptr;
-    size_t max_bucketsR = 0, max_bucketsZ = 0, max_segs = 0;
+    G1Xyzz *bucketsA = nullptr, *bucketsB = nullptr, *bucketsC = nullptr, *winsums = nullptr;
+    size_t max_bucketsR = 0, max_bucketsZ = 0;
     ChunkRecs recs = {nullptr, nullptr, nullptr, nullptr, nullptr};      // sum S2' (and kzgb_g1_msm)
     ChunkRecs recsA = {nullptr, nullptr, nullptr, nullptr, nullptr}, recsB = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    G1Xyzz* sg_partial = nullptr;      // batched subgroup check: row/column partials and totals, two sums
-    size_t sg_cap = 0;                 // entries per sum
+    G1Xyzz* sg_partial = nullptr;      // bucket reduction scratch of three sums: run sums, totals, slice sums
+    size_t sg_cap = 0;                 // entries per sum (the last 256 are the slice sums)
     size_t sg_min = 32768;             // batches of at least this many proofs use the batched subgroup check (0 = never)
     bool sg_batch = false;             // current shard: K1 ran without the per-point chains
     bool head_mode = false;            // current shard: K1 started after the first eighth of C was resident (ev[17])
@@ -140,7 +140,7 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     // the 255-bit sum is GLV-split into 2(n+1) 128-bit scalars.  Window widths depend on n (msm_make_plan),
     // so size every workspace for the worst case over batch sizes up to n_max
     size_t capR = 0, capZ = 0;
-    s.max_bucketsR = s.max_bucketsZ = s.max_segs = 0;
+    s.max_bucketsR = s.max_bucketsZ = 0;
     for (int k = 1; k <= 64; ++k) {
         size_t nn = n_max * (size_t)k / 64;
         if (nn < 1) nn = 1;
@@ -149,30 +149,31 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
         capZ = std::max(capZ, (size_t)pz.W * 2 * (nn + 1));
         s.max_bucketsR = std::max(s.max_bucketsR, (size_t)pr.total_buckets);
         s.max_bucketsZ = std::max(s.max_bucketsZ, (size_t)pz.total_buckets);
-        s.max_segs = std::max(s.max_segs, (size_t)std::max(pr.total_segs, pz.total_segs));
     }
     capR += capR / 8 + 4096;
     capZ += capZ / 8 + 8192;
-    s.max_bucketsR += 4096; s.max_bucketsZ += 4096; s.max_segs += 4096;
+    s.max_bucketsR += 4096; s.max_bucketsZ += 4096;
     if (slot_alloc_sort(s.sortR, capR, s.max_bucketsR + 512)) return KZGB_ERROR;
     if (slot_alloc_sort(s.sortZ, capZ, s.max_bucketsZ + 512)) return KZGB_ERROR;
     CK(dmalloc(s.bucketsA, s.max_bucketsR + 512)); CK(dmalloc(s.bucketsB, s.max_bucketsR + 512));
     {
-        // scratch of the batched subgroup check: worst case over every window width msm_make_plan can pick
+        // scratch of the bucket reduction (run sums, row / column totals, 256 slice sums) for three concurrent
+        // sums: worst case over every window width msm_make_plan can pick
         s.sg_cap = 0;
         for (int c = 3; c <= 16; ++c) {
             MsmPlan p;
             p.nbits = 128; p.c = c; p.W = (128 + c - 1) / c;
             s.sg_cap = std::max(s.sg_cap, sg_work_entries(p));
         }
-        CK(dmalloc(s.sg_partial, 2 * s.sg_cap));
+        s.sg_cap += 256;
+        CK(dmalloc(s.sg_partial, 3 * s.sg_cap));
     }
     {
         const char* e = getenv("KZGB_SG_BATCH_MIN");
         if (e) s.sg_min = (size_t)strtoull(e, nullptr, 10);
     }
     CK(dmalloc(s.bucketsC, s.max_bucketsZ + 512));
-    CK(dmalloc(s.segsums, 3 * s.max_segs)); CK(dmalloc(s.winsums, 3 * KZ_MSM_MAX_WINDOWS));
+    CK(dmalloc(s.winsums, 3 * KZ_MSM_MAX_WINDOWS));
     {   // chunk records for the balanced accumulation: worst case over the chunk-length schedule
         auto mn = [](size_t a, size_t b) { return a < b ? a : b; };
         size_t tmax = capZ / msm_chunk_len(capZ) + 1;
@@ -238,7 +239,7 @@ void slot_free(DeviceSlot& s) {
                    s.partials, s.sum_ry, s.zs, s.sortR.keys, s.sortR.vals, s.sortR.keys_alt, s.sortR.vals_alt, s.sortR.bucket_start, s.sortR.count, s.sortR.cursor,
                    s.sortZ.count, s.sortZ.cursor,
                    s.sortZ.keys, s.sortZ.vals, s.sortZ.keys_alt, s.sortZ.vals_alt, s.sortZ.bucket_start, s.bucketsA,
-                   s.bucketsB, s.bucketsC, s.segsums, s.winsums, s.sums, s.partial_dev, s.partials_in,
+                   s.bucketsB, s.bucketsC, s.winsums, s.sums, s.partial_dev, s.partials_in,
                    s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb, s.recs.head, s.recs.tail,
                    s.recs.head_key, s.recs.tail_key, s.recs.head_flags, s.recsA.head, s.recsA.tail, s.recsA.head_key,
                    s.recsA.tail_key, s.recsA.head_flags, s.recsB.head, s.recsB.tail, s.recsB.head_key, s.recsB.tail_key,
@@ -261,9 +262,10 @@ MsmWorkspace make_ws(DeviceSlot& s, SortBuf& b, G1Xyzz* buckets) {
     MsmWorkspace ws;
     ws.keys = b.keys; ws.vals = b.vals; ws.keys_alt = b.keys_alt; ws.vals_alt = b.vals_alt;
     ws.capacity = b.capacity; ws.bucket_start = b.bucket_start; ws.count = b.count; ws.cursor = b.cursor;
-    ws.buckets = buckets; ws.segsums = s.segsums;
+    ws.buckets = buckets;
     ws.winsums = s.winsums; ws.recs = s.recs;
-    ws.max_buckets = 0; ws.max_segs = s.max_segs;
+    ws.sg_work = s.sg_partial; ws.slices = s.sg_partial + s.sg_cap - 256;
+    ws.max_buckets = 0;
     return ws;
 }
 void save_ws(SortBuf& b, const MsmWorkspace& ws) {
@@ -373,7 +375,7 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     s.planZ = msm_make_plan(2 * (n + 1), 128);
     if ((size_t)s.planR.W * n > s.sortR.capacity || (size_t)s.planZ.W * 2 * (n + 1) > s.sortZ.capacity ||
         s.planR.total_buckets > s.max_bucketsR + 512 || s.planZ.total_buckets > s.max_bucketsZ + 512 ||
-        s.planZ.total_segs > s.max_segs || s.planR.total_segs > s.max_segs || sg_work_entries(s.planR) > s.sg_cap)
+        sg_work_entries(s.planR) + 256 > s.sg_cap || sg_work_entries(s.planZ) + 256 > s.sg_cap)
         return KZGB_BADARGS;
     MsmWorkspace wr = make_ws(s, s.sortR, s.bucketsA), wz = make_ws(s, s.sortZ, s.bucketsC);
     msm_sort_stage(s2, s.planR, s.r, 4, n, wr);
@@ -385,8 +387,10 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     MsmWorkspace wr2 = wr;
     wr.recs = s.recsA;
     wr2.buckets = s.bucketsB; wr2.recs = s.recsB;
-    wr2.segsums = s.segsums + s.max_segs; wr2.winsums = s.winsums + KZ_MSM_MAX_WINDOWS;
-    wz.segsums = s.segsums + 2 * s.max_segs; wz.winsums = s.winsums + 2 * KZ_MSM_MAX_WINDOWS;
+    wr2.winsums = s.winsums + KZ_MSM_MAX_WINDOWS;
+    wz.winsums = s.winsums + 2 * KZ_MSM_MAX_WINDOWS;
+    wr2.sg_work = s.sg_partial + s.sg_cap; wr2.slices = wr2.sg_work + s.sg_cap - 256;
+    wz.sg_work = s.sg_partial + 2 * s.sg_cap; wz.slices = wz.sg_work + s.sg_cap - 256;
     // Longest chain (S2', twice the points) first, all three sums at normal priority.  The alternative -- S1 and S3
     // at high priority so that the batched subgroup check starts early and overlaps S2' -- is kept behind
     // KZGB_MSM_PRI_MIN; it was slower at every batch size.
@@ -398,26 +402,25 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     CK(cudaStreamWaitEvent(sS1, s.ev[11], 0));
     if (!pri) {
         msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);
-        msm_window_sums_stage(s.stream4, s.planZ, wz);
+        msm_window_sums_stage(s.stream4, s.planZ, wz, false);
         CK(cudaEventRecord(s.ev[13], s.stream4));
     }
     msm_accumulate_stage(sS3, s.planR, s.pts + 2 * n, n, wr2);                   // S3 over pi_i
-    msm_window_sums_stage(sS3, s.planR, wr2);
+    msm_window_sums_stage(sS3, s.planR, wr2, s.sg_batch);
     CK(cudaEventRecord(s.ev[12], sS3));
     msm_accumulate_stage(sS1, s.planR, s.pts, n, wr);                            // S1 over C_i
-    CK(cudaEventRecord(s.ev[10], sS1));                                          // buckets of S1 complete
-    msm_window_sums_stage(sS1, s.planR, wr);
+    msm_window_sums_stage(sS1, s.planR, wr, s.sg_batch);
     CK(cudaEventRecord(s.ev[16], sS1));
     if (pri) {
         msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);   // S2' over pi_i, G and their phi images
-        msm_window_sums_stage(s.stream4, s.planZ, wz);
+        msm_window_sums_stage(s.stream4, s.planZ, wz, false);
         CK(cudaEventRecord(s.ev[13], s.stream4));
     }
     if (s.sg_batch) {
         // batched subgroup check: 128 slice sums of the S3 buckets (all pi_i) and of the S1 buckets (all C_i)
-        launch_sg_batch_check(sS3, s.planR, wr2.buckets, s.sg_partial, s.counters);
-        CK(cudaStreamWaitEvent(sS3, s.ev[10], 0));
-        launch_sg_batch_check(sS3, s.planR, wr.buckets, s.sg_partial + s.sg_cap, s.counters);
+        launch_sg_check(sS3, s.planR, wr2, s.counters);
+        CK(cudaStreamWaitEvent(sS3, s.ev[16], 0));                               // slice sums of S1 are complete
+        launch_sg_check(sS3, s.planR, wr, s.counters);
         // the verdict of the check travels on this stream: the main stream goes on to the pairing without it
         CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sS3));
         CK(cudaEventRecord(s.ev[9], sS3));
@@ -729,7 +732,7 @@ kzgb_ret kzgb_g1_msm(uint8_t affine_out[96], const uint8_t* points_affine, const
     const bool glv = nbits == 255;
     size_t mm = glv ? 2 * m : m;
     MsmPlan plan = msm_make_plan(mm, 128);
-    if ((size_t)plan.W * mm > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || plan.total_segs > s.max_segs) {
+    if ((size_t)plan.W * mm > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || sg_work_entries(plan) + 256 > s.sg_cap) {
         cudaFree(d_pts); cudaFree(d_sc);
         return KZGB_BADARGS;
     }
@@ -828,7 +831,7 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     {
         size_t mm = 2 * M;
         MsmPlan plan = msm_make_plan(mm, 128);
-        if ((size_t)plan.W * mm > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || plan.total_segs > s.max_segs)
+        if ((size_t)plan.W * mm > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || sg_work_entries(plan) + 256 > s.sg_cap)
             return KZGB_BADARGS;
         MsmWorkspace ws = make_ws(s, s.sortZ, s.bucketsC);
         launch_glv_split(st, s.rz, M, s.zs);
@@ -841,7 +844,7 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     // B-side: sum r_k pi_k, 128-bit scalars
     {
         MsmPlan plan = msm_make_plan(m, 128);
-        if ((size_t)plan.W * m > s.sortR.capacity || plan.total_buckets > s.max_bucketsR + 512 || plan.total_segs > s.max_segs)
+        if ((size_t)plan.W * m > s.sortR.capacity || plan.total_buckets > s.max_bucketsR + 512 || sg_work_entries(plan) + 256 > s.sg_cap)
             return KZGB_BADARGS;
         MsmWorkspace ws = make_ws(s, s.sortR, s.bucketsA);
         ws.recs = s.recsA;

@@ -189,32 +189,51 @@ __global__ void __launch_bounds__(128) k_msm_chunk_pass2(u32 T, G1Xyzz* __restri
     msm_chunk_pass2(T, t, buckets, R);
 }
 
-__global__ void __launch_bounds__(128) k_msm_segments(const G1Xyzz* __restrict__ buckets, G1Xyzz* __restrict__ segsums,
-                                                      const __grid_constant__ MsmPlan plan) {
-    u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= plan.total_segs) return;
-    int w = 0;
-    while (s >= plan.seg_off[w + 1]) ++w;
-    segsums[s] = msm_segment_body(buckets + plan.bucket_off[w], plan.nb[w], s - plan.seg_off[w], plan.seg);
+// ---- bucket reduction (msm.cuh "bucket reduction through row / column totals")
+__global__ void __launch_bounds__(128) k_sg_pass1(const G1Xyzz* __restrict__ buckets, G1Xyzz* __restrict__ part, u32 stride,
+                                                   const __grid_constant__ MsmPlan plan) {
+    const int w = blockIdx.y;
+    const SgWin g = sg_win(plan, w);
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.jobs) return;
+    part[(size_t)w * stride + t] = sg_run_sum(buckets + plan.bucket_off[w], g, t);
 }
-
-// one block per window: sum of its segment sums
-#define KZ_WIN_THREADS 128
-__global__ void __launch_bounds__(KZ_WIN_THREADS) k_msm_window_sum(const G1Xyzz* __restrict__ segsums,
-                                                                   G1Xyzz* __restrict__ winsums,
-                                                                   const __grid_constant__ MsmPlan plan) {
-    __shared__ G1Xyzz red[KZ_WIN_THREADS];
-    int w = blockIdx.x;
-    u32 lo = plan.seg_off[w], hi = plan.seg_off[w + 1];
-    G1Xyzz acc = xyzz_inf();
-    for (u32 s = lo + threadIdx.x; s < hi; s += KZ_WIN_THREADS) acc = xyzz_add(acc, segsums[s]);
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int st = KZ_WIN_THREADS / 2; st > 0; st >>= 1) {
+__global__ void __launch_bounds__(128) k_sg_pass2(const G1Xyzz* __restrict__ part, u32 stride, G1Xyzz* __restrict__ tot, u32 tstride,
+                                                   const __grid_constant__ MsmPlan plan) {
+    const int w = blockIdx.y;
+    const SgWin g = sg_win(plan, w);
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.rows + g.cols) return;
+    tot[(size_t)w * tstride + t] = sg_total(part + (size_t)w * stride, g, t);
+}
+// one warp per slice: strided partial sums, shared-memory tree, slice sum to slices[sid]
+__global__ void __launch_bounds__(32) k_sg_slices(const G1Xyzz* __restrict__ buckets, const G1Xyzz* __restrict__ tot, u32 tstride,
+                                                   G1Xyzz* __restrict__ slices, int want_all, const __grid_constant__ MsmPlan plan) {
+    __shared__ G1Xyzz red[32];
+    const SgSlice sl = sg_slice(plan, (int)blockIdx.x);
+    if (sl.all && !want_all) return;
+    const SgWin g = sg_win(plan, sl.w);
+    red[threadIdx.x] = sg_slice_part(tot + (size_t)sl.w * tstride, buckets + plan.bucket_off[sl.w], g, sl, threadIdx.x, 32);
+    __syncwarp();
+    for (int st = 16; st > 0; st >>= 1) {
         if ((int)threadIdx.x < st) red[threadIdx.x] = xyzz_add(red[threadIdx.x], red[threadIdx.x + st]);
-        __syncthreads();
+        __syncwarp();
     }
-    if (threadIdx.x == 0) winsums[w] = red[0];
+    if (threadIdx.x == 0) slices[blockIdx.x] = red[0];
+}
+// one thread per window: Horner over its bit slices
+__global__ void __launch_bounds__(32) k_msm_window_horner(const G1Xyzz* __restrict__ buckets, const G1Xyzz* __restrict__ slices,
+                                                           G1Xyzz* __restrict__ winsums, const __grid_constant__ MsmPlan plan) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= plan.W) return;
+    const SgWin g = sg_win(plan, w);
+    winsums[w] = msm_window_from_slices(slices + (size_t)w * plan.c, g.k, buckets[plan.bucket_off[w] + (1u << g.k) - 1u]);
+}
+// batched subgroup check: one thread per slice sum; counters[2] += sums outside G1
+__global__ void __launch_bounds__(32) k_sg_check(const G1Xyzz* __restrict__ slices, int nslices, u32* __restrict__ counters) {
+    const int sid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sid >= nslices) return;
+    if (!sg_sum_in_g1(slices[sid])) atomicAdd(counters + 2, 1u);
 }
 // Horner combine; one block per job so the three sums of a batch run their serial chains concurrently
 struct CombineJobs {
@@ -260,11 +279,24 @@ void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, si
     k_msm_chunk_pass2<<<(T + 127) / 128, 128, 0, s>>>(T, ws.buckets, ws.recs);
     KZ_COUNT_LAUNCH();
 }
-// bucket reduction of one sum up to its per-window totals (ws.winsums)
-void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws) {
-    k_msm_segments<<<(plan.total_segs + 127) / 128, 128, 0, s>>>(ws.buckets, ws.segsums, plan);
+// bucket reduction of one sum up to its per-window totals (ws.winsums); ws.slices keeps the nbits slice sums.
+// want_all: also the "all" slices of the signed windows (needed only by the batched subgroup check)
+void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, bool want_all) {
+    const SgLayout L = sg_layout(plan);
+    G1Xyzz* part = ws.sg_work;
+    G1Xyzz* tot = ws.sg_work + (size_t)plan.W * L.stride;
+    k_sg_pass1<<<dim3((L.stride + 127) / 128, (unsigned)plan.W), 128, 0, s>>>(ws.buckets, part, L.stride, plan);
     KZ_COUNT_LAUNCH();
-    k_msm_window_sum<<<plan.W, KZ_WIN_THREADS, 0, s>>>(ws.segsums, ws.winsums, plan);
+    k_sg_pass2<<<dim3((L.tstride + 127) / 128, (unsigned)plan.W), 128, 0, s>>>(part, L.stride, tot, L.tstride, plan);
+    KZ_COUNT_LAUNCH();
+    k_sg_slices<<<(unsigned)plan.nbits, 32, 0, s>>>(ws.buckets, tot, L.tstride, ws.slices, want_all ? 1 : 0, plan);
+    KZ_COUNT_LAUNCH();
+    k_msm_window_horner<<<(unsigned)((plan.W + 31) / 32), 32, 0, s>>>(ws.buckets, ws.slices, ws.winsums, plan);
+    KZ_COUNT_LAUNCH();
+}
+// batched subgroup check on the slice sums msm_window_sums_stage(.., want_all = true) left in ws.slices
+void launch_sg_check(cudaStream_t s, const MsmPlan& plan, const MsmWorkspace& ws, uint32_t* counters) {
+    k_sg_check<<<(unsigned)((plan.nbits + 31) / 32), 32, 0, s>>>(ws.slices, plan.nbits, counters);
     KZ_COUNT_LAUNCH();
 }
 // Horner combine of up to 3 sums whose window totals are ready; one block per sum
@@ -277,7 +309,7 @@ void msm_combine_stage(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace
     KZ_COUNT_LAUNCH();
 }
 void msm_reduce_stage_multi(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs) {
-    for (int j = 0; j < njobs; ++j) msm_window_sums_stage(s, *plans[j], *wss[j]);
+    for (int j = 0; j < njobs; ++j) msm_window_sums_stage(s, *plans[j], *wss[j], false);
     msm_combine_stage(s, plans, wss, outs, njobs);
 }
 void msm_reduce_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, G1Jac* out) {

@@ -25,9 +25,6 @@ void launch_decompress_points(cudaStream_t s, const uint8_t* in, size_t m, Fp* o
 // K1a only / per-point subgroup check only (batched subgroup check and its fallback)
 void launch_decompress_sqrt_points(cudaStream_t s, const uint8_t* in, size_t m, Fp* out_pts, uint8_t* status, uint32_t* counters);
 void launch_subgroup_points(cudaStream_t s, Fp* pts, size_t m, Fp* tmp, uint8_t* status, uint32_t* counters);
-// batched subgroup check on the buckets of a 128-bit sum: counters[2] += slice sums outside G1
-size_t sg_work_entries(const MsmPlan& plan);          // G1Xyzz entries of scratch one call needs
-void launch_sg_batch_check(cudaStream_t s, const MsmPlan& plan, const G1Xyzz* buckets, G1Xyzz* work, uint32_t* counters);
 void launch_points_to_be(cudaStream_t s, const Fp* pts, size_t m, uint8_t* out96);           // canonical x||y
 void launch_points_from_be(cudaStream_t s, const uint8_t* in96, size_t m, Fp* pts, uint32_t* counters);
 void launch_debug_op(cudaStream_t s, int op, const uint8_t* in, uint8_t* out, size_t count);
@@ -55,10 +52,11 @@ struct MsmWorkspace {
     uint32_t* bucket_start;                        // total_buckets + 2: exclusive scan of the key histogram
     uint32_t *count, *cursor;                      // total_buckets + 2 each: histogram, scatter cursors
     G1Xyzz* buckets;                               // max total buckets
-    G1Xyzz* segsums;                               // max total segs
+    G1Xyzz* sg_work;                               // sg_work_entries(plan): run sums and row / column totals
+    G1Xyzz* slices;                                // 256: slice sums of the last reduction
     G1Xyzz* winsums;                               // KZ_MSM_MAX_WINDOWS
     ChunkRecs recs;                                // partial records, capacity/4 + 1 chunks
-    size_t max_buckets, max_segs;
+    size_t max_buckets;
 };
 // GLV: 255-bit scalars (8 limbs) -> k1 (m x 4 limbs) | k2 (m x 4 limbs); points P -> phi(P) = (beta^2 x, y)
 void launch_glv_split(cudaStream_t s, const uint32_t* scalars8, size_t m, uint32_t* out4);
@@ -69,9 +67,11 @@ void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars
 // accumulate + reduce + combine over points `pts` (2 Fp each, m points) using the sorted entries in ws
 void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, size_t m, MsmWorkspace& ws);
 void msm_reduce_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, G1Jac* out);
-void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws);
+void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, bool want_all);
+// batched subgroup check on ws.slices (after msm_window_sums_stage with want_all): counters[2] += sums outside G1
+void launch_sg_check(cudaStream_t s, const MsmPlan& plan, const MsmWorkspace& ws, uint32_t* counters);
 void msm_combine_stage(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs);
-// up to 3 jobs; each job needs its own buckets / segsums / winsums; the serial Horner chains run concurrently
+// up to 3 jobs; each job needs its own buckets / sg_work / slices / winsums; the serial Horner chains run concurrently
 void msm_reduce_stage_multi(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs);
 
 // ---- k_pairing.cu

@@ -10,11 +10,9 @@ struct MsmPlan {
     int nbits;                   // scalar width: 128 or 255
     int c;                       // window width
     int W;                       // number of windows = ceil(nbits / c)
-    u32 seg;                     // buckets per reduction segment
     u32 nb[KZ_MSM_MAX_WINDOWS];          // buckets per window (top window is unsigned)
     u32 bucket_off[KZ_MSM_MAX_WINDOWS + 1];   // prefix sums of nb
-    u32 seg_off[KZ_MSM_MAX_WINDOWS + 1];      // prefix sums of ceil(nb / SEG)
-    u32 total_buckets, total_segs;
+    u32 total_buckets;
 };
 
 // Signed windows 0..W-2 (digit in [-2^(c-1), 2^(c-1)]), unsigned top window that absorbs the last carry,
@@ -41,17 +39,13 @@ inline MsmPlan msm_make_plan(size_t n, int nbits) {
     p.nbits = nbits;
     p.c = c;
     p.W = (nbits + c - 1) / c;
-    p.seg = c >= 15 ? 16u : 8u;   // short serial chains: the reduction is latency-bound
     p.bucket_off[0] = 0;
-    p.seg_off[0] = 0;
     for (int w = 0; w < p.W; ++w) {
         int tb = nbits - c * (p.W - 1);
         p.nb[w] = (w < p.W - 1) ? (1u << (c - 1)) : (1u << tb);
         p.bucket_off[w + 1] = p.bucket_off[w] + p.nb[w];
-        p.seg_off[w + 1] = p.seg_off[w] + (p.nb[w] + p.seg - 1) / p.seg;
     }
     p.total_buckets = p.bucket_off[p.W];
-    p.total_segs = p.seg_off[p.W];
     return p;
 }
 
@@ -228,31 +222,6 @@ KZ_HD void msm_chunk_pass2(u32 T, u32 t, G1Xyzz* buckets, const ChunkRecs& R) {
     }
 }
 
-// [k]P by double-and-add for a small k (< 2^17)
-KZ_COLD G1Xyzz xyzz_mul_small(const G1Xyzz& p, u32 k) {
-    if (!k) return xyzz_inf();
-    int top = 16;
-    while (!((k >> top) & 1)) --top;
-    G1Xyzz r = p;
-    for (int i = top - 1; i >= 0; --i) {
-        r = xyzz_dbl(r);
-        if ((k >> i) & 1) r = xyzz_add(r, p);
-    }
-    return r;
-}
-// segment `seg` of window w: local buckets k = base+1 .. min(base+seglen, nb), base = seg*seglen.
-// returns sum_k k * B_k  (running-sum trick inside the segment plus [base] * run).
-KZ_HD G1Xyzz msm_segment_body(const G1Xyzz* buckets, u32 nb, u32 seg, u32 seglen) {
-    u32 base = seg * seglen;
-    u32 top = base + seglen < nb ? base + seglen : nb;
-    G1Xyzz run = xyzz_inf(), acc = xyzz_inf();
-    for (u32 k = top; k > base; --k) {          // bucket with value k is stored at index k-1
-        run = xyzz_add(run, buckets[k - 1]);
-        acc = xyzz_add(acc, run);
-    }
-    if (base) acc = xyzz_add(acc, xyzz_mul_small(run, base));
-    return acc;
-}
 // Horner over window sums: result = sum_w 2^(c w) * win[w].  The chain of c(W-1) doublings is serial, so it
 // runs in Jacobian coordinates (2M+5S per doubling instead of 6M+3S in XYZZ).
 KZ_COLD G1Jac msm_combine_body(const G1Xyzz* win, int W, int c) {
@@ -265,34 +234,107 @@ KZ_COLD G1Jac msm_combine_body(const G1Xyzz* win, int W, int c) {
     return acc;
 }
 
-// ---- batched subgroup check on the bucket sums of a 128-bit MSM (DESIGN.md "Batched subgroup check").
-// The signed digits of the challenges r_i are 128 fair, independent coins per point: for a signed window the
-// c-1 magnitude bits and the sign, for the unsigned top window its tb bits (c(W-1) + tb = 128).  Slice (w, b)
-// sums the buckets of window w whose magnitude has bit b set; slice (w, c-1) of a signed window sums all its
-// buckets (coefficient = sign of the digit).  Point P_i enters each slice with a coefficient in {-1, 0, 1}
-// that takes any fixed value with probability <= 1/2 + 2^-c, independently over the 128 slices, so a point with
-// a non-zero cofactor component (odd order >= 3) leaves every one of the 128 slice sums inside G1 with
-// probability <= 2^-127: checking the 128 sums replaces 2n per-point checks.  No extra point additions are
-// needed -- the buckets are the ones the sum  sum r_i P_i  fills anyway.
-struct SgSlice { int w; int b; bool all; u32 count; };
+// ---- bucket reduction through row / column totals, and the batched subgroup check that shares them.
+// A window with k magnitude bits (k = c-1, or tb for the unsigned top window) is a 2^kh x 2^kl table of buckets,
+// m = row * 2^kl + col, kl = k / 2 (the bucket of magnitude m sits at index m - 1; m = 0 is no bucket, m = 2^k is
+// the one bucket outside the table).  Bit b of m is a column bit (b < kl) or a row bit, so the slice sums
+//     T_b = sum { B_m : bit b of m set }        b = 0 .. k-1
+// are sums of column totals Q_c or of row totals R_r, and the window total is a Horner chain over them:
+//     sum_m m B_m = 2^k B_{2^k} + sum_b 2^b T_b.
+//   pass 1  sums of runs of KZ_SG_RUN buckets along rows and along columns (every lane busy)
+//   pass 2  the 2^kh row totals and 2^kl column totals
+//   slices  T_b from the totals (one block per slice), plus, for the batched subgroup check, the slice "all" =
+//           sum of every bucket of a signed window
+//   window  Horner over the k slices of each window (one thread per window)
+// 2 * 2^k additions per window, all of them independent, then 2k serial point operations.
+//
+// Batched subgroup check: the signed digits of the challenges r_i are 128 fair, independent coins per
+// point -- for a signed window the c-1 magnitude bits and the sign, for the top window its tb bits.  Point P_i
+// enters slice (w, b) with coefficient sign * bit in {-1, 0, 1} and slice (w, all) with its sign; each value has
+// probability <= 1/2 + 2^-c, independently over the 128 slices, so a point with a non-zero cofactor component (odd
+// order >= 3) leaves all 128 slice sums inside G1 with probability <= 2^-127.  Checking the 128 sums of
+// sum r_i C_i and of sum r_i pi_i replaces 2n per-point checks, with no extra point additions.
+#define KZ_SG_RUN 16
+struct SgWin { int k, kl, kh; u32 rows, cols, tpr, tpc, rjobs, jobs; };
+KZ_HD SgWin sg_win(const MsmPlan& P, int w) {
+    SgWin g;
+    g.k = w < P.W - 1 ? P.c - 1 : P.nbits - P.c * (P.W - 1);
+    g.kl = g.k / 2; g.kh = g.k - g.kl;
+    g.rows = 1u << g.kh; g.cols = 1u << g.kl;
+    g.tpr = g.cols > KZ_SG_RUN ? g.cols / KZ_SG_RUN : 1u;       // threads per row
+    g.tpc = g.rows > KZ_SG_RUN ? g.rows / KZ_SG_RUN : 1u;       // threads per column
+    g.rjobs = g.rows * g.tpr;
+    g.jobs = g.rjobs + g.cols * g.tpc;
+    return g;
+}
+// scratch layout of one sum: [W][stride] run sums, then [W][tstride] totals (R then Q); strides of the widest window
+struct SgLayout { u32 stride, tstride; };
+inline SgLayout sg_layout(const MsmPlan& P) {
+    int kmax = P.c - 1, tb = P.nbits - P.c * (P.W - 1);
+    if (P.W == 1 || tb > kmax) kmax = tb;
+    int kl = kmax / 2, kh = kmax - kl;              // floor and ceil are monotone in k: the widest window bounds all
+    u32 rows = 1u << kh, cols = 1u << kl;
+    u32 tpr = cols > KZ_SG_RUN ? cols / KZ_SG_RUN : 1u, tpc = rows > KZ_SG_RUN ? rows / KZ_SG_RUN : 1u;
+    return {rows * tpr + cols * tpc, rows + cols};
+}
+inline size_t sg_work_entries(const MsmPlan& P) {
+    SgLayout L = sg_layout(P);
+    return (size_t)P.W * (L.stride + L.tstride);
+}
+KZ_HD G1Xyzz sg_bucket(const G1Xyzz* base, u32 m) { return m ? base[m - 1] : xyzz_inf(); }
+// pass 1, job t of window g: a run along a row (t < rjobs) or along a column
+KZ_HD G1Xyzz sg_run_sum(const G1Xyzz* base, const SgWin& g, u32 t) {
+    G1Xyzz acc = xyzz_inf();
+    if (t < g.rjobs) {
+        u32 r = t / g.tpr, p = t - r * g.tpr, len = g.cols / g.tpr;
+        u32 m0 = (r << g.kl) + p * len;
+        for (u32 i = 0; i < len; ++i) acc = xyzz_add(acc, sg_bucket(base, m0 + i));
+    } else {
+        u32 u = t - g.rjobs, c = u / g.tpc, p = u - c * g.tpc, len = g.rows / g.tpc;
+        for (u32 i = 0; i < len; ++i) acc = xyzz_add(acc, sg_bucket(base, ((p * len + i) << g.kl) + c));
+    }
+    return acc;
+}
+// pass 2, job t: row total R[t] (t < rows) or column total Q[t - rows] from the run sums of the window
+KZ_HD G1Xyzz sg_total(const G1Xyzz* part_w, const SgWin& g, u32 t) {
+    const G1Xyzz* src = part_w + (t < g.rows ? t * g.tpr : g.rjobs + (t - g.rows) * g.tpc);
+    const u32 cnt = t < g.rows ? g.tpr : g.tpc;
+    G1Xyzz acc = src[0];
+    for (u32 i = 1; i < cnt; ++i) acc = xyzz_add(acc, src[i]);
+    return acc;
+}
+// slice ids: signed window w: w*c + b, b < c-1 magnitude bits, b = c-1 the slice "all"; top window: c(W-1) + b
+struct SgSlice { int w; int b; bool all; };
 KZ_HD SgSlice sg_slice(const MsmPlan& P, int sid) {
     SgSlice s;
     int signed_slices = P.c * (P.W - 1);
     if (sid < signed_slices) { s.w = sid / P.c; s.b = sid - s.w * P.c; s.all = s.b == P.c - 1; }
     else { s.w = P.W - 1; s.b = sid - signed_slices; s.all = false; }
-    s.count = s.all ? P.nb[s.w] : P.nb[s.w] / 2;
     return s;
 }
-// j-th member (j < count) -> bucket index inside the window (bucket of magnitude m sits at m - 1)
-KZ_HD u32 sg_member_bucket(const SgSlice& s, u32 j) {
-    if (s.all) return j;
-    u32 low = (1u << s.b) - 1u;
-    u32 m = ((j & ~low) << 1) | (1u << s.b) | (j & low);
-    return m - 1u;
+// the part of a slice sum that lane `lane` of `nl` lanes adds up (tot_w = R then Q of the window)
+KZ_HD G1Xyzz sg_slice_part(const G1Xyzz* tot_w, const G1Xyzz* base, const SgWin& g, const SgSlice& sl, u32 lane, u32 nl) {
+    const G1Xyzz* R = tot_w;
+    const G1Xyzz* Q = tot_w + g.rows;
+    G1Xyzz acc = xyzz_inf();
+    if (sl.all) {
+        for (u32 r = lane; r < g.rows; r += nl) acc = xyzz_add(acc, R[r]);
+        if (lane == 0) acc = xyzz_add(acc, base[(1u << g.k) - 1u]);            // magnitude 2^k
+    } else if (sl.b < g.kl) {
+        for (u32 c = lane; c < g.cols; c += nl) if ((c >> sl.b) & 1u) acc = xyzz_add(acc, Q[c]);
+    } else {
+        for (u32 r = lane; r < g.rows; r += nl) if ((r >> (sl.b - g.kl)) & 1u) acc = xyzz_add(acc, R[r]);
+    }
+    return acc;
+}
+// window total from its k bit slices T[0..k) and the bucket of magnitude 2^k
+KZ_COLD G1Xyzz msm_window_from_slices(const G1Xyzz* T, int k, const G1Xyzz& ext) {
+    G1Xyzz acc = ext;
+    for (int b = k - 1; b >= 0; --b) acc = xyzz_add(xyzz_dbl(acc), T[b]);
+    return acc;
 }
 KZ_COLD bool sg_sum_in_g1(const G1Xyzz& t) {
     if (xyzz_is_inf(t)) return true;
     G1Aff a = jac_to_aff(xyzz_to_jac(t));
     return g1_in_subgroup(a);
 }
-

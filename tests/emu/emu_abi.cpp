@@ -70,7 +70,7 @@ static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nb
     for (size_t i = 0; i < N; ++i) { sk[i] = keys[order[i]]; sv[i] = vals[order[i]]; }
     std::vector<u32> start(plan.total_buckets + 2);
     for (u32 b = 0; b <= plan.total_buckets + 1; ++b) start[b] = (u32)(std::lower_bound(sk.begin(), sk.end(), b) - sk.begin());
-    std::vector<G1Xyzz> buckets(plan.total_buckets), segs(plan.total_segs), wins(plan.W);
+    std::vector<G1Xyzz> buckets(plan.total_buckets), wins(plan.W);
     // balanced two-pass accumulation with a short chunk so that buckets straddle many chunks
     {
         u32 L = 3, n_valid = start[plan.total_buckets], T = (u32)((N + L - 1) / L);
@@ -88,23 +88,32 @@ static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nb
             if (!same) { fprintf(stderr, "emu: bucket %u differs\n", b); abort(); }
         }
     }
-    if (sg_fail) {
-        for (int sid = 0; sid < plan.nbits; ++sid) {
-            SgSlice sl = sg_slice(plan, sid);
-            G1Xyzz acc = xyzz_inf();
-            for (u32 j = 0; j < sl.count; ++j) acc = xyzz_add(acc, buckets[plan.bucket_off[sl.w] + sg_member_bucket(sl, j)]);
-            *sg_fail += !sg_sum_in_g1(acc);
-        }
+    // bucket reduction exactly as the device does it: run sums, row / column totals, slice sums, window Horner
+    const SgLayout L = sg_layout(plan);
+    std::vector<G1Xyzz> part((size_t)plan.W * L.stride), tot((size_t)plan.W * L.tstride), slices(plan.nbits);
+    for (int w = 0; w < plan.W; ++w) {
+        const SgWin g = sg_win(plan, w);
+        for (u32 t = 0; t < g.jobs; ++t) part[(size_t)w * L.stride + t] = sg_run_sum(buckets.data() + plan.bucket_off[w], g, t);
+        for (u32 t = 0; t < g.rows + g.cols; ++t) tot[(size_t)w * L.tstride + t] = sg_total(part.data() + (size_t)w * L.stride, g, t);
     }
-    for (u32 s = 0; s < plan.total_segs; ++s) {
-        int w = 0;
-        while (s >= plan.seg_off[w + 1]) ++w;
-        segs[s] = msm_segment_body(buckets.data() + plan.bucket_off[w], plan.nb[w], s - plan.seg_off[w], plan.seg);
+    for (int sid = 0; sid < plan.nbits; ++sid) {
+        const SgSlice sl = sg_slice(plan, sid);
+        const SgWin g = sg_win(plan, sl.w);
+        G1Xyzz acc = xyzz_inf();
+        for (u32 lane = 0; lane < 5; ++lane)          // any lane count gives the same sum
+            acc = xyzz_add(acc, sg_slice_part(tot.data() + (size_t)sl.w * L.tstride, buckets.data() + plan.bucket_off[sl.w], g, sl, lane, 5));
+        slices[sid] = acc;
+        if (sg_fail && !sg_sum_in_g1(acc)) *sg_fail += 1;
     }
     for (int w = 0; w < plan.W; ++w) {
-        G1Xyzz acc = xyzz_inf();
-        for (u32 s = plan.seg_off[w]; s < plan.seg_off[w + 1]; ++s) acc = xyzz_add(acc, segs[s]);
-        wins[w] = acc;
+        const SgWin g = sg_win(plan, w);
+        wins[w] = msm_window_from_slices(slices.data() + (size_t)w * plan.c, g.k, buckets[plan.bucket_off[w] + (1u << g.k) - 1u]);
+        // cross-check against the definition sum_m m * B_m
+        G1Xyzz run = xyzz_inf(), ref = xyzz_inf();
+        for (u32 m = plan.nb[w]; m >= 1; --m) { run = xyzz_add(run, buckets[plan.bucket_off[w] + m - 1]); ref = xyzz_add(ref, run); }
+        G1Jac a = xyzz_to_jac(ref), c2 = xyzz_to_jac(wins[w]);
+        bool same = jac_is_inf(a) ? jac_is_inf(c2) : (!jac_is_inf(c2) && aff_is_inf(jac_to_aff(jac_add(a, jac_neg(c2)))));
+        if (!same) { fprintf(stderr, "emu: window %d total differs\n", w); abort(); }
     }
     return msm_combine_body(wins.data(), plan.W, plan.c);
 }
