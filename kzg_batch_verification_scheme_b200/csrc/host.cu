@@ -418,9 +418,8 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     }
     if (s.sg_batch) {
         // batched subgroup check: 128 slice sums of the S3 buckets (all pi_i) and of the S1 buckets (all C_i)
-        launch_sg_check(sS3, s.planR, wr2, s.counters);
         CK(cudaStreamWaitEvent(sS3, s.ev[16], 0));                               // slice sums of S1 are complete
-        launch_sg_check(sS3, s.planR, wr, s.counters);
+        launch_sg_check(sS3, s.planR, wr2, wr, s.counters);
         // the verdict of the check travels on this stream: the main stream goes on to the pairing without it
         CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sS3));
         CK(cudaEventRecord(s.ev[9], sS3));

@@ -229,11 +229,12 @@ __global__ void __launch_bounds__(32) k_msm_window_horner(const G1Xyzz* __restri
     const SgWin g = sg_win(plan, w);
     winsums[w] = msm_window_from_slices(slices + (size_t)w * plan.c, g.k, buckets[plan.bucket_off[w] + (1u << g.k) - 1u]);
 }
-// batched subgroup check: one thread per slice sum; counters[2] += sums outside G1
-__global__ void __launch_bounds__(32) k_sg_check(const G1Xyzz* __restrict__ slices, int nslices, u32* __restrict__ counters) {
+// batched subgroup check: one thread per slice sum of the two sums; counters[2] += sums outside G1
+__global__ void __launch_bounds__(32) k_sg_check(const G1Xyzz* __restrict__ slices_a, const G1Xyzz* __restrict__ slices_b, int nslices,
+                                                  u32* __restrict__ counters) {
     const int sid = blockIdx.x * blockDim.x + threadIdx.x;
     if (sid >= nslices) return;
-    if (!sg_sum_in_g1(slices[sid])) atomicAdd(counters + 2, 1u);
+    if (!sg_sum_in_g1((blockIdx.y ? slices_b : slices_a)[sid])) atomicAdd(counters + 2, 1u);
 }
 // Horner combine; one block per job so the three sums of a batch run their serial chains concurrently
 struct CombineJobs {
@@ -294,9 +295,10 @@ void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws
     k_msm_window_horner<<<(unsigned)((plan.W + 31) / 32), 32, 0, s>>>(ws.buckets, ws.slices, ws.winsums, plan);
     KZ_COUNT_LAUNCH();
 }
-// batched subgroup check on the slice sums msm_window_sums_stage(.., want_all = true) left in ws.slices
-void launch_sg_check(cudaStream_t s, const MsmPlan& plan, const MsmWorkspace& ws, uint32_t* counters) {
-    k_sg_check<<<(unsigned)((plan.nbits + 31) / 32), 32, 0, s>>>(ws.slices, plan.nbits, counters);
+// batched subgroup check on the slice sums msm_window_sums_stage(.., want_all = true) left in the two workspaces
+// (same plan): the 2 x 128 serial |x|^2 chains run side by side in one launch
+void launch_sg_check(cudaStream_t s, const MsmPlan& plan, const MsmWorkspace& wa, const MsmWorkspace& wb, uint32_t* counters) {
+    k_sg_check<<<dim3((unsigned)((plan.nbits + 31) / 32), 2), 32, 0, s>>>(wa.slices, wb.slices, plan.nbits, counters);
     KZ_COUNT_LAUNCH();
 }
 // Horner combine of up to 3 sums whose window totals are ready; one block per sum
