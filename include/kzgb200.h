@@ -152,6 +152,21 @@ kzgb_ret kzgb_last_stage_ms(kzgb_ctx *ctx, float ms_out[KZGB_N_STAGES]);
 uint64_t kzgb_launch_count(const kzgb_ctx *ctx);
 /* threads the oracle uses (oracle library only; product returns 0) */
 int kzgb_set_threads(kzgb_ctx *ctx, int n_threads);
+/* ---- Blob batch (DESIGN.md "Blob batch"): the caller one step before the hot path, shaped
+ * like c-kzg-4844's verify_blob_kzg_proof_batch(ok, blobs, commitments_bytes, proofs_bytes, n, settings).
+ * blobs: m x 4096 field elements (32 B big-endian, < r), the evaluations of a polynomial of degree < 4096 over the
+ * 4096-th roots of unity in bit-reversed order.  Per blob: z = hash(blob, commitment) mod r, y = p(z) (barycentric),
+ * then the plain batch verify_kzg_proof_batch(C, z, y, proofs).  Hashing convention and domain are this library's
+ * (not EIP-4844 wire compatible).  KZGB_BADARGS: a blob element >= r or a malformed point. */
+kzgb_ret verify_blob_kzg_proof_batch(bool *ok, const uint8_t *blobs, const uint8_t *commitments, const uint8_t *proofs,
+                                     size_t m, kzgb_ctx *ctx);
+/* stage export: z_out, y_out (m x 32 B big-endian) of the blob batch above */
+kzgb_ret kzgb_blob_challenges_evals(uint8_t *z_out, uint8_t *y_out, const uint8_t *blobs, const uint8_t *commitments,
+                                    size_t m, kzgb_ctx *ctx);
+/* stage export: y_out[j] = p_j(z_in[j]) for caller-chosen points (covers z on the evaluation domain) */
+kzgb_ret kzgb_blob_eval(uint8_t *y_out, const uint8_t *blobs, const uint8_t *z_in, size_t m, kzgb_ctx *ctx);
+#define KZGB_BLOB_BYTES 131072
+
 /* Batches (shards) of at least n_min proofs establish subgroup membership of all 2n points through 128 slice
  * sums per MSM of the bucket tables that sum r_i C_i and sum r_i pi_i fill anyway (soundness 2^-127 per point,
  * DESIGN.md "Batched subgroup check"); smaller ones, and any batch in which a slice sum fails, run the

@@ -89,6 +89,9 @@ class KzgLib:
             "kzgb_imad32_peak": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
             "kzgb_last_stage_ms": [vp, C.POINTER(C.c_float * N_STAGES)],
             "kzgb_set_subgroup_batch_min": [vp, sz],
+            "verify_blob_kzg_proof_batch": [C.POINTER(C.c_bool), vp, vp, vp, sz, vp],
+            "kzgb_blob_challenges_evals": [vp, vp, vp, vp, sz, vp],
+            "kzgb_blob_eval": [vp, vp, vp, sz, vp],
         }
         for name, args in sig.items():
             f = getattr(lib, name)
@@ -103,7 +106,7 @@ class KzgLib:
                "kzgb_combine_verify", "kzgb_g1_decompress_batch", "kzgb_fs_challenges", "kzgb_g1_msm",
                "kzgb_g1_msm_times", "kzgb_pairing_check", "kzgb_last_artifacts", "kzgb_synth_instance",
                "kzgb_synth_setup", "kzgb_debug_op", "kzgb_imad_peak", "kzgb_imad32_peak", "kzgb_last_stage_ms", "kzgb_launch_count", "kzgb_set_threads",
-               "kzgb_set_subgroup_batch_min", "kzgb_version"]
+               "kzgb_set_subgroup_batch_min", "verify_blob_kzg_proof_batch", "kzgb_blob_challenges_evals", "kzgb_blob_eval", "kzgb_version"]
 
     def version(self) -> str:
         return self.lib.kzgb_version().decode()
@@ -280,6 +283,28 @@ class Context:
 
     def set_threads(self, n: int) -> int:
         return int(self.lib.kzgb_set_threads(self.h, n))
+
+    def verify_blob_kzg_proof_batch(self, blobs, commitments: bytes, proofs: bytes, m=None):
+        """(rc, ok): m blobs of 4096 x 32 B (bytes or a raw host address), m commitments, m proofs
+        (include/kzgb200.h "Blob batch")."""
+        m = len(commitments) // 48 if m is None else m
+        assert isinstance(blobs, int) or len(blobs) == 131072 * m
+        assert len(proofs) == 48 * m
+        ok = C.c_bool(False)
+        rc = self.lib.verify_blob_kzg_proof_batch(C.byref(ok), _ptr(blobs), _ptr(commitments), _ptr(proofs), m, self.h)
+        return rc, bool(ok.value)
+
+    def blob_challenges_evals(self, blobs: bytes, commitments: bytes):
+        m = len(commitments) // 48
+        z, y = C.create_string_buffer(32 * m), C.create_string_buffer(32 * m)
+        rc = self.lib.kzgb_blob_challenges_evals(z, y, _ptr(blobs), _ptr(commitments), m, self.h)
+        return rc, z.raw, y.raw
+
+    def blob_eval(self, blobs: bytes, z: bytes):
+        m = len(z) // 32
+        y = C.create_string_buffer(32 * m)
+        rc = self.lib.kzgb_blob_eval(y, _ptr(blobs), _ptr(z), m, self.h)
+        return rc, y.raw
 
     def set_subgroup_batch_min(self, n_min: int) -> int:
         """Batches of >= n_min proofs use the batched subgroup check (0: always the per-point check)."""

@@ -77,6 +77,9 @@ struct DeviceSlot {
     uint32_t *d_ci = nullptr, *d_xi = nullptr;
     Fr* cell_coefs = nullptr;
     size_t cell_cap = 0;
+    // blob batch: staging for KZ_BLOB_STAGE blobs and their leaf digests
+    uint8_t* d_blobs = nullptr;
+    uint32_t* blob_leaves = nullptr;
     bool have_ab = false;              // sums[3], sums[4] hold the pairing inputs of the last call
     // pinned mailboxes
     uint8_t* h_digests = nullptr;      // 32 * ceil(n_max/1024)
@@ -207,9 +210,12 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     CK(cudaStreamSynchronize(s.stream));
     CK(cudaGetLastError());
     if (!(st[0] && st[1] && st[2])) return KZGB_BADARGS;
+    // powers of the 8192-th root of unity: cell batch and blob batch
+    CK(dmalloc(s.cell_W, 8192));
+    launch_cell_twiddles(s.stream, s.cell_W);
     if (n1 >= 64 && n2 >= 65) {
         // cell batch setup: 64 G1 monomials through K1 (decompress + subgroup), lines for (G2, [tau^64]G2), twiddles
-        CK(dmalloc(s.cell_g1, 2 * 64)); CK(dmalloc(s.lines_cell, 2)); CK(dmalloc(s.cell_W, 8192));
+        CK(dmalloc(s.cell_g1, 2 * 64)); CK(dmalloc(s.lines_cell, 2));
         CK(cudaMemcpyAsync(s.scratch, g1m, 48 * 64, cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(s.scratch + 4096, g2m, 96, cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(s.scratch + 4096 + 96, g2m + 96 * 64, 96, cudaMemcpyHostToDevice, s.stream));
@@ -217,7 +223,6 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
         CK(cudaMemsetAsync(s.setup_status, 0, 4 * sizeof(int), s.stream));
         launch_decompress_points(s.stream, s.scratch, 64, s.cell_g1, s.k1_tmp, s.status, s.counters);
         launch_g2_setup(s.stream, s.scratch + 4096, s.lines_cell, s.setup_status);
-        launch_cell_twiddles(s.stream, s.cell_W);
         uint32_t cnt[2];
         uint8_t stat[64];
         CK(cudaMemcpyAsync(st, s.setup_status, sizeof st, cudaMemcpyDeviceToHost, s.stream));
@@ -243,7 +248,7 @@ void slot_free(DeviceSlot& s) {
                    s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb, s.recs.head, s.recs.tail,
                    s.recs.head_key, s.recs.tail_key, s.recs.head_flags, s.recsA.head, s.recsA.tail, s.recsA.head_key,
                    s.recsA.tail_key, s.recsA.head_flags, s.recsB.head, s.recsB.tail, s.recsB.head_key, s.recsB.tail_key,
-                   s.recsB.head_flags, s.sg_partial, s.cell_g1, s.lines_cell, s.cell_W, s.d_cells, s.d_ci, s.d_xi, s.cell_coefs};
+                   s.recsB.head_flags, s.sg_partial, s.cell_g1, s.lines_cell, s.cell_W, s.d_cells, s.d_ci, s.d_xi, s.cell_coefs, s.d_blobs, s.blob_leaves};
     for (void* p : dev) if (p) cudaFree(p);
     if (s.h_digests) cudaFreeHost(s.h_digests);
     if (s.h_small) cudaFreeHost(s.h_small);
@@ -662,6 +667,77 @@ kzgb_ret kzgb_combine_verify(kzgb_ctx* ctx, const uint8_t* partials, int n_parti
     DeviceSlot& s = ctx->slots[0];
     if (n_partials != 1) s.have_sums = false;
     return combine(s, partials, n_partials, ok);
+}
+
+// ---- blob batch: z and y of every blob on the device, left in s.dz / s.dy
+#define KZ_BLOB_STAGE 64
+static kzgb_ret blob_zy(DeviceSlot& s, const uint8_t* blobs, const uint8_t* comms, const uint8_t* z_in, size_t m, uint32_t* n_bad) {
+    if (m == 0 || m > s.n_max) return KZGB_BADARGS;
+    CK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
+    if (!s.d_blobs) {
+        CK(dmalloc(s.d_blobs, (size_t)KZ_BLOB_STAGE * KZGB_BLOB_BYTES));
+        CK(dmalloc(s.blob_leaves, (size_t)KZ_BLOB_STAGE * 128 * 8));
+    }
+    uint32_t* bad_dev = (uint32_t*)(s.scratch + 4096);
+    CK(cudaMemsetAsync(bad_dev, 0, sizeof(uint32_t), st));
+    if (comms) CK(cudaMemcpyAsync(s.dC, comms, 48 * m, cudaMemcpyHostToDevice, st));
+    if (z_in) CK(cudaMemcpyAsync(s.dz, z_in, 32 * m, cudaMemcpyHostToDevice, st));
+    for (size_t done = 0; done < m; done += KZ_BLOB_STAGE) {
+        size_t k = m - done < KZ_BLOB_STAGE ? m - done : KZ_BLOB_STAGE;
+        CK(cudaMemcpyAsync(s.d_blobs, blobs + (size_t)KZGB_BLOB_BYTES * done, (size_t)KZGB_BLOB_BYTES * k, cudaMemcpyHostToDevice, st));
+        if (!z_in) launch_blob_challenges(st, s.d_blobs, s.dC + 48 * done, k, s.blob_leaves, s.dz + 32 * done);
+        launch_blob_eval(st, s.cell_W, s.d_blobs, s.dz + 32 * done, k, s.dy + 32 * done, bad_dev);
+    }
+    CK(cudaMemcpyAsync(s.h_small + 24, bad_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    *n_bad = s.h_small[24];
+    return KZGB_OK;
+}
+kzgb_ret kzgb_blob_challenges_evals(uint8_t* z_out, uint8_t* y_out, const uint8_t* blobs, const uint8_t* comms, size_t m,
+                                    kzgb_ctx* ctx) {
+    if (!z_out || !y_out || !blobs || !comms || !ctx || m == 0) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    uint32_t bad = 0;
+    kzgb_ret rc = blob_zy(s, blobs, comms, nullptr, m, &bad);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(z_out, s.dz, 32 * m, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(y_out, s.dy, 32 * m, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    memset(&ctx->art, 0, sizeof ctx->art);
+    ctx->art.n = m;
+    ctx->art.n_bad_scalars = bad;
+    return bad ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret kzgb_blob_eval(uint8_t* y_out, const uint8_t* blobs, const uint8_t* z_in, size_t m, kzgb_ctx* ctx) {
+    if (!y_out || !blobs || !z_in || !ctx || m == 0) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    uint32_t bad = 0;
+    kzgb_ret rc = blob_zy(s, blobs, nullptr, z_in, m, &bad);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(y_out, s.dy, 32 * m, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    return bad ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret verify_blob_kzg_proof_batch(bool* ok, const uint8_t* blobs, const uint8_t* comms, const uint8_t* proofs, size_t m,
+                                     kzgb_ctx* ctx) {
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!ctx || !blobs || !comms || !proofs || m == 0) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    uint32_t bad = 0;
+    kzgb_ret rc = blob_zy(s, blobs, comms, nullptr, m, &bad);
+    if (rc) return rc;
+    if (bad) {
+        memset(&ctx->art, 0, sizeof ctx->art);
+        ctx->art.n = m;
+        ctx->art.n_bad_scalars = bad;
+        return KZGB_BADARGS;
+    }
+    CK(cudaMemcpyAsync(s.dpi, proofs, 48 * m, cudaMemcpyHostToDevice, s.stream));
+    // the plain batch on device-resident (C, z, y, pi); one proof is still a batch of one (challenge r_0 from the root)
+    return verify_common(ok, s.dC, s.dz, s.dy, s.dpi, m, ctx, true, false);
 }
 
 kzgb_ret kzgb_g1_decompress_batch(uint8_t* affine_out, uint8_t* status_out, const uint8_t* in, size_t m, kzgb_ctx* ctx) {

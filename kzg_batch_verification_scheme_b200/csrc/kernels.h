@@ -95,6 +95,9 @@ void launch_pairing_debug(cudaStream_t s, int op, const G2Lines* lines, const ui
 
 // ---- k_cells.cu (cell batch, BASELINE.json config[4])
 void launch_cell_twiddles(cudaStream_t s, Fr* W /*8192*/);
+// ---- k_blob.cu (blob batch): leaves = 128 x 8 words per blob of scratch; z_out / y_out 32 B big-endian per blob
+void launch_blob_challenges(cudaStream_t s, const uint8_t* blobs, const uint8_t* comms, size_t m, uint32_t* leaves, uint8_t* z_out);
+void launch_blob_eval(cudaStream_t s, const Fr* W, const uint8_t* blobs, const uint8_t* z_in, size_t m, uint8_t* y_out, uint32_t* counter);
 void launch_cell_leaf_hash(cudaStream_t s, const uint32_t* ci, const uint32_t* xi, const uint8_t* cells, const uint8_t* proofs, size_t m,
                            uint32_t* leaves);
 void launch_cell_scalars(cudaStream_t s, const Fr* W, const uint32_t* root_words, const uint32_t* ci, const uint32_t* xi, uint32_t nc,

@@ -9,7 +9,7 @@
 
 #include <mutex>
 
-#include "cells.hpp"
+#include "blobs.hpp"
 #include "../include/kzgb200.h"
 
 using namespace orc;
@@ -177,6 +177,40 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     int rc = verify_cells(v, c->art, c->cells, comms, nc, ci, xi, cells, proofs, m, c->threads);
     *ok = v;
     return rc ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret kzgb_blob_challenges_evals(uint8_t* z_out, uint8_t* y_out, const uint8_t* blobs, const uint8_t* comms, size_t m, kzgb_ctx* c) {
+    if (!z_out || !y_out || !blobs || !comms || !c || m == 0) return KZGB_BADARGS;
+    unsigned bad = blob_challenges_evals(z_out, y_out, blobs, comms, m, c->threads);
+    c->art = Artifacts();
+    c->art.n = m;
+    c->art.n_bad_scalars = bad;
+    return bad ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret kzgb_blob_eval(uint8_t* y_out, const uint8_t* blobs, const uint8_t* z_in, size_t m, kzgb_ctx* c) {
+    if (!y_out || !blobs || !z_in || !c || m == 0) return KZGB_BADARGS;
+    unsigned bad = 0;
+    for (size_t j = 0; j < m; ++j) {
+        Fr z, y;
+        if (!fr_from_be(z, z_in + 32 * j)) { ++bad; continue; }
+        bad += blob_eval(y, blobs + BLOB_BYTES * j, z);
+        y.to_bytes_be(y_out + 32 * j);
+    }
+    return bad ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret verify_blob_kzg_proof_batch(bool* ok, const uint8_t* blobs, const uint8_t* comms, const uint8_t* proofs, size_t m, kzgb_ctx* c) {
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!c || !blobs || !comms || !proofs || m == 0) return KZGB_BADARGS;
+    std::vector<u8> z(32 * m), y(32 * m);
+    kzgb_ret rc = kzgb_blob_challenges_evals(z.data(), y.data(), blobs, comms, m, c);
+    if (rc) return rc;
+    return verify_impl(ok, comms, z.data(), y.data(), proofs, m, c, false);
+}
+// oracle-only: synthetic blobs with their commitments and proofs (known test tau)
+kzgb_ret kzgb_oracle_synth_blobs(uint64_t seed, size_t m, uint8_t* blobs, uint8_t* comms, uint8_t* proofs, int threads) {
+    if (!blobs || !comms || !proofs) return KZGB_BADARGS;
+    synth_blobs(seed, m, blobs, comms, proofs, threads > 0 ? threads : (int)std::thread::hardware_concurrency());
+    return KZGB_OK;
 }
 // oracle-only: synthetic cells (n_blobs * cells_per_blob openings)
 kzgb_ret kzgb_oracle_synth_cells(uint64_t seed, size_t n_blobs, size_t cells_per_blob, size_t ncoef, uint8_t* comms, uint32_t* ci,

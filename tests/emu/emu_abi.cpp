@@ -15,6 +15,7 @@
 #include "../../kzg_batch_verification_scheme_b200/csrc/sha256.cuh"
 #include "../../kzg_batch_verification_scheme_b200/csrc/cells.cuh"
 #include "../../kzg_batch_verification_scheme_b200/csrc/fpd.cuh"
+#include "../../kzg_batch_verification_scheme_b200/csrc/blob.cuh"
 
 struct kzgb_ctx {
     G2Lines lines[2];
@@ -554,5 +555,63 @@ kzgb_ret kzgb_imad32_peak(kzgb_ctx*, double*, double*) { return KZGB_ERROR; }
 kzgb_ret kzgb_last_stage_ms(kzgb_ctx*, float*) { return KZGB_ERROR; }
 uint64_t kzgb_launch_count(const kzgb_ctx*) { return 0; }
 int kzgb_set_threads(kzgb_ctx*, int) { return 0; }
+// blob batch through the device bodies (blob.cuh): lanes and blobs become loops
+static const std::vector<Fr>& emu_twiddles() {
+    static const std::vector<Fr> W = [] {
+        std::vector<Fr> w(KZ_N_EXT);
+        Fr base = fr_const(FR_OMEGA_INV), acc = fr_const(FR_ONE);
+        for (u32 t = 0; t < KZ_N_EXT; ++t) { w[t] = acc; acc = fr_mul(acc, base); }
+        return w;
+    }();
+    return W;
+}
+static u32 emu_blob_zy(u8* z_out, u8* y_out, const u8* blobs, const u8* comms, const u8* z_in, size_t m) {
+    const std::vector<Fr>& W = emu_twiddles();
+    u32 bad = 0;
+    for (size_t j = 0; j < m; ++j) {
+        const u8* blob = blobs + (size_t)KZ_BLOB_LEN * 32 * j;
+        Fr zr;
+        if (z_in) fr_raw_from_be(zr, z_in + 32 * j);
+        else {
+            std::vector<u32> leaves(8 * KZ_BLOB_LEAVES), piece(256), cw(12);
+            for (int k = 0; k < KZ_BLOB_LEAVES; ++k) { memcpy(piece.data(), blob + 1024 * k, 1024); blob_leaf_words(&leaves[8 * k], piece.data()); }
+            memcpy(cw.data(), comms + 48 * j, 48);
+            zr = blob_z(cw.data(), leaves.data());
+        }
+        const bool z_ok = fr_raw_is_canonical(zr);
+        bad += !z_ok;
+        if (z_out) fr_raw_to_be(z_out + 32 * j, zr);
+        Fr z = fr_to_mont(z_ok ? zr : fr_zero()), total = fr_zero(), hit = fr_zero();
+        bool has_hit = false;
+        for (u32 lane = 0; lane < KZ_BLOB_THREADS; ++lane) {
+            BlobLane L = blob_eval_lane(W.data(), blob, z, lane);
+            total = fr_add(total, L.sum);
+            if (L.has_hit) { has_hit = true; hit = L.hit; }
+            bad += L.bad;
+        }
+        fr_raw_to_be(y_out + 32 * j, fr_from_mont(has_hit ? hit : blob_eval_finish(z, total)));
+    }
+    return bad;
+}
+kzgb_ret kzgb_blob_challenges_evals(uint8_t* z_out, uint8_t* y_out, const uint8_t* blobs, const uint8_t* comms, size_t m, kzgb_ctx* c) {
+    if (!z_out || !y_out || !blobs || !comms || !c || m == 0) return KZGB_BADARGS;
+    u32 bad = emu_blob_zy(z_out, y_out, blobs, comms, nullptr, m);
+    memset(&c->art, 0, sizeof c->art);
+    c->art.n = m; c->art.n_bad_scalars = bad;
+    return bad ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret kzgb_blob_eval(uint8_t* y_out, const uint8_t* blobs, const uint8_t* z_in, size_t m, kzgb_ctx* c) {
+    if (!y_out || !blobs || !z_in || !c || m == 0) return KZGB_BADARGS;
+    return emu_blob_zy(nullptr, y_out, blobs, nullptr, z_in, m) ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret verify_blob_kzg_proof_batch(bool* ok, const uint8_t* blobs, const uint8_t* comms, const uint8_t* proofs, size_t m, kzgb_ctx* c) {
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!c || !blobs || !comms || !proofs || m == 0) return KZGB_BADARGS;
+    std::vector<u8> z(32 * m), y(32 * m);
+    kzgb_ret rc = kzgb_blob_challenges_evals(z.data(), y.data(), blobs, comms, m, c);
+    if (rc) return rc;
+    return emu_verify(ok, comms, z.data(), y.data(), proofs, m, c, false);
+}
 kzgb_ret kzgb_set_subgroup_batch_min(kzgb_ctx* c, size_t n_min) { if (!c) return KZGB_BADARGS; c->sg_min = n_min; return KZGB_OK; }
 }

@@ -5,6 +5,8 @@ Every check drives the library under test and the CPU oracle through the same C 
 against the CPU oracle: the accept/reject decision, every canonical affine MSM output and every
 decompressed point").
 """
+import ctypes as C
+import hashlib
 import random
 
 from oracle.pymodel import bls12_381 as b
@@ -370,3 +372,74 @@ def check_random_differential(gpu_ctx, oracle_ctx, sizes=(1, 2, 3, 17, 64, 255, 
             for key in ("S1", "S2", "S3", "A", "B", "sum_ry", "root"):
                 assert a1[key] == a2[key], (trial, kind, key)
     assert len(outcomes) >= 2, outcomes          # at least two of accepted / rejected / malformed were exercised
+
+
+# ---- blob batch (include/kzgb200.h "Blob batch")
+BLOB_LEN = 4096
+OMEGA_4096 = pow(7, (R - 1) // 4096, R)
+
+
+def _brp12(i):
+    return int(format(i, "012b")[::-1], 2)
+
+
+def blob_domain_point(i):
+    return pow(OMEGA_4096, _brp12(i), R)
+
+
+def poly_eval(coeffs, x):
+    """coeffs: {degree: coefficient}"""
+    return sum(a * pow(x, d, R) for d, a in coeffs.items()) % R
+
+
+def python_blob_challenge(blob, comm):
+    leaves = b"".join(hashlib.sha256(b"KZGB200/bleaf_v1" + blob[1024 * j:1024 * j + 1024]).digest() for j in range(128))
+    return int.from_bytes(hashlib.sha256(b"KZGB200/blobz_v1" + comm + leaves).digest(), "big") % R
+
+
+def python_blob(rnd):
+    """One blob from a sparse polynomial of degree 4095, with commitment and proof from the known test tau."""
+    coeffs = {d: rnd.randrange(R) for d in (0, 1, 2, 77, 2048, 4095)}
+    blob = b"".join(poly_eval(coeffs, blob_domain_point(i)).to_bytes(32, "big") for i in range(BLOB_LEN))
+    pt = poly_eval(coeffs, k.TAU)
+    comm = b.g1_compress(b.g1_mul(pt, b.G1))
+    z = python_blob_challenge(blob, comm)
+    y = poly_eval(coeffs, z)
+    proof = b.g1_compress(b.g1_mul((pt - y) * pow(k.TAU - z, R - 2, R) % R, b.G1))
+    return blob, comm, proof, coeffs
+
+
+def synth_blobs(oracle_lib, seed, m):
+    blobs, comms, proofs = C.create_string_buffer(131072 * m), C.create_string_buffer(48 * m), C.create_string_buffer(48 * m)
+    f = oracle_lib.lib.kzgb_oracle_synth_blobs
+    f.argtypes, f.restype = [C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int], C.c_int
+    assert f(seed, m, blobs, comms, proofs, 0) == 0
+    return blobs.raw, comms.raw, proofs.raw
+
+
+def check_blob_batch(ctx, oracle, inst):
+    blobs, comms, proofs = inst
+    m = len(comms) // 48
+    rc1, z1, y1 = ctx.blob_challenges_evals(blobs, comms)
+    rc2, z2, y2 = oracle.blob_challenges_evals(blobs, comms)
+    assert rc1 == rc2 == 0 and z1 == z2 and y1 == y2
+    assert ctx.verify_blob_kzg_proof_batch(blobs, comms, proofs) == oracle.verify_blob_kzg_proof_batch(blobs, comms, proofs) == (0, True)
+    a1, a2 = ctx.last_artifacts(), oracle.last_artifacts()
+    assert a1["A"] == a2["A"] and a1["B"] == a2["B"] and a1["root"] == a2["root"]
+    # the blob path ends in the plain batch on (C, z, y, proofs)
+    assert ctx.verify_kzg_proof_batch(comms, z1, y1, proofs, m) == (0, True)
+    bad = bytearray(blobs); bad[131072 * (m - 1) + 32 * 1000 + 31] ^= 1            # one evaluation changed
+    assert ctx.verify_blob_kzg_proof_batch(bytes(bad), comms, proofs) == oracle.verify_blob_kzg_proof_batch(bytes(bad), comms, proofs) == (0, False)
+    if m >= 2:
+        pr2 = proofs[48:96] + proofs[:48] + proofs[96:]
+        assert ctx.verify_blob_kzg_proof_batch(blobs, comms, pr2) == oracle.verify_blob_kzg_proof_batch(blobs, comms, pr2) == (0, False)
+    bad = bytearray(blobs); bad[32 * 5:32 * 6] = (R).to_bytes(32, "big")                # element == r
+    assert ctx.verify_blob_kzg_proof_batch(bytes(bad), comms, proofs) == oracle.verify_blob_kzg_proof_batch(bytes(bad), comms, proofs) == (1, False)
+    assert ctx.verify_blob_kzg_proof_batch(blobs, b.g1_compress((0, 2)) + comms[48:], proofs) == (1, False)   # off-subgroup commitment
+    # caller-chosen evaluation points, including points of the domain
+    pts = [blob_domain_point(3), blob_domain_point(4095), 0, 1, R - 1][:max(1, min(5, m))]
+    zin = b"".join(v.to_bytes(32, "big") for v in pts)
+    r1, r2 = ctx.blob_eval(blobs[:131072 * len(pts)], zin), oracle.blob_eval(blobs[:131072 * len(pts)], zin)
+    assert r1 == r2 and r1[0] == 0
+    assert r1[1][:32] == blobs[32 * 3:32 * 4]
+

@@ -33,6 +33,10 @@ def test_emu_subgroup_batch(emu_ctx, oracle_ctx):
     ps.check_subgroup_batch(emu_ctx, oracle_ctx, n=6)
 
 
+def test_emu_blob_batch(emu_ctx, oracle_ctx, oracle_lib):
+    ps.check_blob_batch(emu_ctx, oracle_ctx, ps.synth_blobs(oracle_lib, 0x4B5A4742, 2))
+
+
 def test_emu_sha_single_block(emu_ctx, oracle_ctx):
     import random
     rnd = random.Random(1)

@@ -29,6 +29,18 @@ def test_gpu_subgroup_batch_default_threshold(gpu_ctx, oracle_ctx):
     ps.check_subgroup_batch(gpu_ctx, oracle_ctx, n=1 << 15, min_batch=32768, ells=(3, 11))
 
 
+def test_gpu_blob_batch(gpu_ctx, oracle_ctx, oracle_lib):
+    """Blob-level caller: z, y bit-exact vs the oracle, verdicts, malformed blobs; 70 blobs
+    cross the 64-blob staging buffer."""
+    ps.check_blob_batch(gpu_ctx, oracle_ctx, ps.synth_blobs(oracle_lib, 0x4B5A4743, 70))
+    import random
+    blob, comm, proof, coeffs = ps.python_blob(random.Random(12))          # against direct polynomial evaluation
+    rc, zs, ys = gpu_ctx.blob_challenges_evals(blob, comm)
+    z = ps.python_blob_challenge(blob, comm)
+    assert rc == 0 and zs == z.to_bytes(32, "big") and ys == ps.poly_eval(coeffs, z).to_bytes(32, "big")
+    assert gpu_ctx.verify_blob_kzg_proof_batch(blob, comm, proof) == (0, True)
+
+
 def test_gpu_fpd_ops(gpu_ctx, oracle_ctx):
     ps.check_fpd_ops(gpu_ctx, oracle_ctx)
 
