@@ -670,7 +670,7 @@ kzgb_ret kzgb_combine_verify(kzgb_ctx* ctx, const uint8_t* partials, int n_parti
 }
 
 // ---- blob batch: z and y of every blob on the device, left in s.dz / s.dy
-#define KZ_BLOB_STAGE 64
+#define KZ_BLOB_STAGE 256
 static kzgb_ret blob_zy(DeviceSlot& s, const uint8_t* blobs, const uint8_t* comms, const uint8_t* z_in, size_t m, uint32_t* n_bad) {
     if (m == 0 || m > s.n_max) return KZGB_BADARGS;
     CK(cudaSetDevice(s.device));
