@@ -66,6 +66,33 @@ KZ_HD Fp fp_sqr(const Fp& a) {
     return r;
 #endif
 }
+// Lazy variants for pure product chains (square root): operands and results in [0, 2p).  R = 2^384 > 4p, so a
+// Montgomery product of operands below 2p is below 1.5p and the conditional subtraction can wait until the end
+// of the chain (tools/gen_mont.py --selftest covers operands up to 2p - 1).  fp_reduce_once: [0, 2p) -> [0, p).
+KZ_HD Fp fp_mul_lazy(const Fp& a, const Fp& b) {
+#if defined(KZGB_EMU)
+    return fp_mul(a, b);
+#else
+    Fp r;
+    fp_mont_mul_ptx(r.v, a.v, b.v);
+    return r;
+#endif
+}
+KZ_HD Fp fp_sqr_lazy(const Fp& a) {
+#if defined(KZGB_EMU)
+    return fp_mul(a, a);
+#else
+    Fp r;
+    fp_mont_sqr_ptx(r.v, a.v);
+    return r;
+#endif
+}
+KZ_HD Fp fp_reduce_once(Fp r) {
+#if !defined(KZGB_EMU)
+    fp_reduce_ptx(r.v);
+#endif
+    return r;
+}
 KZ_HD Fp fp_add(const Fp& a, const Fp& b) {
     Fp r;
 #if defined(KZGB_EMU)

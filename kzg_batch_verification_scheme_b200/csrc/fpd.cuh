@@ -114,16 +114,6 @@ KZ_HD FpD fpd_sqr(const FpD& a) {
     return fpd_redc(L, H);
 }
 
-// [0, 2p) -> [0, p) on the integer limbs
-KZ_HD Fp fp_reduce_once(Fp r) {
-#if defined(KZGB_EMU)
-    return fp_add(r, fp_zero());
-#else
-    fp_reduce_ptx(r.v);
-    return r;
-#endif
-}
-
 // ---- conversions (values stay in Montgomery form; only the limb width changes)
 KZ_HD FpD fpd_from_fp(const Fp& a) {
     FpD r;
@@ -145,5 +135,9 @@ KZ_HD Fp fpd_to_fp(const FpD& a) {
         r.v[3 * k + 1] = (u32)(e >> 32) | ((u32)o << 16);
         r.v[3 * k + 2] = (u32)(o >> 16);
     }
+#if defined(KZGB_EMU)
+    return fp_add(r, fp_zero());          // host: one conditional subtraction through the portable adder
+#else
     return fp_reduce_once(r);
+#endif
 }

@@ -159,18 +159,19 @@ KZ_HD bool aff_from_be96(G1Aff& p, const u8* in) { return fp_from_be(p.x, in) & 
 // 376 squarings + 78 table multiplications + 8 products to build the odd-power table (a, a^3, .., a^15).
 // The schedule is a compile-time constant (same for every thread), so the table lives in local memory
 // with uniform, coalesced indexing and all branches are warp-uniform.
+// The chain is products only, so it runs on lazy values in [0, 2p) (field.cuh) with one reduction at the end.
 KZ_HD Fp fp_sqrt_candidate(const Fp& a) {
     Fp tab[8];
     tab[0] = a;
-    Fp a2 = fp_sqr(a);
-    for (int i = 1; i < 8; ++i) tab[i] = fp_mul(tab[i - 1], a2);
+    Fp a2 = fp_sqr_lazy(a);
+    for (int i = 1; i < 8; ++i) tab[i] = fp_mul_lazy(tab[i - 1], a2);
     Fp r = tab[SQRT_SCHED[1]];                       // first step: leading window, no squarings
     for (int s = 1; s < SQRT_SCHED_STEPS; ++s) {
         int nsq = SQRT_SCHED[2 * s], idx = SQRT_SCHED[2 * s + 1];
-        for (int k = 0; k < nsq; ++k) r = fp_sqr(r);
-        if (idx != 0xFF) r = fp_mul(r, tab[idx]);
+        for (int k = 0; k < nsq; ++k) r = fp_sqr_lazy(r);
+        if (idx != 0xFF) r = fp_mul_lazy(r, tab[idx]);
     }
-    return r;
+    return fp_reduce_once(r);
 }
 
 // ------------------------------------------------------------------ subgroup check
