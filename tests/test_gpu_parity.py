@@ -26,7 +26,7 @@ def test_gpu_subgroup_batch_small(gpu_ctx, oracle_ctx):
 
 def test_gpu_subgroup_batch_default_threshold(gpu_ctx, oracle_ctx):
     """n = 2^15 proofs: the batched check is the default path; a single order-3 / order-11 component is found."""
-    ps.check_subgroup_batch(gpu_ctx, oracle_ctx, n=1 << 15, min_batch=32768, ells=(3, 11))
+    ps.check_subgroup_batch(gpu_ctx, oracle_ctx, n=1 << 15, min_batch=16384, ells=(3, 11))
 
 
 def test_gpu_blob_batch(gpu_ctx, oracle_ctx, oracle_lib):
