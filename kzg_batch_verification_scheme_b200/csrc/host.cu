@@ -35,11 +35,8 @@ struct DeviceSlot {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;    // high-priority side stream: hashes, challenges and sorts overlap K1
     cudaStream_t stream3 = nullptr, stream4 = nullptr;   // the three sums accumulate/reduce concurrently
-    cudaStream_t stream6 = nullptr, stream7 = nullptr;   // normal-priority twins of stream3 / stream5 (small batches)
-    size_t pri_min = ~(size_t)0;       // batch size from which S1 and S3 run at high priority (env KZGB_MSM_PRI_MIN);
-                                       // measured slower at every size (2^20: 51.9 vs 50.2 ms), so off by default
-    cudaStream_t stream5 = nullptr;    // high priority like stream3: S1 and S3 finish first so that their bucket slices
-                                       // (batched subgroup check) overlap the longer GLV sum on stream4
+    cudaStream_t stream5 = nullptr;    // S1 (stream3: S3, stream4: S2'); all at normal priority -- running S1 and S3 at high
+                                       // priority so that the subgroup chains start earlier was slower at every batch size
     // staged inputs (host-pointer API)
     uint8_t *dC = nullptr, *dz = nullptr, *dy = nullptr, *dpi = nullptr;
     Fp* pts = nullptr;                 // 3*n_max + 2 affine points: C | pi | G | phi(pi) | phi(G)
@@ -123,12 +120,9 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
         int lo_pri = 0, hi_pri = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
         CK(cudaStreamCreateWithPriority(&s.stream2, cudaStreamNonBlocking, hi_pri));
-        CK(cudaStreamCreateWithPriority(&s.stream3, cudaStreamNonBlocking, hi_pri));
+        CK(cudaStreamCreateWithFlags(&s.stream3, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&s.stream4, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithPriority(&s.stream5, cudaStreamNonBlocking, hi_pri));
-        CK(cudaStreamCreateWithFlags(&s.stream6, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&s.stream7, cudaStreamNonBlocking));
-        if (const char* e = getenv("KZGB_MSM_PRI_MIN")) s.pri_min = (size_t)strtoull(e, nullptr, 10);
+        CK(cudaStreamCreateWithFlags(&s.stream5, cudaStreamNonBlocking));
     }
     for (auto& e : s.ev) CK(cudaEventCreate(&e));
     CK(dmalloc(s.dC, 48 * (n_max + 1))); CK(dmalloc(s.dz, 32 * (n_max + 1))); CK(dmalloc(s.dy, 32 * (n_max + 1))); CK(dmalloc(s.dpi, 48 * (n_max + 1)));
@@ -258,8 +252,6 @@ void slot_free(DeviceSlot& s) {
     if (s.stream3) cudaStreamDestroy(s.stream3);
     if (s.stream4) cudaStreamDestroy(s.stream4);
     if (s.stream5) cudaStreamDestroy(s.stream5);
-    if (s.stream6) cudaStreamDestroy(s.stream6);
-    if (s.stream7) cudaStreamDestroy(s.stream7);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -396,31 +388,21 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     wz.winsums = s.winsums + 2 * KZ_MSM_MAX_WINDOWS;
     wr2.sg_work = s.sg_partial + s.sg_cap; wr2.slices = wr2.sg_work + s.sg_cap - 256;
     wz.sg_work = s.sg_partial + 2 * s.sg_cap; wz.slices = wz.sg_work + s.sg_cap - 256;
-    // Longest chain (S2', twice the points) first, all three sums at normal priority.  The alternative -- S1 and S3
-    // at high priority so that the batched subgroup check starts early and overlaps S2' -- is kept behind
-    // KZGB_MSM_PRI_MIN; it was slower at every batch size.
-    const bool pri = n >= s.pri_min;
-    cudaStream_t sS3 = pri ? s.stream3 : s.stream6, sS1 = pri ? s.stream5 : s.stream7;
+    // Longest chain (S2', twice the points) first, all three sums at normal priority.
+    cudaStream_t sS3 = s.stream3, sS1 = s.stream5;
     CK(cudaEventRecord(s.ev[11], st));
     CK(cudaStreamWaitEvent(sS3, s.ev[11], 0));
     CK(cudaStreamWaitEvent(s.stream4, s.ev[11], 0));
     CK(cudaStreamWaitEvent(sS1, s.ev[11], 0));
-    if (!pri) {
-        msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);
-        msm_window_sums_stage(s.stream4, s.planZ, wz, false);
-        CK(cudaEventRecord(s.ev[13], s.stream4));
-    }
+    msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);    // S2' over pi_i, G and their phi images
+    msm_window_sums_stage(s.stream4, s.planZ, wz, false);
+    CK(cudaEventRecord(s.ev[13], s.stream4));
     msm_accumulate_stage(sS3, s.planR, s.pts + 2 * n, n, wr2);                   // S3 over pi_i
     msm_window_sums_stage(sS3, s.planR, wr2, s.sg_batch);
     CK(cudaEventRecord(s.ev[12], sS3));
     msm_accumulate_stage(sS1, s.planR, s.pts, n, wr);                            // S1 over C_i
     msm_window_sums_stage(sS1, s.planR, wr, s.sg_batch);
     CK(cudaEventRecord(s.ev[16], sS1));
-    if (pri) {
-        msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);   // S2' over pi_i, G and their phi images
-        msm_window_sums_stage(s.stream4, s.planZ, wz, false);
-        CK(cudaEventRecord(s.ev[13], s.stream4));
-    }
     if (s.sg_batch) {
         // batched subgroup check: 128 slice sums of the S3 buckets (all pi_i) and of the S1 buckets (all C_i)
         CK(cudaStreamWaitEvent(sS3, s.ev[16], 0));                               // slice sums of S1 are complete
