@@ -862,15 +862,26 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     CK(cudaMemcpyAsync(s.d_ci, ci, 4 * m, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s.d_xi, xi, 4 * m, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s.d_cells, cells, 2048 * m, cudaMemcpyHostToDevice, st));
-    // Fiat-Shamir: cell leaves -> chunk digests -> host root (binds the commitments as well)
-    launch_cell_leaf_hash(st, s.d_ci, s.d_xi, s.d_cells, s.dpi, m, s.leaves);
-    launch_chunk_hash(st, s.leaves, m, s.digests);
+    // Fiat-Shamir on the side stream: cell leaves -> chunk digests -> host root (binds the commitments as well)
+    CK(cudaEventRecord(s.ev[1], st));
+    CK(cudaStreamWaitEvent(s.stream2, s.ev[1], 0));
+    launch_cell_leaf_hash(s.stream2, s.d_ci, s.d_xi, s.d_cells, s.dpi, m, s.leaves);
+    launch_chunk_hash(s.stream2, s.leaves, m, s.digests);
     size_t nch = (m + KZGB_CHUNK - 1) / KZGB_CHUNK;
-    CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(s.ev[2], st));
-    // K1 on proofs and commitments; the 64 setup monomials follow them in the point array
-    launch_decompress_points(st, s.dpi, m, s.pts, s.k1_tmp, s.status, s.counters);
-    launch_decompress_points(st, s.dC, nc, s.pts + 2 * m, s.k1_tmp + 3 * m, s.status + m, s.counters);
+    CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, s.stream2));
+    CK(cudaEventRecord(s.ev[2], s.stream2));
+    // K1 on proofs and commitments; the 64 setup monomials follow them in the point array.  Large batches prove
+    // subgroup membership of the proofs on the bucket slices of the B-side sum (sum r_k pi_k), like the plain batch;
+    // the few commitments get the per-point check on their own stream (three serial chains of pure latency)
+    const bool sg = s.sg_min && m >= s.sg_min && m >= 2;
+    s.sg_batch = sg;
+    s.cur_n = 0;
+    CK(cudaStreamWaitEvent(s.stream4, s.ev[1], 0));
+    launch_decompress_points(s.stream4, s.dC, nc, s.pts + 2 * m, s.k1_tmp + 3 * m, s.status + m, s.counters);
+    CK(cudaEventRecord(s.ev[13], s.stream4));
+    if (sg) launch_decompress_sqrt_points(st, s.dpi, m, s.pts, s.status, s.counters);
+    else launch_decompress_points(st, s.dpi, m, s.pts, s.k1_tmp, s.status, s.counters);
+    CK(cudaStreamWaitEvent(st, s.ev[13], 0));
     CK(cudaMemcpyAsync(s.pts + 2 * (m + nc), s.cell_g1, 2 * 64 * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     CK(cudaEventSynchronize(s.ev[2]));
     std::vector<uint8_t> dig(32 * nch);
@@ -884,39 +895,66 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     launch_cell_scalars(st, s.cell_W, s.root_words, s.d_ci, s.d_xi, (uint32_t)nc, s.d_cells, m, s.cell_coefs, s.r, s.rz, s.counters);
     launch_cell_reductions(st, s.cell_coefs, s.d_ci, s.r, m, (uint32_t)nc, s.rz + 8 * m, s.rz + 8 * (m + nc));
     CK(cudaMemsetAsync(s.sum_ry, 0, 8 * sizeof(uint32_t), st));
-    // A-side: sum (r_k h^64) pi_k + sum w_i C_i - sum S_j [tau^j]G1, 255-bit scalars, GLV-split
+    CK(cudaEventRecord(s.ev[11], st));
+    // B-side: sum r_k pi_k, 128-bit scalars, on a side stream beside the A-side sum
+    MsmPlan planB = msm_make_plan(m, 128);
+    MsmWorkspace wsB = make_ws(s, s.sortR, s.bucketsA);
     {
-        size_t mm = 2 * M;
-        MsmPlan plan = msm_make_plan(mm, 128);
-        if ((size_t)plan.W * mm > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || sg_work_entries(plan) + 256 > s.sg_cap)
+        if ((size_t)planB.W * m > s.sortR.capacity || planB.total_buckets > s.max_bucketsR + 512 || sg_work_entries(planB) + 256 > s.sg_cap)
             return KZGB_BADARGS;
-        MsmWorkspace ws = make_ws(s, s.sortZ, s.bucketsC);
-        launch_glv_split(st, s.rz, M, s.zs);
-        launch_endo_points(st, s.pts, M, s.pts + 2 * M);
-        msm_sort_stage(st, plan, s.zs, 4, mm, ws);
-        save_ws(s.sortZ, ws);
-        msm_accumulate_stage(st, plan, s.pts, mm, ws);
-        msm_reduce_stage(st, plan, ws, s.sums + 0);
+        cudaStream_t sb = s.stream3;
+        CK(cudaStreamWaitEvent(sb, s.ev[11], 0));
+        wsB.recs = s.recsA;
+        wsB.winsums = s.winsums + KZ_MSM_MAX_WINDOWS;
+        wsB.sg_work = s.sg_partial + s.sg_cap; wsB.slices = wsB.sg_work + s.sg_cap - 256;
+        msm_sort_stage(sb, planB, s.r, 4, m, wsB);
+        save_ws(s.sortR, wsB);
+        msm_accumulate_stage(sb, planB, s.pts, m, wsB);
+        msm_window_sums_stage(sb, planB, wsB, sg);
+        CK(cudaEventRecord(s.ev[12], sb));
+        if (sg) {
+            launch_sg_check(sb, planB, wsB, wsB, s.counters, 1);
+            CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sb));
+            CK(cudaEventRecord(s.ev[9], sb));
+        }
     }
-    // B-side: sum r_k pi_k, 128-bit scalars
+    // A-side: sum (r_k h^64) pi_k + sum w_i C_i - sum S_j [tau^j]G1, 255-bit scalars, GLV-split
+    size_t mm = 2 * M;
+    MsmPlan planA = msm_make_plan(mm, 128);
+    if ((size_t)planA.W * mm > s.sortZ.capacity || planA.total_buckets > s.max_bucketsZ + 512 || sg_work_entries(planA) + 256 > s.sg_cap)
+        return KZGB_BADARGS;
+    MsmWorkspace wsA = make_ws(s, s.sortZ, s.bucketsC);
+    launch_glv_split(st, s.rz, M, s.zs);
+    launch_endo_points(st, s.pts, M, s.pts + 2 * M);
+    msm_sort_stage(st, planA, s.zs, 4, mm, wsA);
+    save_ws(s.sortZ, wsA);
+    msm_accumulate_stage(st, planA, s.pts, mm, wsA);
+    msm_window_sums_stage(st, planA, wsA, false);
+    CK(cudaStreamWaitEvent(st, s.ev[12], 0));
     {
-        MsmPlan plan = msm_make_plan(m, 128);
-        if ((size_t)plan.W * m > s.sortR.capacity || plan.total_buckets > s.max_bucketsR + 512 || sg_work_entries(plan) + 256 > s.sg_cap)
-            return KZGB_BADARGS;
-        MsmWorkspace ws = make_ws(s, s.sortR, s.bucketsA);
-        ws.recs = s.recsA;
-        msm_sort_stage(st, plan, s.r, 4, m, ws);
-        save_ws(s.sortR, ws);
-        msm_accumulate_stage(st, plan, s.pts, m, ws);
-        msm_reduce_stage(st, plan, ws, s.sums + 2);
+        const MsmPlan* plans[2] = {&planA, &planB};
+        MsmWorkspace* wss[2] = {&wsA, &wsB};
+        G1Jac* outs[2] = {s.sums + 0, s.sums + 2};
+        msm_combine_stage(st, plans, wss, outs, 2);
     }
     launch_set_ab(st, s.sums + 0, s.sums + 2, s.sums + 3);
     launch_pairing(st, s.lines_cell, s.sums + 3, s.result_dev);
     CK(cudaMemcpyAsync(s.h_small + 16, s.result_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(s.h_small, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (!sg) CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[8], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    if (sg) {
+        // verdict of the batched check (it ran beside the pairing); on failure the per-point chains name the proofs
+        CK(cudaEventSynchronize(s.ev[9]));
+        if (s.h_small[2]) {
+            launch_subgroup_points(st, s.pts, m, s.k1_tmp, s.status, s.counters);
+            CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+        }
+        s.sg_batch = false;
+    }
     art.n_bad_points = s.h_small[0];
     art.n_bad_scalars = s.h_small[1];
     art.stage_ms[9] = ev_ms(s.ev[0], s.ev[8]);

@@ -260,10 +260,23 @@ void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars
     KZ_COUNT_LAUNCH();
 }
 u32 msm_chunk_len(size_t N) { return N >= (1u << 21) ? 32u : N >= (1u << 20) ? 16u : N >= (1u << 18) ? 8u : 4u; }
+// Chunk length of one sum.  Pass 2 adds the partial records of a bucket one after the other, load / L general
+// additions for the heaviest buckets (the narrow top window), while pass 1 runs L mixed additions per thread; for
+// small sums both are serial latency, balanced at L ~ sqrt(1.4 * heaviest expected load).  Large sums are
+// throughput-bound and keep the length chosen from the entry count.
+static u32 msm_chunk_len_plan(const MsmPlan& plan, size_t m) {
+    u32 base = msm_chunk_len(m * (size_t)plan.W);
+    u32 nb_min = plan.nb[0];
+    for (int w = 1; w < plan.W; ++w) if (plan.nb[w] < nb_min) nb_min = plan.nb[w];
+    double heavy = (double)m / (double)(nb_min ? nb_min : 1);
+    u32 L = 4;
+    while (L < 32 && (double)L * (double)L < 1.4 * heavy) L <<= 1;
+    return L > base ? L : base;
+}
 
 void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, size_t m, MsmWorkspace& ws) {
     size_t N = m * (size_t)plan.W;
-    u32 L = msm_chunk_len(N);
+    u32 L = msm_chunk_len_plan(plan, m);
     u32 T = (u32)((N + L - 1) / L);
     cudaMemsetAsync(ws.buckets, 0, sizeof(G1Xyzz) * (size_t)plan.total_buckets, s);      // empty buckets = infinity
     static const int staged = [] { const char* e = getenv("KZGB_ACC_STAGED"); return e ? atoi(e) : 1; }();
@@ -297,8 +310,8 @@ void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws
 }
 // batched subgroup check on the slice sums msm_window_sums_stage(.., want_all = true) left in the two workspaces
 // (same plan): the 2 x 128 serial |x|^2 chains run side by side in one launch
-void launch_sg_check(cudaStream_t s, const MsmPlan& plan, const MsmWorkspace& wa, const MsmWorkspace& wb, uint32_t* counters) {
-    k_sg_check<<<dim3((unsigned)((plan.nbits + 31) / 32), 2), 32, 0, s>>>(wa.slices, wb.slices, plan.nbits, counters);
+void launch_sg_check(cudaStream_t s, const MsmPlan& plan, const MsmWorkspace& wa, const MsmWorkspace& wb, uint32_t* counters, int nsums) {
+    k_sg_check<<<dim3((unsigned)((plan.nbits + 31) / 32), (unsigned)nsums), 32, 0, s>>>(wa.slices, wb.slices, plan.nbits, counters);
     KZ_COUNT_LAUNCH();
 }
 // Horner combine of up to 3 sums whose window totals are ready; one block per sum

@@ -69,7 +69,8 @@ void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, si
 void msm_reduce_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, G1Jac* out);
 void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, bool want_all);
 // batched subgroup check on the slice sums of two sums (after msm_window_sums_stage with want_all): counters[2] += sums outside G1
-void launch_sg_check(cudaStream_t s, const MsmPlan& plan, const MsmWorkspace& wa, const MsmWorkspace& wb, uint32_t* counters);
+void launch_sg_check(cudaStream_t s, const MsmPlan& plan, const MsmWorkspace& wa, const MsmWorkspace& wb, uint32_t* counters,
+                     int nsums = 2);      // nsums = 1: only wa
 void msm_combine_stage(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs);
 // up to 3 jobs; each job needs its own buckets / sg_work / slices / winsums; the serial Horner chains run concurrently
 void msm_reduce_stage_multi(cudaStream_t s, const MsmPlan* const* plans, MsmWorkspace* const* wss, G1Jac* const* outs, int njobs);
