@@ -41,6 +41,23 @@ def test_gpu_blob_batch(gpu_ctx, oracle_ctx, oracle_lib):
     assert gpu_ctx.verify_blob_kzg_proof_batch(blob, comm, proof) == (0, True)
 
 
+@pytest.mark.parametrize("n", [16383, 16384, 16385, 17001, 33333])
+def test_gpu_sizes_around_the_batched_check_threshold(gpu_ctx, oracle_ctx, oracle_lib, n):
+    """Ragged sizes on both sides of the default threshold of the batched subgroup check (16384): verdict and every
+    artefact equal the oracle's; a planted wrong proof is rejected with equal pairing inputs."""
+    seed = 0x4B5A4750 + n
+    C, Z, Y, PI = oracle_ctx.synth_instance(seed, 0, n)
+    assert gpu_ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == oracle_ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    a1, a2 = gpu_ctx.last_artifacts(), oracle_ctx.last_artifacts()
+    for key in ("S1", "S2", "S3", "A", "B", "sum_ry", "root"):
+        assert a1[key] == a2[key], key
+    j = n - 2
+    PIb = PI[:48 * j] + PI[48 * (j + 1):48 * (j + 2)] + PI[48 * j:48 * (j + 1)] + PI[48 * (j + 2):]
+    assert gpu_ctx.verify_kzg_proof_batch(C, Z, Y, PIb, n) == oracle_ctx.verify_kzg_proof_batch(C, Z, Y, PIb, n) == (0, False)
+    a1, a2 = gpu_ctx.last_artifacts(), oracle_ctx.last_artifacts()
+    assert a1["A"] == a2["A"] and a1["B"] == a2["B"]
+
+
 def test_gpu_fpd_ops(gpu_ctx, oracle_ctx):
     ps.check_fpd_ops(gpu_ctx, oracle_ctx)
 
