@@ -82,7 +82,7 @@ struct DeviceSlot {
     uint8_t* h_digests = nullptr;      // 32 * ceil(n_max/1024)
     uint32_t* h_small = nullptr;       // 64 words: [0..2] counters, [8..15] root words, [16] result
     uint8_t* h_partial = nullptr;      // 320 * 64
-    cudaEvent_t ev[20] = {};
+    cudaEvent_t ev[24] = {};
     // current shard (between phase 1 and phase 2)
     const uint8_t *cur_C = nullptr, *cur_z = nullptr, *cur_y = nullptr, *cur_pi = nullptr;
     size_t cur_n = 0;
@@ -658,18 +658,30 @@ static kzgb_ret blob_zy(DeviceSlot& s, const uint8_t* blobs, const uint8_t* comm
     CK(cudaSetDevice(s.device));
     cudaStream_t st = s.stream;
     if (!s.d_blobs) {
-        CK(dmalloc(s.d_blobs, (size_t)KZ_BLOB_STAGE * KZGB_BLOB_BYTES));
-        CK(dmalloc(s.blob_leaves, (size_t)KZ_BLOB_STAGE * 128 * 8));
+        CK(dmalloc(s.d_blobs, (size_t)2 * KZ_BLOB_STAGE * KZGB_BLOB_BYTES));        // two staging buffers
+        CK(dmalloc(s.blob_leaves, (size_t)2 * KZ_BLOB_STAGE * 128 * 8));
     }
     uint32_t* bad_dev = (uint32_t*)(s.scratch + 4096);
     CK(cudaMemsetAsync(bad_dev, 0, sizeof(uint32_t), st));
     if (comms) CK(cudaMemcpyAsync(s.dC, comms, 48 * m, cudaMemcpyHostToDevice, st));
     if (z_in) CK(cudaMemcpyAsync(s.dz, z_in, 32 * m, cudaMemcpyHostToDevice, st));
-    for (size_t done = 0; done < m; done += KZ_BLOB_STAGE) {
+    // double buffering: the copy stream fills one staging buffer while the kernels work on the other
+    cudaStream_t cp = s.stream2;
+    CK(cudaEventRecord(s.ev[14], st));
+    CK(cudaStreamWaitEvent(cp, s.ev[14], 0));
+    size_t chunk = 0;
+    for (size_t done = 0; done < m; done += KZ_BLOB_STAGE, ++chunk) {
         size_t k = m - done < KZ_BLOB_STAGE ? m - done : KZ_BLOB_STAGE;
-        CK(cudaMemcpyAsync(s.d_blobs, blobs + (size_t)KZGB_BLOB_BYTES * done, (size_t)KZGB_BLOB_BYTES * k, cudaMemcpyHostToDevice, st));
-        if (!z_in) launch_blob_challenges(st, s.d_blobs, s.dC + 48 * done, k, s.blob_leaves, s.dz + 32 * done);
-        launch_blob_eval(st, s.cell_W, s.d_blobs, s.dz + 32 * done, k, s.dy + 32 * done, bad_dev);
+        int b = (int)(chunk & 1);
+        uint8_t* buf = s.d_blobs + (size_t)b * KZ_BLOB_STAGE * KZGB_BLOB_BYTES;
+        uint32_t* leaves = s.blob_leaves + (size_t)b * KZ_BLOB_STAGE * 128 * 8;
+        if (chunk >= 2) CK(cudaStreamWaitEvent(cp, s.ev[20 + b], 0));              // buffer b is free again
+        CK(cudaMemcpyAsync(buf, blobs + (size_t)KZGB_BLOB_BYTES * done, (size_t)KZGB_BLOB_BYTES * k, cudaMemcpyHostToDevice, cp));
+        CK(cudaEventRecord(s.ev[18 + b], cp));
+        CK(cudaStreamWaitEvent(st, s.ev[18 + b], 0));
+        if (!z_in) launch_blob_challenges(st, buf, s.dC + 48 * done, k, leaves, s.dz + 32 * done);
+        launch_blob_eval(st, s.cell_W, buf, s.dz + 32 * done, k, s.dy + 32 * done, bad_dev);
+        CK(cudaEventRecord(s.ev[20 + b], st));
     }
     CK(cudaMemcpyAsync(s.h_small + 24, bad_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
