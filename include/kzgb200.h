@@ -30,7 +30,8 @@ typedef enum { KZGB_OK = 0, KZGB_BADARGS = 1, KZGB_ERROR = 2, KZGB_MALLOC = 3 } 
 /* per-point status bytes of the decompression stage (first failure wins; App. B.2) */
 enum { KZGB_ST_OK = 0, KZGB_ST_BAD_FLAGS = 1, KZGB_ST_X_GE_P = 2, KZGB_ST_NOT_ON_CURVE = 3, KZGB_ST_NOT_IN_G1 = 4 };
 
-#define KZGB_CHUNK 1024u          /* proofs per Fiat-Shamir chunk digest (App. B.4) */
+#define KZGB_CHUNK 128u           /* proofs per Fiat-Shamir chunk digest (128, not the 1024 of SURVEY App. B --
+                                     the serial SHA-256 over a chunk is on the critical path of small batches) */
 #define KZGB_PARTIAL_BYTES 320u   /* per-shard partial: A_shard = S1+S2-(sum r_i y_i)G1 (Jacobian X|Y|Z, 144 B) | S3 (144 B) | sum r_i y_i (32 B) */
 #define KZGB_N_STAGES 10
 
@@ -83,7 +84,7 @@ kzgb_ret verify_kzg_proof_batch_device(bool *ok, const uint8_t *dC, const uint8_
  * process boundaries.  n_local must be a multiple of KZGB_CHUNK unless this is the last shard. */
 kzgb_ret kzgb_shard_phase1(kzgb_ctx *ctx, int slot, const uint8_t *C, const uint8_t *z, const uint8_t *y,
                            const uint8_t *pi, size_t n_local, int inputs_on_device, void *stream,
-                           uint8_t *chunk_digests_out /*32*ceil(n_local/1024)*/, uint32_t *n_bad_out);
+                           uint8_t *chunk_digests_out /*32*ceil(n_local/KZGB_CHUNK)*/, uint32_t *n_bad_out);
 kzgb_ret kzgb_fs_root(uint8_t root_out[32], const uint8_t *chunk_digests, size_t n_chunks, uint64_t n_total);
 kzgb_ret kzgb_shard_phase2(kzgb_ctx *ctx, int slot, const uint8_t root[32], uint64_t global_offset, void *stream,
                            uint8_t partial_out[KZGB_PARTIAL_BYTES]);

@@ -13,7 +13,7 @@ from pathlib import Path
 
 KZGB_OK, KZGB_BADARGS, KZGB_ERROR, KZGB_MALLOC = 0, 1, 2, 3
 ST_OK, ST_BAD_FLAGS, ST_X_GE_P, ST_NOT_ON_CURVE, ST_NOT_IN_G1 = 0, 1, 2, 3, 4
-CHUNK = 1024
+CHUNK = 128
 PARTIAL_BYTES = 320
 N_STAGES = 10
 STAGE_NAMES = ["h2d", "decompress", "hash", "root_host", "challenges", "msm_sort", "msm_accumulate",

@@ -21,3 +21,5 @@
 typedef uint8_t u8;
 typedef uint32_t u32;
 typedef uint64_t u64;
+
+#define KZ_FS_CHUNK 128u      /* leaves per Fiat-Shamir chunk digest = KZGB_CHUNK of include/kzgb200.h (checked in host.cu) */

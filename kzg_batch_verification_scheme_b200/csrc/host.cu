@@ -1,6 +1,6 @@
 // Host orchestration + the C ABI of include/kzgb200.h for the CUDA product library (libkzgb200.so).
 // One DeviceSlot per GPU: own stream, workspaces sized for n_max, pinned mailboxes.  A batch is cut into
-// contiguous shards (multiples of 1024 proofs) over the slots; only chunk digests (32 B / 1024 proofs),
+// contiguous shards (multiples of KZGB_CHUNK proofs) over the slots; only chunk digests (32 B / KZGB_CHUNK proofs),
 // the 32-byte root and one 320-byte partial per shard cross the host (BASELINE.json:5: "combined on the
 // host, so no NCCL is needed").  There is NO CPU fallback: every arithmetic step runs in a kernel.
 #include <cstdio>
@@ -20,6 +20,8 @@
             return KZGB_ERROR;                                                                        \
         }                                                                                             \
     } while (0)
+
+static_assert(KZGB_CHUNK == KZ_FS_CHUNK, "chunk size of the public header and of the device hash must agree");
 
 namespace {
 
@@ -79,7 +81,7 @@ struct DeviceSlot {
     uint32_t* blob_leaves = nullptr;
     bool have_ab = false;              // sums[3], sums[4] hold the pairing inputs of the last call
     // pinned mailboxes
-    uint8_t* h_digests = nullptr;      // 32 * ceil(n_max/1024)
+    uint8_t* h_digests = nullptr;      // 32 * ceil(n_max/KZGB_CHUNK)
     uint32_t* h_small = nullptr;       // 64 words: [0..2] counters, [8..15] root words, [16] result
     uint8_t* h_partial = nullptr;      // 320 * 64
     cudaEvent_t ev[24] = {};
@@ -332,11 +334,17 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
             launch_decompress_sqrt_points(st, s.cur_C, head, s.pts, s.status, s.counters);
             CK(cudaStreamWaitEvent(st, s.ev[1], 0));
             launch_decompress_sqrt_points(st, s.cur_C + 48 * head, n - head, s.pts + 2 * head, s.status + head, s.counters);
-        } else {
+            CK(cudaStreamWaitEvent(st, s.ev[13], 0));
+            launch_decompress_sqrt_points(st, s.cur_pi, n, s.pts + 2 * n, s.status + n, s.counters);
+        } else if (n >= 65536) {
             launch_decompress_sqrt_points(st, s.cur_C, n, s.pts, s.status, s.counters);
+            CK(cudaStreamWaitEvent(st, s.ev[13], 0));
+            launch_decompress_sqrt_points(st, s.cur_pi, n, s.pts + 2 * n, s.status + n, s.counters);
+        } else {
+            // small batch: one launch over both arrays (two would be two serial latencies of the square-root chain)
+            CK(cudaStreamWaitEvent(st, s.ev[13], 0));
+            launch_decompress_sqrt(st, s.cur_C, s.cur_pi, n, s.pts, s.status, s.counters);
         }
-        CK(cudaStreamWaitEvent(st, s.ev[13], 0));
-        launch_decompress_sqrt_points(st, s.cur_pi, n, s.pts + 2 * n, s.status + n, s.counters);
     } else if (!on_device && n >= 32768) {
         // K1 in two halves: commitments, then (once pi is resident) proofs -- hides most of the H2D copy
         launch_decompress_points(st, s.cur_C, n, s.pts, s.k1_tmp, s.status, s.counters);
@@ -487,7 +495,7 @@ kzgb_ret verify_common(bool* ok, const uint8_t* C, const uint8_t* z, const uint8
     *ok = false;
     if (!ctx || !C || !z || !y || !pi || n == 0) return KZGB_BADARGS;
     size_t G = on_device ? 1 : ctx->slots.size();
-    // contiguous shards, multiples of the 1024-proof hash chunk
+    // contiguous shards, multiples of the hash chunk
     size_t nch = (n + KZGB_CHUNK - 1) / KZGB_CHUNK;
     if (G > nch) G = nch;
     std::vector<size_t> lo(G + 1);

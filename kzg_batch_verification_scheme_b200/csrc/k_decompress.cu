@@ -68,6 +68,11 @@ void launch_subgroup_points(cudaStream_t s, Fp* pts, size_t m, Fp* tmp, uint8_t*
     launch_subgroup_chains(s, pts, m, tmp, status, counters, cfg / 10 % 10, cfg % 10);
     KZ_COUNT_LAUNCH(); KZ_COUNT_LAUNCH();
 }
+// K1a only on both input arrays in one launch (small batches: two launches would be two serial latencies)
+void launch_decompress_sqrt(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, Fp* out_pts, uint8_t* status,
+                            uint32_t* counters) {
+    launch_decompress_impl(s, inC, inPi, n, 2 * n, out_pts, nullptr, status, counters, false);
+}
 void launch_decompress_sqrt_points(cudaStream_t s, const uint8_t* in, size_t m, Fp* out_pts, uint8_t* status, uint32_t* counters) {
     launch_decompress_impl(s, in, in, m, m, out_pts, nullptr, status, counters, false);
 }

@@ -47,13 +47,13 @@ void launch_leaf_hash(cudaStream_t s, const uint8_t* C, const uint8_t* z, const 
     KZ_COUNT_LAUNCH();
 }
 
-// ---- chunk digests: one thread per chunk of 1024 leaves (serial SHA-256 over <= 32 KiB)
+// ---- chunk digests: one thread per chunk of KZ_FS_CHUNK leaves (serial SHA-256 over <= 4 KiB)
 __global__ void k_chunk_hash(const u32* __restrict__ leaves, size_t n, u32* __restrict__ digests) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t nch = (n + 1023) / 1024;
+    size_t nch = (n + KZ_FS_CHUNK - 1) / KZ_FS_CHUNK;
     if (j >= nch) return;
-    size_t lo = j * 1024;
-    u32 cnt = (u32)((n - lo) < 1024 ? (n - lo) : 1024);
+    size_t lo = j * KZ_FS_CHUNK;
+    u32 cnt = (u32)((n - lo) < KZ_FS_CHUNK ? (n - lo) : KZ_FS_CHUNK);
     u32 h[8];
     fs_chunk_words(h, leaves + 8 * lo, cnt);
 #pragma unroll
@@ -61,7 +61,7 @@ __global__ void k_chunk_hash(const u32* __restrict__ leaves, size_t n, u32* __re
 }
 void launch_chunk_hash(cudaStream_t s, const uint32_t* leaves, size_t n, uint32_t* digests_words) {
     if (!n) return;
-    size_t nch = (n + 1023) / 1024;
+    size_t nch = (n + KZ_FS_CHUNK - 1) / KZ_FS_CHUNK;
     k_chunk_hash<<<(unsigned)((nch + 31) / 32), 32, 0, s>>>(leaves, n, digests_words);
     KZ_COUNT_LAUNCH();
 }

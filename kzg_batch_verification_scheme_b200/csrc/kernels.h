@@ -24,6 +24,8 @@ void launch_decompress_points(cudaStream_t s, const uint8_t* in, size_t m, Fp* o
                               uint32_t* counters);
 // K1a only / per-point subgroup check only (batched subgroup check and its fallback)
 void launch_decompress_sqrt_points(cudaStream_t s, const uint8_t* in, size_t m, Fp* out_pts, uint8_t* status, uint32_t* counters);
+void launch_decompress_sqrt(cudaStream_t s, const uint8_t* inC, const uint8_t* inPi, size_t n, Fp* out_pts, uint8_t* status,
+                            uint32_t* counters);
 void launch_subgroup_points(cudaStream_t s, Fp* pts, size_t m, Fp* tmp, uint8_t* status, uint32_t* counters);
 void launch_points_to_be(cudaStream_t s, const Fp* pts, size_t m, uint8_t* out96);           // canonical x||y
 void launch_points_from_be(cudaStream_t s, const uint8_t* in96, size_t m, Fp* pts, uint32_t* counters);

@@ -3,8 +3,8 @@ combine of 320-byte partials, no NCCL on the data path).  The only exchanges are
 (chunk digests, partials) moved with torch.distributed object collectives over the CPU (gloo) group.
 
     rank r owns proofs [r*n_local, (r+1)*n_local) of ONE batch of world*n_local proofs
-    phase 1 (local)   : K1 + leaf/chunk hashes                  -> 32 B digest per 1024 proofs
-    all_gather        : digests  (<= 32 KiB per 2^20 proofs)
+    phase 1 (local)   : K1 + leaf/chunk hashes                  -> 32 B digest per 128 proofs
+    all_gather        : digests  (256 KiB per 2^20 proofs)
     root (every rank) : SHA-256 over all digests (host)
     phase 2 (local)   : challenges, three MSMs                  -> 320-byte partial
     gather to rank 0  : partials

@@ -14,7 +14,7 @@
 
 namespace orc {
 
-constexpr size_t CHUNK = 1024;
+constexpr size_t CHUNK = 128;
 constexpr u64 FIELD_ELEMENTS_PER_BLOB = 4096;
 
 // ------------------------------------------------------------------ threads
@@ -50,7 +50,7 @@ inline void fs_leaf(u8 out[32], const u8* C, const u8* z, const u8* y, const u8*
     s.update(TAG_LEAF, 16); s.update(C, 48); s.update(z, 32); s.update(y, 32); s.update(pi, 48);
     s.final(out);
 }
-// digests for proofs [0,n): out has 32*ceil(n/1024) bytes
+// digests for proofs [0,n): out has 32*ceil(n/CHUNK) bytes
 inline void fs_chunk_digests(u8* out, const u8* C, const u8* z, const u8* y, const u8* pi, size_t n, int threads) {
     size_t nch = (n + CHUNK - 1) / CHUNK;
     parallel_for(nch, threads, [&](size_t b, size_t e) {

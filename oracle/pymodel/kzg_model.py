@@ -11,7 +11,7 @@ import struct
 from . import bls12_381 as bls
 from .bls12_381 import P, R
 
-CHUNK = 1024
+CHUNK = 128
 FIELD_ELEMENTS_PER_BLOB = 4096
 
 TAG_LEAF = b"KZGB200/leaf_v1_"

@@ -169,12 +169,12 @@ static void emu_digests(std::vector<u8>& dig, const u8* C, const u8* z, const u8
         words_from_be(zw, z + 32 * i, 8); words_from_be(yw, y + 32 * i, 8);
         fs_leaf_words(&leaves[8 * i], cw, zw, yw, pw);
     }
-    size_t nch = (n + 1023) / 1024;
+    size_t nch = (n + KZ_FS_CHUNK - 1) / KZ_FS_CHUNK;
     dig.resize(32 * nch);
     for (size_t j = 0; j < nch; ++j) {
         u32 h[8];
-        size_t lo = j * 1024;
-        fs_chunk_words(h, &leaves[8 * lo], (u32)std::min<size_t>(1024, n - lo));
+        size_t lo = j * KZ_FS_CHUNK;
+        fs_chunk_words(h, &leaves[8 * lo], (u32)std::min<size_t>(KZ_FS_CHUNK, n - lo));
         words_to_be(&dig[32 * j], h, 8);
     }
 }
@@ -475,11 +475,11 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     std::vector<u32> leaves(8 * m);
     for (size_t k = 0; k < m; ++k)
         fs_cell_leaf_words(&leaves[8 * k], ci[k], xi[k], reinterpret_cast<const u32*>(cells + 2048 * k), reinterpret_cast<const u32*>(proofs + 48 * k));
-    size_t nch = (m + 1023) / 1024;
+    size_t nch = (m + KZ_FS_CHUNK - 1) / KZ_FS_CHUNK;
     std::vector<u8> dig(32 * nch);
     for (size_t j = 0; j < nch; ++j) {
         u32 h[8];
-        fs_chunk_words(h, &leaves[8 * j * 1024], (u32)std::min<size_t>(1024, m - j * 1024));
+        fs_chunk_words(h, &leaves[8 * j * KZ_FS_CHUNK], (u32)std::min<size_t>(KZ_FS_CHUNK, m - j * KZ_FS_CHUNK));
         words_to_be(&dig[32 * j], h, 8);
     }
     auto sha_msg = [](std::vector<u8> msg, u8 out[32]) {

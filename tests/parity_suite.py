@@ -104,7 +104,7 @@ def check_tower_and_pairing(ctx, oracle):
         assert lib.pairing_check(b.g1_affine_bytes(A), bytes(96)) == (0, False)
 
 
-def check_fs(ctx, oracle, sizes=(1, 2, 63, 1023, 1024, 1025, 2500)):
+def check_fs(ctx, oracle, sizes=(1, 2, 63, 127, 128, 129, 1023, 1024, 1025, 2500)):
     seed = 0x4B5A4703
     nmax = max(sizes)
     C, Z, Y, PI = oracle.synth_instance(seed, 0, nmax)
@@ -327,7 +327,7 @@ def check_cell_batch(ctx, oracle, inst):
     assert ctx.verify_cell_kzg_proof_batch(b.g1_compress((0, 2)) + comms[48:], ci, xi, cells, proofs) == (1, False)
 
 
-def check_random_differential(gpu_ctx, oracle_ctx, sizes=(1, 2, 3, 17, 64, 255, 256, 1000, 1024, 1025, 2049, 3000), trials=40, pool=3000):
+def check_random_differential(gpu_ctx, oracle_ctx, sizes=(1, 2, 3, 17, 64, 127, 128, 129, 255, 256, 1000, 1024, 1025, 2049, 3000), trials=40, pool=3000):
     """Randomised differential test: random batch sizes and random single-byte / structural corruptions;
     return code, verdict and (when well-formed) the pairing inputs must equal the oracle's."""
     rnd = random.Random(20261018)

@@ -57,7 +57,7 @@ def test_emu_tower_and_pairing(emu_ctx, oracle_ctx):
 
 
 def test_emu_fs(emu_ctx, oracle_ctx):
-    ps.check_fs(emu_ctx, oracle_ctx, sizes=(1, 2, 63, 1024, 1025))
+    ps.check_fs(emu_ctx, oracle_ctx, sizes=(1, 2, 63, 127, 128, 129, 1025))
 
 
 def test_emu_msm(emu_ctx, oracle_ctx):

@@ -155,7 +155,7 @@ def test_gpu_shards_equal_single_and_cross_library_combine(gpu_lib, oracle_lib):
     C, Z, Y, PI = ctx.synth_instance(seed, 0, n)
     assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)        # 3 slots on device 0
     ref_root = ctx.last_artifacts()["root"]
-    for bounds in ([0, n], [0, 2048, n], [0, 1024, 4096, n]):
+    for bounds in ([0, n], [0, 2048, n], [0, 384, 4096, n]):
         digs = b""
         for s in range(len(bounds) - 1):
             lo, hi = bounds[s], bounds[s + 1]
@@ -195,7 +195,7 @@ def test_gpu_device_resident_entry_point(gpu_lib):
     ctx.close()
 
 
-@pytest.mark.parametrize("n", [3, 63, 64, 65, 1023, 1024, 1025, 2047, 3000])
+@pytest.mark.parametrize("n", [3, 63, 64, 65, 127, 128, 129, 1023, 1024, 1025, 2047, 3000])
 def test_gpu_verify_ragged_sizes(gpu_ctx, oracle_ctx, n):
     """Ragged batch sizes around the window / chunk boundaries: verdict + all artefacts bit-exact."""
     seed = 0x4B5A4710 + n

@@ -185,7 +185,7 @@ def test_sharded_equals_single(oracle_lib):
     rc, ok = ctx.verify_kzg_proof_batch(C, Z, Y, PI, n)
     assert (rc, ok) == (0, True)
     ref = ctx.last_artifacts()
-    for bounds in ([0, n], [0, 1024, n], [0, 1024, 2048, n]):
+    for bounds in ([0, n], [0, 384, n], [0, 1024, 2048, n]):
         digs, parts = b"", b""
         for s in range(len(bounds) - 1):
             lo, hi = bounds[s], bounds[s + 1]
