@@ -32,7 +32,7 @@ IMAD_PER_FPMUL, IMAD_PER_FPSQR = 300, 234
 K1_M_PER_POINT = 85 + 1 + 126 * 2 + 5 * 8 + 5 * 12 + 3 + 2           # + to/from Montgomery
 K1_S_PER_POINT = 377 + 2 + 126 * 5 + 5 * 3 + 5 * 4 + 1
 K1_IMAD_PER_POINT = K1_M_PER_POINT * IMAD_PER_FPMUL + K1_S_PER_POINT * IMAD_PER_FPSQR
-# batches of >= KZGB_SG_BATCH_MIN (default 16384) proofs: the subgroup check is done on 128 bucket-slice sums per MSM,
+# batches of >= KZGB_SG_BATCH_MIN (default 2) proofs: the subgroup check is done on 128 bucket-slice sums per MSM,
 # K1 is the decompression kernel alone (sqrt + on-curve + Montgomery conversions)
 K1A_M_PER_POINT, K1A_S_PER_POINT = 85 + 1 + 2, 377 + 2
 K1A_IMAD_PER_POINT = K1A_M_PER_POINT * IMAD_PER_FPMUL + K1A_S_PER_POINT * IMAD_PER_FPSQR
@@ -268,7 +268,7 @@ def main():
             except Exception:                                   # noqa: BLE001
                 pass
         k1_ms = stages.get("decompress", 0.0)
-        sg_min = int(os.environ.get("KZGB_SG_BATCH_MIN", "16384"))
+        sg_min = int(os.environ.get("KZGB_SG_BATCH_MIN", "2"))
         sg_batch = sg_min > 0 and n_local >= sg_min
         if k1_ms > 0:
             per_point = K1A_IMAD_PER_POINT if sg_batch else K1_IMAD_PER_POINT

@@ -54,7 +54,7 @@ struct DeviceSlot {
     ChunkRecs recsA = {nullptr, nullptr, nullptr, nullptr, nullptr}, recsB = {nullptr, nullptr, nullptr, nullptr, nullptr};
     G1Xyzz* sg_partial = nullptr;      // bucket reduction scratch of three sums: run sums, totals, slice sums
     size_t sg_cap = 0;                 // entries per sum (the last 256 are the slice sums)
-    size_t sg_min = 16384;             // batches of at least this many proofs use the batched subgroup check (0 = never)
+    size_t sg_min = 2;                 // batches of at least this many proofs use the batched subgroup check (0 = never)
     bool sg_batch = false;             // current shard: K1 ran without the per-point chains
     bool head_mode = false;            // current shard: K1 started after the first eighth of C was resident (ev[17])
     G1Jac* sums = nullptr;             // [0] S1 [1] S2' [2] S3 [3] A [4] B

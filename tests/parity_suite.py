@@ -297,7 +297,7 @@ def check_subgroup_batch(ctx, oracle, n=24, min_batch=2, ells=(3, 11, 10177, 859
         assert ctx.verify_kzg_proof_batch(C, Zb, Y, PI, n) == oracle.verify_kzg_proof_batch(C, Zb, Y, PI, n) == (1, False)
         assert ctx.last_artifacts()["n_bad_scalars"] == oracle.last_artifacts()["n_bad_scalars"] == 1
     finally:
-        ctx.set_subgroup_batch_min(16384)
+        ctx.set_subgroup_batch_min(2)
 
 
 def check_cell_batch(ctx, oracle, inst):

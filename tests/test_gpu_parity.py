@@ -20,6 +20,17 @@ def test_gpu_field_ops(gpu_ctx, oracle_ctx):
     ps.check_field_ops(gpu_ctx, oracle_ctx, n_random=2000)
 
 
+def test_gpu_per_point_subgroup_path(gpu_lib, oracle_ctx, oracle_lib):
+    """The deterministic per-point subgroup check (kzgb_set_subgroup_batch_min(0)) stays a first-class path: the
+    batched check falls back to it, verify_kzg_proof and the cell commitments use it."""
+    ctx = gpu_lib.context(n_max=1 << 16)
+    assert ctx.set_subgroup_batch_min(0) == 0
+    ps.check_verify(ctx, oracle_ctx, oracle_lib, sizes=(1, 2, 9, 1000))
+    ps.check_status_classes(ctx, oracle_ctx, n=64)
+    ps.check_degenerate(ctx, oracle_ctx, n=40)
+    ctx.close()
+
+
 def test_gpu_subgroup_batch_small(gpu_ctx, oracle_ctx):
     ps.check_subgroup_batch(gpu_ctx, oracle_ctx, n=24)
 
