@@ -238,8 +238,95 @@ void launch_synth(cudaStream_t s, uint64_t seed, uint64_t offset, size_t n, cons
     KZ_COUNT_LAUNCH();
 }
 
-// ---- host SHA-256 for the root (<= 32 KiB at n = 2^20; the one cross-shard step)
+// ---- host SHA-256 for the root (32 B per 128 proofs: 256 KiB at n = 2^20, 2 MiB for 8 x 2^20; the one cross-shard step).
+// Whole blocks go straight from the input; with the x86 SHA extensions (checked with cpuid at run time) the
+// compression runs on sha256rnds2 / sha256msg1 / sha256msg2, otherwise on the portable rounds.
+#if defined(__x86_64__)
+#include <cpuid.h>
+#include <immintrin.h>
+#endif
 namespace {
+static const uint32_t HK[64] = {
+    0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+    0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+    0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+    0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+    0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+    0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+    0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+    0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+
+static inline uint32_t hrotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static void sha_blocks_portable(uint32_t h[8], const uint8_t* p, size_t nblocks) {
+    for (; nblocks; --nblocks, p += 64) {
+        uint32_t w[64];
+        for (int i = 0; i < 16; ++i) w[i] = (uint32_t)p[4 * i] << 24 | (uint32_t)p[4 * i + 1] << 16 | (uint32_t)p[4 * i + 2] << 8 | p[4 * i + 3];
+        for (int i = 16; i < 64; ++i) {
+            uint32_t s0 = hrotr(w[i - 15], 7) ^ hrotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+            uint32_t s1 = hrotr(w[i - 2], 17) ^ hrotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+        }
+        uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+        for (int i = 0; i < 64; ++i) {
+            uint32_t t1 = hh + (hrotr(e, 6) ^ hrotr(e, 11) ^ hrotr(e, 25)) + ((e & f) ^ (~e & g)) + HK[i] + w[i];
+            uint32_t t2 = (hrotr(a, 2) ^ hrotr(a, 13) ^ hrotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+}
+#if defined(__x86_64__)
+// SHA extensions: the state lives in two registers as (A,B,E,F) and (C,D,G,H); four rounds per sha256rnds2 pair
+__attribute__((target("sha,sse4.1,ssse3"))) static void sha_blocks_ni(uint32_t h[8], const uint8_t* p, size_t nblocks) {
+    const __m128i bswap = _mm_set_epi64x(0x0c0d0e0f08090a0bLL, 0x0405060700010203LL);
+    __m128i tmp = _mm_loadu_si128((const __m128i*)&h[0]);        // DCBA
+    __m128i st1 = _mm_loadu_si128((const __m128i*)&h[4]);        // HGFE
+    tmp = _mm_shuffle_epi32(tmp, 0xB1);                          // CDAB
+    st1 = _mm_shuffle_epi32(st1, 0x1B);                          // EFGH
+    __m128i st0 = _mm_alignr_epi8(tmp, st1, 8);                  // ABEF
+    st1 = _mm_blend_epi16(st1, tmp, 0xF0);                       // CDGH
+    for (; nblocks; --nblocks, p += 64) {
+        const __m128i save0 = st0, save1 = st1;
+        __m128i m[4];
+        for (int i = 0; i < 4; ++i) m[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(p + 16 * i)), bswap);
+        for (int r = 0; r < 16; ++r) {                           // 16 groups of four rounds
+            __m128i cur = m[r & 3];
+            __m128i wk = _mm_add_epi32(cur, _mm_loadu_si128((const __m128i*)&HK[4 * r]));
+            st1 = _mm_sha256rnds2_epu32(st1, st0, wk);
+            st0 = _mm_sha256rnds2_epu32(st0, st1, _mm_shuffle_epi32(wk, 0x0E));
+            if (r < 12) {
+                // message schedule: w[t+16..t+19] from the four most recent groups (cur = w[t..t+3] is the oldest)
+                __m128i w1 = m[(r + 1) & 3], w2 = m[(r + 2) & 3], w3 = m[(r + 3) & 3];
+                __m128i x = _mm_sha256msg1_epu32(cur, w1);
+                x = _mm_add_epi32(x, _mm_alignr_epi8(w3, w2, 4));
+                m[r & 3] = _mm_sha256msg2_epu32(x, w3);
+            }
+        }
+        st0 = _mm_add_epi32(st0, save0);
+        st1 = _mm_add_epi32(st1, save1);
+    }
+    tmp = _mm_shuffle_epi32(st0, 0x1B);                          // FEBA
+    st1 = _mm_shuffle_epi32(st1, 0xB1);                          // DCHG
+    st0 = _mm_blend_epi16(tmp, st1, 0xF0);                       // DCBA
+    st1 = _mm_alignr_epi8(st1, tmp, 8);                          // HGFE
+    _mm_storeu_si128((__m128i*)&h[0], st0);
+    _mm_storeu_si128((__m128i*)&h[4], st1);
+}
+static bool cpu_has_sha() {
+    unsigned a = 0, b = 0, c = 0, d = 0;
+    if (!__get_cpuid_count(7, 0, &a, &b, &c, &d)) return false;
+    bool sha = (b >> 29) & 1u;
+    if (!__get_cpuid(1, &a, &b, &c, &d)) return false;
+    return sha && ((c >> 19) & 1u) && ((c >> 9) & 1u);           // SHA, SSE4.1, SSSE3
+}
+#endif
+static void sha_blocks(uint32_t h[8], const uint8_t* p, size_t nblocks) {
+#if defined(__x86_64__)
+    static const bool ni = cpu_has_sha() && !getenv("KZGB_NO_SHANI");
+    if (ni) { sha_blocks_ni(h, p, nblocks); return; }
+#endif
+    sha_blocks_portable(h, p, nblocks);
+}
 struct HostSha {
     uint32_t h[8];
     uint8_t buf[64];
@@ -248,44 +335,24 @@ struct HostSha {
         static const uint32_t iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
         memcpy(h, iv, sizeof h);
     }
-    static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
-    void block(const uint8_t* p) {
-        static const uint32_t K[64] = {
-            0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
-            0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
-            0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
-            0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
-            0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
-            0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
-            0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
-            0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
-        uint32_t w[64];
-        for (int i = 0; i < 16; ++i) w[i] = (uint32_t)p[4 * i] << 24 | p[4 * i + 1] << 16 | p[4 * i + 2] << 8 | p[4 * i + 3];
-        for (int i = 16; i < 64; ++i) {
-            uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
-            uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
-            w[i] = w[i - 16] + s0 + w[i - 7] + s1;
-        }
-        uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
-        for (int i = 0; i < 64; ++i) {
-            uint32_t t1 = hh + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
-            uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
-            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
-        }
-        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
-    }
     void update(const uint8_t* p, size_t n) {
-        for (size_t i = 0; i < n; ++i) {
-            buf[len++ % 64] = p[i];
-            if (len % 64 == 0) block(buf);
+        size_t fill = (size_t)(len % 64);
+        len += n;
+        if (fill) {
+            size_t take = 64 - fill < n ? 64 - fill : n;
+            memcpy(buf + fill, p, take);
+            p += take; n -= take;
+            if (fill + take < 64) return;
+            sha_blocks(h, buf, 1);
         }
+        if (n >= 64) { sha_blocks(h, p, n / 64); p += n & ~(size_t)63; n &= 63; }
+        if (n) memcpy(buf, p, n);
     }
     void final(uint8_t out[32]) {
         uint64_t bits = len * 8;
-        uint8_t pad = 0x80;
-        update(&pad, 1);
-        pad = 0;
-        while (len % 64 != 56) update(&pad, 1);
+        uint8_t pad[72] = {0x80};
+        size_t fill = (size_t)(len % 64), padlen = (fill < 56 ? 56 : 120) - fill;
+        update(pad, padlen);
         uint8_t lb[8];
         for (int i = 0; i < 8; ++i) lb[i] = (uint8_t)(bits >> (56 - 8 * i));
         update(lb, 8);
