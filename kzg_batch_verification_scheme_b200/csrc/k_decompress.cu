@@ -1,6 +1,8 @@
-// K1: batch G1 decompression + on-curve + subgroup check (BASELINE.json:5 item (b)) -- ~89 % of all
-// integer work of a batch verification.  One thread per point; 48-byte inputs are
-// read with three 128-bit loads, the 96-byte Montgomery affine result is written with six.
+// K1: batch G1 decompression + on-curve + subgroup check (BASELINE.json:5 item (b)).  One thread per point; 48-byte
+// inputs are read with three 128-bit loads, the 96-byte Montgomery affine result is written with six.
+// Batches of two or more proofs run K1a alone and establish subgroup membership on the bucket-slice sums of the
+// MSMs (msm.cuh, DESIGN.md "Batched subgroup check"); K1b/K1c are the per-point check used by verify_kzg_proof,
+// the cell commitments, kzgb_g1_decompress_batch and as the fallback that names the offending points.
 // Also hosts the small conversion kernels, the primitive debug operator and the IMAD microbenchmark.
 #include <cstdlib>
 

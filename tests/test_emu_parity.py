@@ -37,6 +37,16 @@ def test_emu_blob_batch(emu_ctx, oracle_ctx, oracle_lib):
     ps.check_blob_batch(emu_ctx, oracle_ctx, ps.synth_blobs(oracle_lib, 0x4B5A4742, 2))
 
 
+def test_emu_random_differential_batched_check(emu_ctx, oracle_ctx):
+    """The randomised corruptions again with the batched subgroup check switched on in the emulation (the CUDA
+    library's default): return codes, verdicts and pairing inputs must still equal the oracle's."""
+    assert emu_ctx.set_subgroup_batch_min(2) == 0
+    try:
+        ps.check_random_differential(emu_ctx, oracle_ctx, sizes=(2, 3, 9), trials=10, pool=12)
+    finally:
+        emu_ctx.set_subgroup_batch_min(0)
+
+
 def test_emu_sha_single_block(emu_ctx, oracle_ctx):
     import random
     rnd = random.Random(1)
