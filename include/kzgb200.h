@@ -169,7 +169,7 @@ kzgb_ret kzgb_blob_eval(uint8_t *y_out, const uint8_t *blobs, const uint8_t *z_i
 #define KZGB_BLOB_BYTES 131072
 
 /* Batches (shards) of at least n_min proofs establish subgroup membership of all 2n points through 128 slice
- * sums per MSM of the bucket tables that sum r_i C_i and sum r_i pi_i fill anyway (soundness 2^-127 per point,
+ * sums per MSM of the bucket tables that sum r_i C_i and sum r_i pi_i fill anyway (soundness 2^-128 per point,
  * DESIGN.md "Batched subgroup check"); smaller ones, and any batch in which a slice sum fails, run the
  * deterministic per-point check.  0 = always per point.  Default 2: every batch (env KZGB_SG_BATCH_MIN). */
 kzgb_ret kzgb_set_subgroup_batch_min(kzgb_ctx *ctx, size_t n_min);

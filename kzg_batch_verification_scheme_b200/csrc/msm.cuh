@@ -251,8 +251,8 @@ KZ_COLD G1Jac msm_combine_body(const G1Xyzz* win, int W, int c) {
 // Batched subgroup check: the signed digits of the challenges r_i are 128 fair, independent coins per
 // point -- for a signed window the c-1 magnitude bits and the sign, for the top window its tb bits.  Point P_i
 // enters slice (w, b) with coefficient sign * bit in {-1, 0, 1} and slice (w, all) with its sign; each value has
-// probability <= 1/2 + 2^-c, independently over the 128 slices, so a point with a non-zero cofactor component (odd
-// order >= 3) leaves all 128 slice sums inside G1 with probability <= 2^-127.  Checking the 128 sums of
+// probability <= 1/2, independently over the 128 slices, so a point with a non-zero cofactor component (odd
+// order >= 3) leaves all 128 slice sums inside G1 with probability <= 2^-128.  Checking the 128 sums of
 // sum r_i C_i and of sum r_i pi_i replaces 2n per-point checks, with no extra point additions.
 #define KZ_SG_RUN 16
 struct SgWin { int k, kl, kh; u32 rows, cols, tpr, tpc, rjobs, jobs; };

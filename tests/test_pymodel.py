@@ -1,6 +1,8 @@
 """Pure-Python model self-checks: known answers of SURVEY.md Appendix A + algebraic pairing tests."""
 import random
 
+import pytest
+
 from oracle.pymodel import bls12_381 as b
 from oracle.pymodel import kzg_model as k
 
@@ -67,3 +69,55 @@ def test_kzg_semantics_small():
     assert k.verdict_tau_shortcut(k.batch_artifacts(C, Z, Y, PI, 2))
     art1 = k.batch_artifacts(C[:48], Z[:32], Y[:32], PI[:48], 1, single=True)
     assert k.verdict_tau_shortcut(art1)
+
+
+def _signed_digits(r, c, nbits=128):
+    """Digit recoding of csrc/msm.cuh (msm_digits_body): signed windows, unsigned top window absorbing the carry."""
+    W = (nbits + c - 1) // c
+    out, carry = [], 0
+    for w in range(W):
+        width = c if w < W - 1 else nbits - c * (W - 1)
+        v = ((r >> (c * w)) & ((1 << width) - 1)) + carry
+        if w < W - 1 and v > (1 << (c - 1)):
+            out.append(v - (1 << c)); carry = 1
+        else:
+            out.append(v); carry = 0
+    assert sum(d << (c * w) for w, d in enumerate(out)) == r
+    return out
+
+
+@pytest.mark.parametrize("c", [3, 8, 13, 16])
+def test_slice_coefficients_of_the_batched_subgroup_check_are_fair_coins(c):
+    """DESIGN.md "Batched subgroup check": a point enters slice (w, b) with coefficient sign * bit_b(|digit|) and slice
+    (w, all) with its sign.  Soundness needs every coefficient value to have probability <= 1/2 (exact: of the 2^c
+    equally likely window values, half have bit b of the magnitude clear, half are positive) and the 128 coefficients
+    of one point to be independent.  Empirical check over random 128-bit challenges."""
+    import random
+    rnd = random.Random(1000 + c)
+    nbits, N = 128, 6000
+    W = (nbits + c - 1) // c
+    tb = nbits - c * (W - 1)
+    slices = [(w, b) for w in range(W - 1) for b in range(c)] + [(W - 1, b) for b in range(tb)]
+    assert len(slices) == nbits
+    counts = [dict() for _ in slices]
+    zero_pairs = 0
+    s0, s1 = 0, len(slices) // 2                     # two slices of different windows
+    z0 = z1 = 0
+    for _ in range(N):
+        d = _signed_digits(rnd.getrandbits(nbits), c)
+        coef = []
+        for w, b in slices:
+            m, sgn = abs(d[w]), (1 if d[w] > 0 else -1 if d[w] < 0 else 0)
+            if w < W - 1 and b == c - 1:
+                v = sgn                                # the slice "all"
+            else:
+                v = sgn * ((m >> b) & 1)
+            coef.append(v)
+        for k, v in enumerate(coef):
+            counts[k][v] = counts[k].get(v, 0) + 1
+        a, bq = coef[s0] == 0, coef[s1] == 0
+        z0 += a; z1 += bq; zero_pairs += a and bq
+    slack = 4 * (0.25 / N) ** 0.5                       # four standard deviations
+    for k, cnt in enumerate(counts):
+        assert max(cnt.values()) / N <= 0.5 + slack, (slices[k], cnt)
+    assert abs(zero_pairs / N - (z0 / N) * (z1 / N)) < 0.03          # no visible dependence between windows
