@@ -41,9 +41,9 @@ def test_gpu_subgroup_batch_default_threshold(gpu_ctx, oracle_ctx):
 
 
 def test_gpu_blob_batch(gpu_ctx, oracle_ctx, oracle_lib):
-    """Blob-level caller: z, y bit-exact vs the oracle, verdicts, malformed blobs; 260 blobs
-    cross the 256-blob staging buffer."""
-    ps.check_blob_batch(gpu_ctx, oracle_ctx, ps.synth_blobs(oracle_lib, 0x4B5A4743, 260))
+    """Blob-level caller: z, y bit-exact vs the oracle, verdicts, malformed blobs; 600 blobs
+    fill both 256-blob staging buffers and reuse the first."""
+    ps.check_blob_batch(gpu_ctx, oracle_ctx, ps.synth_blobs(oracle_lib, 0x4B5A4743, 600))
     import random
     blob, comm, proof, coeffs = ps.python_blob(random.Random(12))          # against direct polynomial evaluation
     rc, zs, ys = gpu_ctx.blob_challenges_evals(blob, comm)
