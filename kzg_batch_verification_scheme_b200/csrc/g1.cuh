@@ -65,6 +65,14 @@ KZ_HD G1Jac jac_add(const G1Jac& p, const G1Jac& q) {
     return r;
 }
 KZ_HD G1Jac jac_neg(const G1Jac& p) { return {p.X, fp_neg(p.Y), p.Z}; }
+// the same test for a Jacobian point J (not infinity), without an inversion:
+// beta X_J Z_Q^2 == X_Q Z_J^2  and  Y_J Z_Q^3 == -Y_Q Z_J^3
+KZ_HD bool g1_subgroup_compare_jac(const G1Jac& j, const G1Jac& q) {
+    if (jac_is_inf(q)) return false;
+    Fp zq2 = fp_sqr(q.Z), zj2 = fp_sqr(j.Z);
+    if (!fp_eq(fp_mul(fp_mul(fp_const(FP_BETA), j.X), zq2), fp_mul(q.X, zj2))) return false;
+    return fp_eq(fp_mul(j.Y, fp_mul(zq2, q.Z)), fp_neg(fp_mul(q.Y, fp_mul(zj2, j.Z))));
+}
 KZ_COLD G1Aff jac_to_aff(const G1Jac& p) {        // one inversion; infinity -> (0,0)
     if (jac_is_inf(p)) return aff_inf();
     Fp zi = fp_inv(p.Z), zi2 = fp_sqr(zi);

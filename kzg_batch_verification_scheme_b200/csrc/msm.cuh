@@ -335,6 +335,6 @@ KZ_COLD G1Xyzz msm_window_from_slices(const G1Xyzz* T, int k, const G1Xyzz& ext)
 }
 KZ_COLD bool sg_sum_in_g1(const G1Xyzz& t) {
     if (xyzz_is_inf(t)) return true;
-    G1Aff a = jac_to_aff(xyzz_to_jac(t));
-    return g1_in_subgroup(a);
+    G1Jac j = xyzz_to_jac(t);                    // no inversion on the serial path: both chains and the test are projective
+    return g1_subgroup_compare_jac(j, jac_mul_xabs(jac_mul_xabs(j)));
 }
