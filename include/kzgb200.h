@@ -47,7 +47,8 @@ typedef struct {
     uint32_t n_bad_scalars;         /* count of z_i/y_i >= r */
     /* device ms per stage of the last call (0 where not applicable):
        0 h2d, 1 decompress+validate, 2 leaf+chunk hashes, 3 root (host), 4 challenges+scalars,
-       5 msm digits+sort, 6 msm bucket accumulate, 7 msm bucket reduce+combine, 8 pairing, 9 total */
+       5 msm digits+sort, 6 msm bucket accumulate + reduction to window totals, 7 Horner combine + partial,
+       8 pairing, 9 total */
     float stage_ms[KZGB_N_STAGES];
 } kzgb_artifacts;
 
