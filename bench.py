@@ -121,7 +121,7 @@ def run_reference(args):
     if rank != 0:
         return
     lib = oracle_lib()
-    octx = lib.context()
+    octx = lib.test_context()
     cores = os.cpu_count() or 1
     # calibrate a sample that takes a few seconds per step
     rate, _ = time_oracle(octx, 1024, cores)
@@ -170,7 +170,7 @@ def main():
     n_local = n_total_cfg if args.scaling == "weak" else max(CHUNK, n_total_cfg // world)
     n_total = n_local * world
     lib = load()
-    ctx = lib.context(devices=[local], n_max=n_local)
+    ctx = lib.test_context(devices=[local], n_max=n_local)
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---- synthetic inputs: generated ON the device, then mirrored into pinned host memory for e2e
@@ -302,7 +302,7 @@ def main():
             # CPU baseline: oracle port on the box's host cores, bounded sample (~10-20 s)
             try:
                 olib = oracle_lib()
-                octx = olib.context()
+                octx = olib.test_context()
                 cores = os.cpu_count() or 1
                 rate, _ = time_oracle(octx, 1024, cores)
                 n_s = 1024
@@ -337,7 +337,7 @@ def main():
                         continue
                     npl = 1 << lg
                     depth = 3 if lg <= 16 else 2
-                    ctxs = [ctx] + [lib.context(devices=[local], n_max=npl) for _ in range(depth - 1)]
+                    ctxs = [ctx] + [lib.test_context(devices=[local], n_max=npl) for _ in range(depth - 1)]
 
                     def work(c, k):
                         for _ in range(k):

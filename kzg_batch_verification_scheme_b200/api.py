@@ -118,8 +118,19 @@ class KzgLib:
             raise KzgError(f"kzgb_synth_setup -> {rc}")
         return g1.raw, g2.raw
 
-    def context(self, g1_monomial=None, g2_monomial=None, devices=None, n_max=1 << 16):
+    def context(self, g1_monomial, g2_monomial, devices=None, n_max=1 << 16):
+        """Verifier over the caller's trusted setup (compressed [tau^i]G1, [tau^i]G2).  The setup is mandatory:
+        a verifier is only as trustworthy as its setup, so there is no default."""
+        if g1_monomial is None or g2_monomial is None:
+            raise KzgError("a trusted setup is required (g1_monomial, g2_monomial); for tests and benchmarks use "
+                           "test_context(), whose tau is public")
         return Context(self, g1_monomial, g2_monomial, devices, n_max)
+
+    def test_context(self, devices=None, n_max=1 << 16):
+        """INSECURE: context over the repository's test setup, whose tau is derivable by anyone
+        (SHA256("kzgb200/insecure-test-tau") mod r) -- forged proofs verify against it.  Tests and bench only."""
+        g1, g2 = test_setup()
+        return Context(self, g1, g2, devices, n_max)
 
 
 class Context:
@@ -128,7 +139,7 @@ class Context:
     def __init__(self, klib: KzgLib, g1_monomial, g2_monomial, devices, n_max):
         self.klib, self.lib = klib, klib.lib
         if g1_monomial is None or g2_monomial is None:
-            g1_monomial, g2_monomial = test_setup()
+            raise KzgError("a trusted setup is required (see KzgLib.test_context for the insecure test setup)")
         devs = None
         nd = 0
         if devices is not None:

@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "quad.cuh"
 
 __global__ void __launch_bounds__(128) k_msm_digits(const u32* __restrict__ scalars, int nl, size_t m,
                                                     u32* __restrict__ keys, u32* __restrict__ vals, u32* __restrict__ count,
@@ -206,35 +207,91 @@ __global__ void __launch_bounds__(128) k_sg_pass2(const G1Xyzz* __restrict__ par
     if (t >= g.rows + g.cols) return;
     tot[(size_t)w * tstride + t] = sg_total(part + (size_t)w * stride, g, t);
 }
-// one warp per slice: strided partial sums, shared-memory tree, slice sum to slices[sid]
-__global__ void __launch_bounds__(32) k_sg_slices(const G1Xyzz* __restrict__ buckets, const G1Xyzz* __restrict__ tot, u32 tstride,
-                                                   G1Xyzz* __restrict__ slices, int want_all, const __grid_constant__ MsmPlan plan) {
-    __shared__ G1Xyzz red[32];
+// ---- the same reduction with quad-lane point arithmetic (quad.cuh): latency-optimised, used while the bucket tables
+// are small enough for the reduction to be a serial chain rather than a throughput problem.
+// One block of KZ_RED_THREADS / 4 quads per row / column total: strided partial sums, then a tree over the quads.
+#define KZ_RED_THREADS 64
+__global__ void __launch_bounds__(KZ_RED_THREADS) k_red_totals(const G1Xyzz* __restrict__ buckets, G1Xyzz* __restrict__ tot, u32 tstride,
+                                                               const __grid_constant__ MsmPlan plan) {
+    constexpr int NQ = KZ_RED_THREADS / 4;
+    __shared__ Fp qsm[NQ * KZ_QUAD_SLOTS];
+    __shared__ G1Xyzz red[NQ];
+    const int w = blockIdx.y;
+    const SgWin g = sg_win(plan, w);
+    const u32 t = blockIdx.x;
+    if (t >= g.rows + g.cols) return;                       // uniform over the block
+    const int qi = threadIdx.x >> 2;
+    Quad q = quad_make(qsm, qi);
+    const G1Xyzz* base = buckets + plan.bucket_off[w];
+    G1Xyzz acc = xyzz_inf();
+    if (t < g.rows) {
+        for (u32 e = qi; e < g.cols; e += NQ) acc = quad_xyzz_add(q, acc, sg_bucket(base, (t << g.kl) + e));
+    } else {
+        const u32 c = t - g.rows;
+        for (u32 e = qi; e < g.rows; e += NQ) acc = quad_xyzz_add(q, acc, sg_bucket(base, (e << g.kl) + c));
+    }
+    for (int st = NQ / 2; st > 0; st >>= 1) {               // level st: quads [st, 2st) publish, quads [0, st) add
+        if (qi >= st && qi < 2 * st && q.ql == 0) red[qi] = acc;
+        __syncthreads();
+        if (qi < st) acc = quad_xyzz_add(q, acc, red[qi + st]);
+    }
+    if (threadIdx.x == 0) tot[(size_t)w * tstride + t] = acc;
+}
+// one block of 32 quads per slice sum
+#define KZ_SLICE_THREADS 128
+__global__ void __launch_bounds__(KZ_SLICE_THREADS) k_red_slices(const G1Xyzz* __restrict__ buckets, const G1Xyzz* __restrict__ tot, u32 tstride,
+                                                                 G1Xyzz* __restrict__ slices, int want_all, const __grid_constant__ MsmPlan plan) {
+    constexpr int NQ = KZ_SLICE_THREADS / 4;
+    __shared__ Fp qsm[NQ * KZ_QUAD_SLOTS];
+    __shared__ G1Xyzz red[NQ];
     const SgSlice sl = sg_slice(plan, (int)blockIdx.x);
     if (sl.all && !want_all) return;
     const SgWin g = sg_win(plan, sl.w);
-    red[threadIdx.x] = sg_slice_part(tot + (size_t)sl.w * tstride, buckets + plan.bucket_off[sl.w], g, sl, threadIdx.x, 32);
-    __syncwarp();
-    for (int st = 16; st > 0; st >>= 1) {
-        if ((int)threadIdx.x < st) red[threadIdx.x] = xyzz_add(red[threadIdx.x], red[threadIdx.x + st]);
-        __syncwarp();
+    const int qi = threadIdx.x >> 2;
+    Quad q = quad_make(qsm, qi);
+    const G1Xyzz* R = tot + (size_t)sl.w * tstride;
+    const G1Xyzz* Q = R + g.rows;
+    G1Xyzz acc = xyzz_inf();
+    if (sl.all) {
+        for (u32 r = qi; r < g.rows; r += NQ) acc = quad_xyzz_add(q, acc, R[r]);
+        if (qi == 0) acc = quad_xyzz_add(q, acc, buckets[plan.bucket_off[sl.w] + (1u << g.k) - 1u]);       // magnitude 2^k
+    } else if (sl.b < g.kl) {
+        // the columns with bit b set, enumerated densely: c = (hi << (b+1)) | 1 << b | lo
+        const u32 half = g.cols >> 1, lowmask = (1u << sl.b) - 1u;
+        for (u32 i = qi; i < half; i += NQ) acc = quad_xyzz_add(q, acc, Q[((i & ~lowmask) << 1) | (1u << sl.b) | (i & lowmask)]);
+    } else {
+        const u32 b = sl.b - g.kl, half = g.rows >> 1, lowmask = (1u << b) - 1u;
+        for (u32 i = qi; i < half; i += NQ) acc = quad_xyzz_add(q, acc, R[((i & ~lowmask) << 1) | (1u << b) | (i & lowmask)]);
     }
-    if (threadIdx.x == 0) slices[blockIdx.x] = red[0];
+    for (int st = NQ / 2; st > 0; st >>= 1) {
+        if (qi >= st && qi < 2 * st && q.ql == 0) red[qi] = acc;
+        __syncthreads();
+        if (qi < st) acc = quad_xyzz_add(q, acc, red[qi + st]);
+    }
+    if (threadIdx.x == 0) slices[blockIdx.x] = acc;
 }
-// one thread per window: Horner over its bit slices
-__global__ void __launch_bounds__(32) k_msm_window_horner(const G1Xyzz* __restrict__ buckets, const G1Xyzz* __restrict__ slices,
-                                                           G1Xyzz* __restrict__ winsums, const __grid_constant__ MsmPlan plan) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+// one quad per window: Horner over its bit slices
+__global__ void __launch_bounds__(32) k_msm_window_horner_q(const G1Xyzz* __restrict__ buckets, const G1Xyzz* __restrict__ slices,
+                                                             G1Xyzz* __restrict__ winsums, const __grid_constant__ MsmPlan plan) {
+    __shared__ Fp qsm[8 * KZ_QUAD_SLOTS];
+    const int qi = threadIdx.x >> 2, w = blockIdx.x * 8 + qi;
     if (w >= plan.W) return;
+    Quad q = quad_make(qsm, qi);
     const SgWin g = sg_win(plan, w);
-    winsums[w] = msm_window_from_slices(slices + (size_t)w * plan.c, g.k, buckets[plan.bucket_off[w] + (1u << g.k) - 1u]);
+    const G1Xyzz* T = slices + (size_t)w * plan.c;
+    G1Xyzz acc = buckets[plan.bucket_off[w] + (1u << g.k) - 1u];
+    for (int b = g.k - 1; b >= 0; --b) acc = quad_xyzz_add(q, quad_xyzz_dbl(q, acc), T[b]);
+    if (q.ql == 0) winsums[w] = acc;
 }
-// batched subgroup check: one thread per slice sum of the two sums; counters[2] += sums outside G1
-__global__ void __launch_bounds__(32) k_sg_check(const G1Xyzz* __restrict__ slices_a, const G1Xyzz* __restrict__ slices_b, int nslices,
-                                                  u32* __restrict__ counters) {
-    const int sid = blockIdx.x * blockDim.x + threadIdx.x;
+// batched subgroup check: one quad per slice sum of the two sums; counters[2] += sums outside G1
+__global__ void __launch_bounds__(32) k_sg_check_q(const G1Xyzz* __restrict__ slices_a, const G1Xyzz* __restrict__ slices_b, int nslices,
+                                                    u32* __restrict__ counters) {
+    __shared__ Fp qsm[8 * KZ_QUAD_SLOTS];
+    const int qi = threadIdx.x >> 2, sid = blockIdx.x * 8 + qi;
     if (sid >= nslices) return;
-    if (!sg_sum_in_g1((blockIdx.y ? slices_b : slices_a)[sid])) atomicAdd(counters + 2, 1u);
+    Quad q = quad_make(qsm, qi);
+    const bool ok = quad_sum_in_g1(q, (blockIdx.y ? slices_b : slices_a)[sid]);
+    if (!ok && q.ql == 0) atomicAdd(counters + 2, 1u);
 }
 // Horner combine; one block per job so the three sums of a batch run their serial chains concurrently
 struct CombineJobs {
@@ -242,10 +299,19 @@ struct CombineJobs {
     G1Jac* out[3];
     int W[3], c[3];
 };
-__global__ void k_msm_combine(CombineJobs jobs) {
-    if (threadIdx.x) return;
-    int j = blockIdx.x;
-    *jobs.out[j] = msm_combine_body(jobs.winsums[j], jobs.W[j], jobs.c[j]);
+__global__ void __launch_bounds__(32) k_msm_combine(CombineJobs jobs) {
+    __shared__ Fp qsm[KZ_QUAD_SLOTS];
+    if (threadIdx.x >= 4) return;
+    Quad q = quad_make(qsm, 0);
+    const int j = blockIdx.x;
+    const G1Xyzz* win = jobs.winsums[j];
+    G1Xyzz acc = xyzz_inf();
+    for (int w = jobs.W[j] - 1; w >= 0; --w) {
+        if (!xyzz_is_inf(acc))
+            for (int k = 0; k < jobs.c[j]; ++k) acc = quad_xyzz_dbl(q, acc);
+        acc = quad_xyzz_add(q, acc, win[w]);
+    }
+    if (q.ql == 0) *jobs.out[j] = xyzz_to_jac(acc);
 }
 
 void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars, int nl, size_t m, MsmWorkspace& ws) {
@@ -293,25 +359,46 @@ void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, si
     k_msm_chunk_pass2<<<(T + 127) / 128, 128, 0, s>>>(T, ws.buckets, ws.recs);
     KZ_COUNT_LAUNCH();
 }
-// bucket reduction of one sum up to its per-window totals (ws.winsums); ws.slices keeps the nbits slice sums.
-// want_all: also the "all" slices of the signed windows (needed only by the batched subgroup check)
-void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, bool want_all) {
+// Slice sums of one sum: ws.slices[0 .. nbits) (sg_slice numbering).  want_all: also the "all" slices of the signed
+// windows (needed only by the batched subgroup check).  Tables of up to 2^KZGB_RED_QUAD_MAXK buckets per window are
+// reduced by the quad kernels (latency), larger ones by the run-sum kernels (throughput).
+static int red_quad_maxk() {
+    static const int v = [] { const char* e = getenv("KZGB_RED_QUAD_MAXK"); return e ? atoi(e) : 12; }();
+    return v;
+}
+void msm_slices_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, bool want_all) {
     const SgLayout L = sg_layout(plan);
     G1Xyzz* part = ws.sg_work;
     G1Xyzz* tot = ws.sg_work + (size_t)plan.W * L.stride;
+    int kmax = plan.c - 1, tb = plan.nbits - plan.c * (plan.W - 1);
+    if (plan.W == 1 || tb > kmax) kmax = tb;
+    if (kmax <= red_quad_maxk()) {
+        k_red_totals<<<dim3(L.tstride, (unsigned)plan.W), KZ_RED_THREADS, 0, s>>>(ws.buckets, tot, L.tstride, plan);
+        KZ_COUNT_LAUNCH();
+        k_red_slices<<<(unsigned)plan.nbits, KZ_SLICE_THREADS, 0, s>>>(ws.buckets, tot, L.tstride, ws.slices, want_all ? 1 : 0, plan);
+        KZ_COUNT_LAUNCH();
+        return;
+    }
     k_sg_pass1<<<dim3((L.stride + 127) / 128, (unsigned)plan.W), 128, 0, s>>>(ws.buckets, part, L.stride, plan);
     KZ_COUNT_LAUNCH();
     k_sg_pass2<<<dim3((L.tstride + 127) / 128, (unsigned)plan.W), 128, 0, s>>>(part, L.stride, tot, L.tstride, plan);
     KZ_COUNT_LAUNCH();
-    k_sg_slices<<<(unsigned)plan.nbits, 32, 0, s>>>(ws.buckets, tot, L.tstride, ws.slices, want_all ? 1 : 0, plan);
-    KZ_COUNT_LAUNCH();
-    k_msm_window_horner<<<(unsigned)((plan.W + 31) / 32), 32, 0, s>>>(ws.buckets, ws.slices, ws.winsums, plan);
+    k_red_slices<<<(unsigned)plan.nbits, KZ_SLICE_THREADS, 0, s>>>(ws.buckets, tot, L.tstride, ws.slices, want_all ? 1 : 0, plan);
     KZ_COUNT_LAUNCH();
 }
-// batched subgroup check on the slice sums msm_window_sums_stage(.., want_all = true) left in the two workspaces
-// (same plan): the 2 x 128 serial |x|^2 chains run side by side in one launch
+// per-window totals (ws.winsums) from the slice sums: only the classic path (Horner combine) needs them
+void msm_winsums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws) {
+    k_msm_window_horner_q<<<(unsigned)((plan.W + 7) / 8), 32, 0, s>>>(ws.buckets, ws.slices, ws.winsums, plan);
+    KZ_COUNT_LAUNCH();
+}
+void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, bool want_all) {
+    msm_slices_stage(s, plan, ws, want_all);
+    msm_winsums_stage(s, plan, ws);
+}
+// batched subgroup check on the slice sums msm_slices_stage(.., want_all = true) left in the two workspaces
+// (same plan): the 2 x 128 |x|^2 chains run side by side in one launch, one quad each
 void launch_sg_check(cudaStream_t s, const MsmPlan& plan, const MsmWorkspace& wa, const MsmWorkspace& wb, uint32_t* counters, int nsums) {
-    k_sg_check<<<dim3((unsigned)((plan.nbits + 31) / 32), (unsigned)nsums), 32, 0, s>>>(wa.slices, wb.slices, plan.nbits, counters);
+    k_sg_check_q<<<dim3((unsigned)((plan.nbits + 7) / 8), (unsigned)nsums), 32, 0, s>>>(wa.slices, wb.slices, plan.nbits, counters);
     KZ_COUNT_LAUNCH();
 }
 // Horner combine of up to 3 sums whose window totals are ready; one block per sum

@@ -69,7 +69,9 @@ void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars
 // accumulate + reduce + combine over points `pts` (2 Fp each, m points) using the sorted entries in ws
 void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, size_t m, MsmWorkspace& ws);
 void msm_reduce_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, G1Jac* out);
-void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, bool want_all);
+void msm_window_sums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, bool want_all);   // slices + per-window totals
+void msm_slices_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, bool want_all);        // ws.slices only
+void msm_winsums_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws);                      // ws.winsums from ws.slices
 // batched subgroup check on the slice sums of two sums (after msm_window_sums_stage with want_all): counters[2] += sums outside G1
 void launch_sg_check(cudaStream_t s, const MsmPlan& plan, const MsmWorkspace& wa, const MsmWorkspace& wb, uint32_t* counters,
                      int nsums = 2);      // nsums = 1: only wa

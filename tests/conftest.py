@@ -42,7 +42,7 @@ def oracle_lib():
 
 @pytest.fixture(scope="session")
 def oracle_ctx(oracle_lib):
-    ctx = oracle_lib.context()
+    ctx = oracle_lib.test_context()
     yield ctx
     ctx.close()
 
@@ -55,6 +55,6 @@ def gpu_lib():
 
 @pytest.fixture(scope="session")
 def gpu_ctx(gpu_lib):
-    ctx = gpu_lib.context(n_max=1 << 16)
+    ctx = gpu_lib.test_context(n_max=1 << 16)
     yield ctx
     ctx.close()

@@ -38,7 +38,7 @@ def test_product_fails_loudly_without_gpu():
     from kzg_batch_verification_scheme_b200.api import KzgError, load
     lib = load()
     with pytest.raises(KzgError):
-        lib.context()
+        lib.test_context()
 
 
 def test_oracle_exports_everything(oracle_lib):

@@ -71,7 +71,7 @@ def test_cell_batch_verdicts(oracle_lib, cell_ctx):
 
 
 def test_cell_batch_needs_extended_setup(oracle_lib):
-    ctx = oracle_lib.context()           # 1 G1 + 2 G2 points only
+    ctx = oracle_lib.test_context()           # 1 G1 + 2 G2 points only
     comms, ci, xi, cells, proofs = synth_cells(oracle_lib, 1, 1, 1, 64)
     assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, cells, proofs) == (1, False)
     ctx.close()

@@ -23,7 +23,7 @@ def test_gpu_field_ops(gpu_ctx, oracle_ctx):
 def test_gpu_per_point_subgroup_path(gpu_lib, oracle_ctx, oracle_lib):
     """The deterministic per-point subgroup check (kzgb_set_subgroup_batch_min(0)) stays a first-class path: the
     batched check falls back to it, verify_kzg_proof and the cell commitments use it."""
-    ctx = gpu_lib.context(n_max=1 << 16)
+    ctx = gpu_lib.test_context(n_max=1 << 16)
     assert ctx.set_subgroup_batch_min(0) == 0
     ps.check_verify(ctx, oracle_ctx, oracle_lib, sizes=(1, 2, 9, 1000))
     ps.check_status_classes(ctx, oracle_ctx, n=64)
@@ -133,8 +133,8 @@ def test_gpu_config_n65536_planted_invalid(gpu_lib, oracle_lib):
     """BASELINE.json config[2]: n=2^16 with one planted invalid proof: must reject; valid batch accepts.
     Verdicts are cross-checked pairing-free with the known test tau (A + tau*B == O)."""
     n, seed = 1 << 16, 0x4B5A4702
-    ctx = gpu_lib.context(n_max=n)
-    octx = oracle_lib.context()
+    ctx = gpu_lib.test_context(n_max=n)
+    octx = oracle_lib.test_context()
     C, Z, Y, PI = ctx.synth_instance(seed, 0, n)
     assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
     art = ctx.last_artifacts()
@@ -161,8 +161,8 @@ def test_gpu_shards_equal_single_and_cross_library_combine(gpu_lib, oracle_lib):
     """Shard-count invariance on ONE device (G virtual shards run sequentially) and the
     cross-library check: partials produced by the CUDA library are accepted by the oracle's combine."""
     n, seed = 5 * 1024 + 100, 0x4B5A4703
-    ctx = gpu_lib.context(devices=[0, 0, 0], n_max=n)
-    octx = oracle_lib.context()
+    ctx = gpu_lib.test_context(devices=[0, 0, 0], n_max=n)
+    octx = oracle_lib.test_context()
     C, Z, Y, PI = ctx.synth_instance(seed, 0, n)
     assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)        # 3 slots on device 0
     ref_root = ctx.last_artifacts()["root"]
@@ -191,7 +191,7 @@ def test_gpu_shards_equal_single_and_cross_library_combine(gpu_lib, oracle_lib):
 def test_gpu_device_resident_entry_point(gpu_lib):
     import torch
     n, seed = 4096, 0x4B5A4704
-    ctx = gpu_lib.context(n_max=n)
+    ctx = gpu_lib.test_context(n_max=n)
     bufs = [torch.empty(s * n, dtype=torch.uint8, device="cuda") for s in (48, 32, 32, 48)]
     ctx.synth_instance(seed, 0, n, device_ptrs=tuple(t.data_ptr() for t in bufs))
     torch.cuda.synchronize()
@@ -233,7 +233,7 @@ def test_gpu_msm_large_random_vs_linearity(gpu_lib):
     """Size-independent property at 2^16 points: MSM(k) + MSM(k') == MSM(k + k') (bit-exact affine bytes
     compared through a 2-point MSM with unit scalars)."""
     n = 1 << 16
-    ctx = gpu_lib.context(n_max=n)
+    ctx = gpu_lib.test_context(n_max=n)
     C, Z, Y, PI = ctx.synth_instance(0x4B5A4722, 0, n)
     rc, aff, st = ctx.g1_decompress_batch(C)
     assert rc == 0 and not any(st)
@@ -277,7 +277,7 @@ def test_gpu_cell_batch_small(gpu_lib, oracle_lib):
     C, Z, Y, PI = octx.synth_instance(0x4B5A4726, 0, 33)
     assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, 33) == octx.verify_kzg_proof_batch(C, Z, Y, PI, 33) == (0, True)
     # and a context without the extended setup refuses the cell batch
-    plain = gpu_lib.context(n_max=4096)
+    plain = gpu_lib.test_context(n_max=4096)
     inst = synth_cells(oracle_lib, 1, 1, 1, 64)
     assert plain.verify_cell_kzg_proof_batch(*inst) == (1, False)
     plain.close(); ctx.close(); octx.close()
@@ -316,12 +316,12 @@ def test_gpu_full_size_2p20_properties(gpu_lib, oracle_lib):
     its pairing inputs satisfy A + tau*B = O (pairing-free check with the known test tau); one swapped
     pair of proofs is rejected and breaks that relation; two virtual shards give byte-identical A, B, root."""
     n, seed = 1 << 20, 0x4B5A4703
-    ctx = gpu_lib.context(devices=[0, 0], n_max=n)
+    ctx = gpu_lib.test_context(devices=[0, 0], n_max=n)
     C, Z, Y, PI = ctx.synth_instance(seed, 0, n)
     assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)            # two slots on device 0
     a2 = ctx.last_artifacts()
     assert oracle_lib.lib.kzgb_oracle_tau_shortcut(a2["A"], a2["B"]) == 1
-    one = gpu_lib.context(n_max=n)
+    one = gpu_lib.test_context(n_max=n)
     assert one.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)            # one slot
     a1 = one.last_artifacts()
     assert a1["A"] == a2["A"] and a1["B"] == a2["B"] and a1["root"] == a2["root"] and a1["sum_ry"] == a2["sum_ry"]
@@ -332,7 +332,7 @@ def test_gpu_full_size_2p20_properties(gpu_lib, oracle_lib):
     ab = one.last_artifacts()
     assert oracle_lib.lib.kzgb_oracle_tau_shortcut(ab["A"], ab["B"]) == 0
     # a slice of the device generator's stream equals the oracle generator's bytes
-    octx = oracle_lib.context()
+    octx = oracle_lib.test_context()
     assert octx.synth_instance(seed, 777777, 32) == tuple(x[w * 777777:w * (777777 + 32)] for x, w in ((C, 48), (Z, 32), (Y, 32), (PI, 48)))
     # MSM linearity at full size: MSM(k) + MSM(k') == MSM(k + k') over 2^20 points
     rc, aff, st = one.g1_decompress_batch(C)

@@ -179,7 +179,7 @@ def test_msm_matches_model(oracle_ctx):
 
 def test_sharded_equals_single(oracle_lib):
     """Shard-count invariance on the oracle: 1 vs 2 vs 3 shards, n not a multiple of 1024."""
-    ctx = oracle_lib.context(devices=[0, 0, 0])
+    ctx = oracle_lib.test_context(devices=[0, 0, 0])
     seed, n = 0x4B5A4702, 2048 + 100
     C, Z, Y, PI = ctx.synth_instance(seed, 0, n)
     rc, ok = ctx.verify_kzg_proof_batch(C, Z, Y, PI, n)

@@ -18,7 +18,7 @@ from kzg_batch_verification_scheme_b200.sharded import sharded_verify
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group(backend="gloo", rank=rank, world_size=world)
 lib = KzgLib(os.path.join(os.environ["KZGB_ROOT"], "oracle", "libkzgb_oracle.so"))
-ctx = lib.context()
+ctx = lib.test_context()
 ctx.set_threads(2)
 n_local, seed = 1024, 0x4B5A4705
 C, Z, Y, PI = ctx.synth_instance(seed, rank * n_local, n_local)
@@ -27,7 +27,7 @@ assert rc == 0
 if rank == 0:
     assert ok is True
     art = ctx.last_artifacts()
-    full = lib.context()
+    full = lib.test_context()
     Cf, Zf, Yf, PIf = full.synth_instance(seed, 0, n_local * world)
     assert full.verify_kzg_proof_batch(Cf, Zf, Yf, PIf, n_local * world) == (0, True)
     ref = full.last_artifacts()

@@ -11,12 +11,12 @@ lib = load()
 for lg in (16, 20):
     n = 1 << lg
     bufs = [torch.empty(s * n, dtype=torch.uint8, device="cuda") for s in (48, 32, 32, 48)]
-    c0 = lib.context(n_max=n)
+    c0 = lib.test_context(n_max=n)
     c0.synth_instance(0x4B5A4701, 0, n, device_ptrs=tuple(t.data_ptr() for t in bufs))
     torch.cuda.synchronize()
     ptrs = [t.data_ptr() for t in bufs]
     for depth in (1, 2, 3):
-        ctxs = [c0] + [lib.context(n_max=n) for _ in range(depth - 1)]
+        ctxs = [c0] + [lib.test_context(n_max=n) for _ in range(depth - 1)]
         steps = 12 if lg == 16 else 6
         def work(ctx, k):
             for _ in range(k):

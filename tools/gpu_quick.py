@@ -14,7 +14,7 @@ from kzg_batch_verification_scheme_b200.api import load  # noqa: E402
 out = {}
 lib = load()
 sizes = [int(a) for a in sys.argv[1:]] or [4096, 1 << 16]
-ctx = lib.context(n_max=max(sizes))
+ctx = lib.test_context(n_max=max(sizes))
 peak, ms = ctx.imad_peak()
 out["imad_peak_per_s"] = peak
 print(f"IMAD.WIDE peak: {peak / 1e12:.2f} T/s  ({ms:.2f} ms)", flush=True)
