@@ -7,6 +7,11 @@
 #include <chrono>
 #include <new>
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/kzgb200.h"
@@ -80,6 +85,16 @@ struct DeviceSlot {
     uint8_t* d_blobs = nullptr;
     uint32_t* blob_leaves = nullptr;
     bool have_ab = false;              // sums[3], sums[4] hold the pairing inputs of the last call
+    // Horner-free pairing check (mpair.cuh): line tables of the 2 x 33 fixed G2 multiples, per-call buffers
+    G2Aff* mp_chain = nullptr;
+    G2Lines *mp_tab = nullptr, *mp_tab_cell = nullptr;
+    G1Xyzz *mp_terms = nullptr, *mp_terms_in = nullptr;     // this shard's 66 terms; all shards' terms (root device)
+    MpCoef* mp_coef = nullptr;
+    Fp12 *mp_part = nullptr, *mp_F = nullptr;
+    uint8_t* h_terms = nullptr;        // pinned: 64 x 66 terms
+    bool classic = false;              // KZGB_CLASSIC=1: Horner combine + two-pairing kernel (the stage-export path) for every batch
+    bool sums_pending = false;         // the last call left slices only: S1, S2', S3 are computed when artefacts are requested
+    MsmWorkspace ws_keep[3];           // workspaces of S1, S3, S2' of the last call (for the deferred Horner combine)
     // pinned mailboxes
     uint8_t* h_digests = nullptr;      // 32 * ceil(n_max/KZGB_CHUNK)
     uint32_t* h_small = nullptr;       // 64 words: [0..2] counters, [8..15] root words, [16] result
@@ -94,11 +109,76 @@ struct DeviceSlot {
 
 }  // namespace
 
+// One persistent host thread per additional device: the per-shard phases of a multi-device batch are issued (and
+// waited for) side by side instead of one device after the other.  Job 0 runs on the calling thread.
+class SlotPool {
+public:
+    ~SlotPool() { stop(); }
+    void start(size_t n_workers) {
+        for (size_t i = 0; i < n_workers; ++i) {
+            workers_.emplace_back(new Worker());
+            Worker* w = workers_.back().get();
+            w->th = std::thread([w] {
+                std::unique_lock<std::mutex> lk(w->mu);
+                for (;;) {
+                    w->cv.wait(lk, [w] { return w->has_job || w->quit; });
+                    if (w->quit) return;
+                    lk.unlock();
+                    w->job();
+                    lk.lock();
+                    w->has_job = false;
+                    w->cv_done.notify_one();
+                }
+            });
+        }
+    }
+    void stop() {
+        for (auto& w : workers_) {
+            { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; }
+            w->cv.notify_one();
+            if (w->th.joinable()) w->th.join();
+        }
+        workers_.clear();
+    }
+    // fn(0) .. fn(n - 1), one job per thread; returns when all are done
+    template <class F>
+    void run(size_t n, F&& fn) {
+        size_t used = n > 0 ? std::min(n - 1, workers_.size()) : 0;
+        for (size_t i = 0; i < used; ++i) {
+            Worker* w = workers_[i].get();
+            { std::lock_guard<std::mutex> lk(w->mu); w->job = [&fn, i] { fn(i + 1); }; w->has_job = true; }
+            w->cv.notify_one();
+        }
+        if (n > 0) fn(0);
+        for (size_t g = used + 1; g < n; ++g) fn(g);            // more jobs than threads: the caller finishes them
+        for (size_t i = 0; i < used; ++i) {
+            Worker* w = workers_[i].get();
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv_done.wait(lk, [w] { return !w->has_job; });
+        }
+    }
+private:
+    struct Worker {
+        std::thread th;
+        std::mutex mu;
+        std::condition_variable cv, cv_done;
+        std::function<void()> job;
+        bool has_job = false, quit = false;
+    };
+    std::vector<std::unique_ptr<Worker>> workers_;
+};
+
 struct kzgb_ctx {
     std::vector<DeviceSlot> slots;
+    SlotPool pool;
     kzgb_artifacts art;
     float msm_ms[4] = {0, 0, 0, 0};
     uint64_t launches_at_create = 0;
+    int n_shards_last = 1;
+    bool terms_combined = false;       // slot 0 holds the pairing terms of the last batch; A and B are computed on request
+    const G1Xyzz* ab_terms = nullptr;  // ... from these terms (device memory of slot 0), ab_shards shards
+    int ab_shards = 0;
+    bool ab_gather_sum_ry = false;     // sum r_i y_i has to be added up over the shards' devices as well
 };
 
 namespace {
@@ -192,20 +272,26 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     }
     CK(dmalloc(s.sums, 5)); CK(dmalloc(s.partial_dev, KZGB_PARTIAL_BYTES)); CK(dmalloc(s.partials_in, KZGB_PARTIAL_BYTES * 64));
     CK(dmalloc(s.scratch, 1 << 20));
-    CK(dmalloc(s.result_dev, 4)); CK(dmalloc(s.lines, 2)); CK(dmalloc(s.g1_pt, 2)); CK(dmalloc(s.setup_status, 4));
+    CK(dmalloc(s.result_dev, 4)); CK(dmalloc(s.lines, 2)); CK(dmalloc(s.g1_pt, 2)); CK(dmalloc(s.setup_status, 8));
     CK(cudaMallocHost((void**)&s.h_digests, 32 * nch)); CK(cudaMallocHost((void**)&s.h_small, 64 * sizeof(uint32_t)));
     CK(cudaMallocHost((void**)&s.h_partial, KZGB_PARTIAL_BYTES * 64));
+    CK(dmalloc(s.mp_chain, KZ_MP_PAIRS)); CK(dmalloc(s.mp_tab, KZ_MP_PAIRS));
+    CK(dmalloc(s.mp_terms, KZ_MP_PAIRS)); CK(dmalloc(s.mp_terms_in, 64 * KZ_MP_PAIRS)); CK(dmalloc(s.mp_coef, KZ_MP_PAIRS));
+    CK(dmalloc(s.mp_part, mp_part_entries())); CK(dmalloc(s.mp_F, KZ_MP_ITERS));
+    CK(cudaMallocHost((void**)&s.h_terms, sizeof(G1Xyzz) * 64 * KZ_MP_PAIRS));
+    { const char* e = getenv("KZGB_CLASSIC"); s.classic = e && atoi(e) != 0; }
     // trusted setup: decompress + check on the device, precompute the G2 lines
     CK(cudaMemcpyAsync(s.scratch, g2m, 192, cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.scratch + 256, g1m, 48, cudaMemcpyHostToDevice, s.stream));
-    CK(cudaMemsetAsync(s.setup_status, 0, 4 * sizeof(int), s.stream));
+    CK(cudaMemsetAsync(s.setup_status, 0, 8 * sizeof(int), s.stream));
     launch_g2_setup(s.stream, s.scratch, s.lines, s.setup_status);
     launch_g1_setup(s.stream, s.scratch + 256, s.g1_pt, s.setup_status);
-    int st[4];
+    launch_mp_setup(s.stream, s.scratch, s.mp_chain, s.mp_tab, s.setup_status + 4);     // lines of [2^(4t)]G2, [2^(4t)][tau]G2
+    int st[8];
     CK(cudaMemcpyAsync(st, s.setup_status, sizeof st, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));
     CK(cudaGetLastError());
-    if (!(st[0] && st[1] && st[2])) return KZGB_BADARGS;
+    if (!(st[0] && st[1] && st[2] && st[4] && st[5] && st[6])) return KZGB_BADARGS;
     // powers of the 8192-th root of unity: cell batch and blob batch
     CK(dmalloc(s.cell_W, 8192));
     launch_cell_twiddles(s.stream, s.cell_W);
@@ -216,9 +302,11 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
         CK(cudaMemcpyAsync(s.scratch + 4096, g2m, 96, cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(s.scratch + 4096 + 96, g2m + 96 * 64, 96, cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), s.stream));
-        CK(cudaMemsetAsync(s.setup_status, 0, 4 * sizeof(int), s.stream));
+        CK(cudaMemsetAsync(s.setup_status, 0, 8 * sizeof(int), s.stream));
         launch_decompress_points(s.stream, s.scratch, 64, s.cell_g1, s.k1_tmp, s.status, s.counters);
         launch_g2_setup(s.stream, s.scratch + 4096, s.lines_cell, s.setup_status);
+        CK(dmalloc(s.mp_tab_cell, KZ_MP_PAIRS));
+        launch_mp_setup(s.stream, s.scratch + 4096, s.mp_chain, s.mp_tab_cell, s.setup_status + 4);
         uint32_t cnt[2];
         uint8_t stat[64];
         CK(cudaMemcpyAsync(st, s.setup_status, sizeof st, cudaMemcpyDeviceToHost, s.stream));
@@ -226,7 +314,7 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
         CK(cudaMemcpyAsync(stat, s.status, 64, cudaMemcpyDeviceToHost, s.stream));
         CK(cudaStreamSynchronize(s.stream));
         CK(cudaGetLastError());
-        if (!(st[0] && st[1]) || cnt[0]) return KZGB_BADARGS;
+        if (!(st[0] && st[1] && st[4] && st[5] && st[6]) || cnt[0]) return KZGB_BADARGS;
         s.cell_ready = true;
     }
     return KZGB_OK;
@@ -244,11 +332,12 @@ void slot_free(DeviceSlot& s) {
                    s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb, s.recs.head, s.recs.tail,
                    s.recs.head_key, s.recs.tail_key, s.recs.head_flags, s.recsA.head, s.recsA.tail, s.recsA.head_key,
                    s.recsA.tail_key, s.recsA.head_flags, s.recsB.head, s.recsB.tail, s.recsB.head_key, s.recsB.tail_key,
-                   s.recsB.head_flags, s.sg_partial, s.cell_g1, s.lines_cell, s.cell_W, s.d_cells, s.d_ci, s.d_xi, s.cell_coefs, s.d_blobs, s.blob_leaves};
+                   s.recsB.head_flags, s.sg_partial, s.mp_chain, s.mp_tab, s.mp_tab_cell, s.mp_terms, s.mp_terms_in, s.mp_coef, s.mp_part, s.mp_F, s.cell_g1, s.lines_cell, s.cell_W, s.d_cells, s.d_ci, s.d_xi, s.cell_coefs, s.d_blobs, s.blob_leaves};
     for (void* p : dev) if (p) cudaFree(p);
     if (s.h_digests) cudaFreeHost(s.h_digests);
     if (s.h_small) cudaFreeHost(s.h_small);
     if (s.h_partial) cudaFreeHost(s.h_partial);
+    if (s.h_terms) cudaFreeHost(s.h_terms);
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     if (s.stream2) cudaStreamDestroy(s.stream2);
     if (s.stream3) cudaStreamDestroy(s.stream3);
@@ -318,6 +407,7 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
     }
     s.cur_n = n;
     s.have_sums = false;
+    s.sums_pending = false;
     s.have_ab = false;
     if (on_device) CK(cudaEventRecord(s.ev[1], st));    // inputs already resident
     CK(cudaEventRecord(s.ev[13], s2));                  // pi, z, y resident
@@ -364,7 +454,9 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
 }
 
 // Phase 2: challenges, the three MSMs, partial.  Leaves the partial in s.h_partial[0..320) after sync.
-kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, bool single) {
+// classic: Horner combine of the three sums and the 320-byte partial (shard-level ABI, stage exports); otherwise the
+// shard's 66 pairing terms (mpair.cuh) are left in s.mp_terms and the sums are computed only if artefacts are requested.
+kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, bool single, bool classic) {
     size_t n = s.cur_n;
     if (!n) return KZGB_BADARGS;
     CK(cudaSetDevice(s.device));
@@ -402,14 +494,17 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     CK(cudaStreamWaitEvent(sS3, s.ev[11], 0));
     CK(cudaStreamWaitEvent(s.stream4, s.ev[11], 0));
     CK(cudaStreamWaitEvent(sS1, s.ev[11], 0));
+    auto reduce = [&](cudaStream_t q, const MsmPlan& plan, MsmWorkspace& w, bool want_all) {
+        if (classic) msm_window_sums_stage(q, plan, w, want_all); else msm_slices_stage(q, plan, w, want_all);
+    };
     msm_accumulate_stage(s.stream4, s.planZ, s.pts + 2 * n, 2 * (n + 1), wz);    // S2' over pi_i, G and their phi images
-    msm_window_sums_stage(s.stream4, s.planZ, wz, false);
+    reduce(s.stream4, s.planZ, wz, false);
     CK(cudaEventRecord(s.ev[13], s.stream4));
     msm_accumulate_stage(sS3, s.planR, s.pts + 2 * n, n, wr2);                   // S3 over pi_i
-    msm_window_sums_stage(sS3, s.planR, wr2, s.sg_batch);
+    reduce(sS3, s.planR, wr2, s.sg_batch);
     CK(cudaEventRecord(s.ev[12], sS3));
     msm_accumulate_stage(sS1, s.planR, s.pts, n, wr);                            // S1 over C_i
-    msm_window_sums_stage(sS1, s.planR, wr, s.sg_batch);
+    reduce(sS1, s.planR, wr, s.sg_batch);
     CK(cudaEventRecord(s.ev[16], sS1));
     if (s.sg_batch) {
         // batched subgroup check: 128 slice sums of the S3 buckets (all pi_i) and of the S1 buckets (all C_i)
@@ -423,14 +518,39 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     CK(cudaStreamWaitEvent(st, s.ev[13], 0));
     CK(cudaStreamWaitEvent(st, s.ev[16], 0));
     CK(cudaEventRecord(s.ev[6], st));
-    const MsmPlan* plans[3] = {&s.planR, &s.planR, &s.planZ};
-    MsmWorkspace* wss[3] = {&wr, &wr2, &wz};
-    G1Jac* outs[3] = {s.sums + 0, s.sums + 2, s.sums + 1};
-    msm_combine_stage(st, plans, wss, outs, 3);
-    launch_make_partial(st, s.sums + 0, s.sums + 1, s.sums + 2, s.sum_ry, s.partial_dev);
-    CK(cudaMemcpyAsync(s.h_partial, s.partial_dev, KZGB_PARTIAL_BYTES, cudaMemcpyDeviceToHost, st));
+    s.ws_keep[0] = wr; s.ws_keep[1] = wr2; s.ws_keep[2] = wz;
+    if (classic) {
+        const MsmPlan* plans[3] = {&s.planR, &s.planR, &s.planZ};
+        MsmWorkspace* wss[3] = {&wr, &wr2, &wz};
+        G1Jac* outs[3] = {s.sums + 0, s.sums + 2, s.sums + 1};
+        msm_combine_stage(st, plans, wss, outs, 3);
+        launch_make_partial(st, s.sums + 0, s.sums + 1, s.sums + 2, s.sum_ry, s.partial_dev);
+        CK(cudaMemcpyAsync(s.h_partial, s.partial_dev, KZGB_PARTIAL_BYTES, cudaMemcpyDeviceToHost, st));
+        s.have_sums = true;
+        s.sums_pending = false;
+    } else {
+        const MpSumDesc d1 = {wr.slices, wr.buckets, s.planR.c, s.planR.W, s.planR.nbits};
+        const MpSumDesc d2 = {wz.slices, wz.buckets, s.planZ.c, s.planZ.W, s.planZ.nbits};
+        const MpSumDesc d3 = {wr2.slices, wr2.buckets, s.planR.c, s.planR.W, s.planR.nbits};
+        launch_mp_terms(st, d1, d2, d3, s.mp_terms);
+        s.have_sums = false;
+        s.sums_pending = true;
+    }
     CK(cudaEventRecord(s.ev[7], st));
     if (!s.sg_batch) CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    return KZGB_OK;
+}
+// S1, S2', S3 of the last batch by the Horner combine, from the slice sums that are still resident (artefacts only)
+kzgb_ret deferred_sums(DeviceSlot& s) {
+    if (!s.sums_pending) return KZGB_OK;
+    CK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
+    const MsmPlan* plans[3] = {&s.planR, &s.planR, &s.planZ};
+    MsmWorkspace* wss[3] = {&s.ws_keep[0], &s.ws_keep[1], &s.ws_keep[2]};
+    G1Jac* outs[3] = {s.sums + 0, s.sums + 2, s.sums + 1};
+    for (int j = 0; j < 3; ++j) msm_winsums_stage(st, *plans[j], *wss[j]);
+    msm_combine_stage(st, plans, wss, outs, 3);
+    s.sums_pending = false;
     s.have_sums = true;
     return KZGB_OK;
 }
@@ -447,6 +567,7 @@ kzgb_ret finish_subgroup(DeviceSlot& s) {
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     s.have_sums = false;
+    s.sums_pending = false;
     return KZGB_OK;
 }
 
@@ -464,6 +585,19 @@ kzgb_ret combine(DeviceSlot& s, const uint8_t* partials, int np, bool* ok) {
     CK(cudaGetLastError());
     *ok = s.h_small[16] == 1;
     s.have_ab = true;
+    return KZGB_OK;
+}
+
+// Pairing check on the terms of n_shards shards resident in terms_dev (device memory of s)
+kzgb_ret mp_finish(DeviceSlot& s, const G1Xyzz* terms_dev, int n_shards, const G2Lines* tab, bool* ok) {
+    cudaStream_t st = s.stream;
+    launch_mp_coefs(st, terms_dev, n_shards, s.mp_coef);
+    launch_mp_check(st, tab, s.mp_coef, s.mp_part, s.mp_F, s.result_dev);
+    CK(cudaMemcpyAsync(s.h_small + 16, s.result_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(s.ev[8], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    *ok = s.h_small[16] == 1;
     return KZGB_OK;
 }
 
@@ -501,61 +635,82 @@ kzgb_ret verify_common(bool* ok, const uint8_t* C, const uint8_t* z, const uint8
     std::vector<size_t> lo(G + 1);
     for (size_t g = 0; g <= G; ++g) { size_t c = nch * g / G * KZGB_CHUNK; lo[g] = c < n ? c : n; }
     lo[G] = n;
+    const bool classic = ctx->slots[0].classic;
+    ctx->terms_combined = false;
     std::vector<uint8_t> digests(32 * nch);
-    for (size_t g = 0; g < G; ++g) {
+    std::vector<kzgb_ret> rcs(G, KZGB_OK);
+    auto first_error = [&]() { for (kzgb_ret r : rcs) if (r) return r; return KZGB_OK; };
+    // phase 1 on every shard at once (one host thread per device): copies, hashes, K1; returns with the digests
+    ctx->pool.run(G, [&](size_t g) {
         size_t a = lo[g], m = lo[g + 1] - a;
-        kzgb_ret rc = phase1(ctx->slots[g], C + 48 * a, z + 32 * a, y + 32 * a, pi + 48 * a, m, on_device,
-                             digests.data() + 32 * (a / KZGB_CHUNK));
-        if (rc) return rc;
-    }
+        rcs[g] = phase1(ctx->slots[g], C + 48 * a, z + 32 * a, y + 32 * a, pi + 48 * a, m, on_device,
+                        digests.data() + 32 * (a / KZGB_CHUNK));
+    });
+    if (kzgb_ret rc = first_error()) return rc;
     uint8_t root[32] = {0};
     auto t0 = std::chrono::steady_clock::now();
     if (!single) host_sha256_root(root, digests.data(), nch, n);
     float root_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    for (size_t g = 0; g < G; ++g) {
-        kzgb_ret rc = phase2(ctx->slots[g], root, lo[g], single);
-        if (rc) return rc;
-    }
-    std::vector<uint8_t> parts(KZGB_PARTIAL_BYTES * G);
-    uint32_t badp = 0, bads = 0;
-    // One slot with the batched subgroup check: the pairing does not wait for the check's verdict (its serial
-    // |x|^2 chains finish while the Miller loop runs); the counters are read after both.
-    const bool speculate = G == 1 && ctx->slots[0].sg_batch;
-    for (size_t g = 0; g < G; ++g) {
+    // One slot with the batched subgroup check: the pairing does not wait for the check's verdict (its |x|^2 chains
+    // finish while the Miller loop runs); the counters are read after both.
+    const bool lone = G == 1 && !classic;
+    std::vector<uint32_t> badp_v(G, 0), bads_v(G, 0);
+    ctx->pool.run(G, [&](size_t g) {
         DeviceSlot& s = ctx->slots[g];
-        CK(cudaSetDevice(s.device));
-        CK(cudaStreamSynchronize(s.stream));
-        CK(cudaGetLastError());
-        if (!speculate) {
-            kzgb_ret frc = finish_subgroup(s);
-            if (frc) return frc;
-            badp += s.h_small[0];
-            bads += s.h_small[1];
-        }
-        memcpy(parts.data() + KZGB_PARTIAL_BYTES * g, s.h_partial, KZGB_PARTIAL_BYTES);
-    }
+        rcs[g] = phase2(s, root, lo[g], single, classic);
+        if (rcs[g] || lone) return;
+        auto body = [&]() -> kzgb_ret {
+            if (!classic) CK(cudaMemcpyAsync(s.h_terms, s.mp_terms, sizeof(G1Xyzz) * KZ_MP_PAIRS, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaStreamSynchronize(s.stream));
+            CK(cudaGetLastError());
+            if (kzgb_ret frc = finish_subgroup(s)) return frc;
+            badp_v[g] = s.h_small[0];
+            bads_v[g] = s.h_small[1];
+            return KZGB_OK;
+        };
+        rcs[g] = body();
+    });
+    if (kzgb_ret rc = first_error()) return rc;
+    uint32_t badp = 0, bads = 0;
+    for (size_t g = 0; g < G; ++g) { badp += badp_v[g]; bads += bads_v[g]; }
     kzgb_artifacts& art = ctx->art;
     memset(&art, 0, sizeof art);
     art.n = n;
     memcpy(art.root, root, 32);
     DeviceSlot& s0 = ctx->slots[0];
+    CK(cudaSetDevice(s0.device));
     kzgb_ret rc = KZGB_OK;
-    if (!(badp || bads)) rc = combine(s0, parts.data(), (int)G, ok);
-    if (speculate) {
-        kzgb_ret frc = finish_subgroup(s0);
-        if (frc) return frc;
+    ctx->n_shards_last = (int)G;
+    if (lone) {
+        rc = mp_finish(s0, s0.mp_terms, 1, s0.mp_tab, ok);
+        if (!rc) rc = finish_subgroup(s0);
         badp = s0.h_small[0];
         bads = s0.h_small[1];
+    } else if (!(badp || bads)) {
+        if (classic) {
+            std::vector<uint8_t> parts(KZGB_PARTIAL_BYTES * G);
+            for (size_t g = 0; g < G; ++g) memcpy(parts.data() + KZGB_PARTIAL_BYTES * g, ctx->slots[g].h_partial, KZGB_PARTIAL_BYTES);
+            rc = combine(s0, parts.data(), (int)G, ok);
+        } else {
+            // "combined on the host": every shard's 66 terms came back through its pinned mailbox; the root device adds them
+            for (size_t g = 0; g < G; ++g)
+                CK(cudaMemcpyAsync(s0.mp_terms_in + g * KZ_MP_PAIRS, ctx->slots[g].h_terms, sizeof(G1Xyzz) * KZ_MP_PAIRS,
+                                   cudaMemcpyHostToDevice, s0.stream));
+            rc = mp_finish(s0, s0.mp_terms_in, (int)G, s0.mp_tab, ok);
+            s0.have_ab = false;
+            ctx->terms_combined = !rc;
+            ctx->ab_terms = s0.mp_terms_in; ctx->ab_shards = (int)G; ctx->ab_gather_sum_ry = true;
+        }
     }
     art.n_bad_points = badp;
     art.n_bad_scalars = bads;
-    if (badp || bads) {
-        *ok = false;
-        for (auto& s : ctx->slots) { s.have_sums = false; s.have_ab = false; }
-        return KZGB_BADARGS;
+    if (rc || badp || bads) {
+        *ok = false;                                        // never leave a verdict next to an error code
+        for (auto& s : ctx->slots) { s.have_sums = false; s.have_ab = false; s.sums_pending = false; }
+        ctx->terms_combined = false;
+        return rc ? rc : KZGB_BADARGS;
     }
-    if (rc) return rc;
-    if (G > 1) s0.have_sums = false;
+    if (G > 1) { s0.have_sums = false; s0.sums_pending = false; }
     fill_stage_ms(art, s0, root_ms);
     art.stage_ms[8] = ev_ms(s0.ev[7], s0.ev[8]);
     art.stage_ms[9] = ev_ms(s0.ev[0], s0.ev[8]);
@@ -587,12 +742,14 @@ kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const ui
         if (rc) { kzgb_ctx_free(c); return rc; }
     }
     memset(&c->art, 0, sizeof c->art);
+    if (nd > 1) c->pool.start((size_t)nd - 1);
     c->launches_at_create = g_kzgb_launches.load();
     *out = c;
     return KZGB_OK;
 }
 void kzgb_ctx_free(kzgb_ctx* c) {
     if (!c) return;
+    c->pool.stop();
     for (auto& s : c->slots) slot_free(s);
     delete c;
 }
@@ -639,7 +796,7 @@ kzgb_ret kzgb_shard_phase2(kzgb_ctx* ctx, int slot, const uint8_t root[32], uint
                            uint8_t partial_out[KZGB_PARTIAL_BYTES]) {
     if (!ctx || slot < 0 || slot >= (int)ctx->slots.size() || !root || !partial_out) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[slot];
-    kzgb_ret rc = phase2(s, root, global_offset, false);
+    kzgb_ret rc = phase2(s, root, global_offset, false, true);
     if (rc) return rc;
     CK(cudaStreamSynchronize(s.stream));
     CK(cudaGetLastError());
@@ -765,6 +922,7 @@ kzgb_ret kzgb_g1_decompress_batch(uint8_t* affine_out, uint8_t* status_out, cons
     CK(cudaFree(d_be));
     CK(cudaGetLastError());
     s.have_sums = false;
+    s.sums_pending = false;
     return KZGB_OK;
 }
 
@@ -835,6 +993,7 @@ kzgb_ret kzgb_g1_msm(uint8_t affine_out[96], const uint8_t* points_affine, const
     CK(cudaFree(d_pts)); CK(cudaFree(d_sc));
     CK(cudaGetLastError());
     s.have_sums = false;
+    s.sums_pending = false;
     ctx->msm_ms[0] = ev_ms(s.ev[0], s.ev[1]);
     ctx->msm_ms[1] = ev_ms(s.ev[1], s.ev[2]);
     ctx->msm_ms[2] = ev_ms(s.ev[2], s.ev[3]);
@@ -871,7 +1030,7 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
         CK(dmalloc(s.d_cells, 2048 * m)); CK(dmalloc(s.d_ci, m)); CK(dmalloc(s.d_xi, m)); CK(dmalloc(s.cell_coefs, 64 * m));
         s.cell_cap = m;
     }
-    s.have_sums = false; s.have_ab = false; s.cur_n = 0;
+    s.have_sums = false; s.have_ab = false; s.sums_pending = false; s.cur_n = 0;
     kzgb_artifacts& art = ctx->art;
     memset(&art, 0, sizeof art);
     art.n = m;
@@ -930,7 +1089,7 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
         msm_sort_stage(sb, planB, s.r, 4, m, wsB);
         save_ws(s.sortR, wsB);
         msm_accumulate_stage(sb, planB, s.pts, m, wsB);
-        msm_window_sums_stage(sb, planB, wsB, sg);
+        if (s.classic) msm_window_sums_stage(sb, planB, wsB, sg); else msm_slices_stage(sb, planB, wsB, sg);
         CK(cudaEventRecord(s.ev[12], sb));
         if (sg) {
             launch_sg_check(sb, planB, wsB, wsB, s.counters, 1);
@@ -949,16 +1108,25 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     msm_sort_stage(st, planA, s.zs, 4, mm, wsA);
     save_ws(s.sortZ, wsA);
     msm_accumulate_stage(st, planA, s.pts, mm, wsA);
-    msm_window_sums_stage(st, planA, wsA, false);
+    if (s.classic) msm_window_sums_stage(st, planA, wsA, false); else msm_slices_stage(st, planA, wsA, false);
     CK(cudaStreamWaitEvent(st, s.ev[12], 0));
-    {
+    ctx->terms_combined = false;
+    if (s.classic) {
         const MsmPlan* plans[2] = {&planA, &planB};
         MsmWorkspace* wss[2] = {&wsA, &wsB};
         G1Jac* outs[2] = {s.sums + 0, s.sums + 2};
         msm_combine_stage(st, plans, wss, outs, 2);
+        launch_set_ab(st, s.sums + 0, s.sums + 2, s.sums + 3);
+        launch_pairing(st, s.lines_cell, s.sums + 3, s.result_dev);
+    } else {
+        // A-side sum and -(B-side sum) as 2 x 33 pairing terms against the multiples of (G2, [tau^64]G2)
+        const MpSumDesc dA = {wsA.slices, wsA.buckets, planA.c, planA.W, planA.nbits};
+        const MpSumDesc dNone = {nullptr, nullptr, 0, 0, -1};
+        const MpSumDesc dB = {wsB.slices, wsB.buckets, planB.c, planB.W, planB.nbits};
+        launch_mp_terms(st, dA, dNone, dB, s.mp_terms);
+        launch_mp_coefs(st, s.mp_terms, 1, s.mp_coef);
+        launch_mp_check(st, s.mp_tab_cell, s.mp_coef, s.mp_part, s.mp_F, s.result_dev);
     }
-    launch_set_ab(st, s.sums + 0, s.sums + 2, s.sums + 3);
-    launch_pairing(st, s.lines_cell, s.sums + 3, s.result_dev);
     CK(cudaMemcpyAsync(s.h_small + 16, s.result_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
     if (!sg) CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(s.ev[8], st));
@@ -979,7 +1147,8 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     art.n_bad_scalars = s.h_small[1];
     art.stage_ms[9] = ev_ms(s.ev[0], s.ev[8]);
     if (s.h_small[0] || s.h_small[1]) return KZGB_BADARGS;
-    s.have_ab = true;
+    if (s.classic) s.have_ab = true;
+    else { ctx->terms_combined = true; ctx->ab_terms = s.mp_terms; ctx->ab_shards = 1; ctx->ab_gather_sum_ry = false; }
     *ok = s.h_small[16] == 1;
     return KZGB_OK;
 }
@@ -1002,6 +1171,7 @@ kzgb_ret kzgb_pairing_check(bool* ok, const uint8_t A_affine[96], const uint8_t 
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     s.have_sums = false;
+    s.sums_pending = false;
     if (s.h_small[0]) return KZGB_BADARGS;
     *ok = s.h_small[16] == 1;
     return KZGB_OK;
@@ -1010,6 +1180,26 @@ kzgb_ret kzgb_pairing_check(bool* ok, const uint8_t A_affine[96], const uint8_t 
 kzgb_ret kzgb_last_artifacts(kzgb_ctx* ctx, kzgb_artifacts* out) {
     if (!ctx || !out) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[0];
+    if (s.sums_pending) { if (kzgb_ret rc = deferred_sums(s)) return rc; }
+    if (ctx->terms_combined) {
+        // several shards, or a cell batch: A and B by Horner over the combined pairing terms (cold path)
+        if (ctx->ab_gather_sum_ry) {
+            for (int g = 0; g < ctx->ab_shards; ++g) {
+                DeviceSlot& sg = ctx->slots[g];
+                CK(cudaSetDevice(sg.device));
+                CK(cudaMemcpy(s.h_small + 32, sg.sum_ry, 32, cudaMemcpyDeviceToHost));
+                CK(cudaSetDevice(s.device));
+                CK(cudaMemcpy(s.scratch + 8192 + 32 * g, s.h_small + 32, 32, cudaMemcpyHostToDevice));
+            }
+            CK(cudaSetDevice(s.device));
+            launch_fr_sum(s.stream, (const uint32_t*)(s.scratch + 8192), ctx->ab_shards, s.sum_ry);
+        }
+        CK(cudaSetDevice(s.device));
+        launch_mp_ab(s.stream, ctx->ab_terms, ctx->ab_shards, s.sums + 3);
+        s.have_ab = true;
+        s.have_sums = false;
+        ctx->terms_combined = false;
+    }
     if (s.have_sums) {
         CK(cudaSetDevice(s.device));
         launch_artifacts(s.stream, s.sums + 0, s.sums + 1, s.sums + 2, s.sum_ry, s.g1_pt, s.scratch);

@@ -1,0 +1,207 @@
+// Kernels of the Horner-free pairing check (mpair.cuh): one-time line tables for the 2 x 33 fixed G2 multiples, then
+// per batch  terms -> coefficients -> line products (all SMs) -> merge -> serial check (one block).
+#include "kernels.h"
+#include "mpair.cuh"
+
+// ------------------------------------------------------------------ one-time setup
+// chain[b][t] = [2^(4t)] Q_b for the two G2 setup points (affine twist coordinates); status[b] = 1 on success
+__global__ void k_mp_setup_chain(const u8* __restrict__ g2_bytes, G2Aff* chain, int* status) {
+    const int b = blockIdx.x;
+    if (threadIdx.x) return;
+    if (b == 0) status[2] = 1;                       // cleared by k_mp_setup_lines on a degenerate step
+    G2Aff q;
+    bool ok = g2_decompress(q, g2_bytes + 96 * b);
+    Fp2 la, lb;
+    for (int t = 0; ok && t < KZ_MP_TERMS; ++t) {
+        chain[b * KZ_MP_TERMS + t] = q;
+        for (int u = 0; ok && u < KZ_MP_G && t + 1 < KZ_MP_TERMS; ++u) ok = g2_dbl_step(q, la, lb);
+    }
+    status[b] = ok ? 1 : 0;
+}
+// lines of the Miller loop for each of the 66 points; one working thread per block (data-dependent inversion loops)
+__global__ void k_mp_setup_lines(const G2Aff* __restrict__ chain, G2Lines* tab, int* status) {
+    if (threadIdx.x) return;
+    G2Aff out;
+    if (!g2_mul_xabs(out, chain[blockIdx.x], &tab[blockIdx.x])) atomicExch(status + 2, 0);
+}
+void launch_mp_setup(cudaStream_t s, const uint8_t* g2_bytes, G2Aff* chain, G2Lines* tab, int* status) {
+    k_mp_setup_chain<<<2, 32, 0, s>>>(g2_bytes, chain, status);
+    KZ_COUNT_LAUNCH();
+    k_mp_setup_lines<<<KZ_MP_PAIRS, 32, 0, s>>>(chain, tab, status);
+    KZ_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------ per batch
+// terms[t] = V_t(S1) + V_t(S2'),  terms[33 + t] = -V_t(S3).  Two terms per block: quads (term, sum).
+__global__ void __launch_bounds__(32) k_mp_terms(const MpSumDesc s1, const MpSumDesc s2, const MpSumDesc s3, G1Xyzz* __restrict__ terms) {
+    __shared__ Fp qsm[8 * KZ_QUAD_SLOTS];
+    __shared__ G1Xyzz ex[2];
+    const int qi = threadIdx.x >> 2, tt = qi / 3, sum = qi - 3 * tt, t = blockIdx.x * 2 + tt;
+    const bool active = qi < 6 && t < KZ_MP_TERMS;
+    Quad q = quad_make(qsm, qi);
+    G1Xyzz acc = xyzz_inf();
+    if (active) {
+        const MpSumDesc d = sum == 0 ? s1 : (sum == 1 ? s2 : s3);
+        acc = mp_term(q, d, t);
+    }
+    if (active && sum == 1 && q.ql == 0) ex[tt] = acc;
+    __syncthreads();
+    if (active && sum == 0) {
+        acc = quad_xyzz_add(q, acc, ex[tt]);
+        if (q.ql == 0) terms[t] = acc;
+    }
+    if (active && sum == 2 && q.ql == 0) terms[KZ_MP_TERMS + t] = xyzz_neg(acc);
+}
+void launch_mp_terms(cudaStream_t s, const MpSumDesc& s1, const MpSumDesc& s2, const MpSumDesc& s3, G1Xyzz* terms) {
+    k_mp_terms<<<(KZ_MP_TERMS + 1) / 2, 32, 0, s>>>(s1, s2, s3, terms);
+    KZ_COUNT_LAUNCH();
+}
+// pair p: sum over the shards' terms, then the three products every line of the pair needs
+__global__ void __launch_bounds__(32) k_mp_coefs(const G1Xyzz* __restrict__ terms_in, int n_shards, MpCoef* __restrict__ coef) {
+    __shared__ Fp qsm[8 * KZ_QUAD_SLOTS];
+    const int qi = threadIdx.x >> 2, p = blockIdx.x * 8 + qi;
+    if (p >= KZ_MP_PAIRS) return;
+    Quad q = quad_make(qsm, qi);
+    G1Xyzz acc = terms_in[p];
+    for (int g = 1; g < n_shards; ++g) acc = quad_xyzz_add(q, acc, terms_in[(size_t)g * KZ_MP_PAIRS + p]);
+    MpCoef c;
+    Fp d0;
+    quad_mul4(q, acc.ZZ, acc.ZZZ, acc.X, acc.ZZZ, acc.Y, acc.ZZ, acc.Y, acc.ZZ, c.alpha, c.beta, c.gamma, d0);
+    c.inf = xyzz_is_inf(acc) ? 1u : 0u;
+    c.pad[0] = c.pad[1] = c.pad[2] = 0;
+    if (q.ql == 0) coef[p] = c;
+}
+void launch_mp_coefs(cudaStream_t s, const G1Xyzz* terms_in, int n_shards, MpCoef* coef) {
+    k_mp_coefs<<<(KZ_MP_PAIRS + 7) / 8, 32, 0, s>>>(terms_in, n_shards, coef);
+    KZ_COUNT_LAUNCH();
+}
+
+// Line products.  Block (step s, group g) evaluates the lines of step s at the pairs p = g, g + NG, ... and multiplies
+// them with a tree of Fp12 products, MP_UNITS products per pass.  part[s * NG + g] = the group's product.
+#define MP_UNITS 2
+#define MP_NG 2
+#define MP_POOL ((KZ_MP_PAIRS + MP_NG - 1) / MP_NG)
+__global__ void __launch_bounds__(128 * MP_UNITS) k_mp_lines(const G2Lines* __restrict__ tab, const MpCoef* __restrict__ coef,
+                                                              Fp12* __restrict__ part) {
+    __shared__ Fp12 pool[MP_POOL];
+    __shared__ MpUnit units[MP_UNITS];
+    const int s = blockIdx.x, grp = blockIdx.y;
+    const int unit = threadIdx.x >> 7, tu = threadIdx.x & 127;
+    const int nl = (KZ_MP_PAIRS - grp + MP_NG - 1) / MP_NG;
+    // line values as dense Fp12: l = a alpha + (b beta) w^2 + gamma w^3; a pair at infinity contributes 1
+    for (int idx = threadIdx.x; idx < nl * 12; idx += blockDim.x) {
+        const int l = idx / 12, ci = idx - 12 * l, p = grp + l * MP_NG;
+        const MpCoef& cf = coef[p];
+        const G2Lines& T = tab[p];
+        const bool inf = cf.inf != 0;
+        Fp v = fp_zero();
+        if (!inf && (ci < 2 || ci == 4 || ci == 5)) {
+            const Fp2& src = ci < 2 ? T.a[s] : T.b[s];
+            v = fp_mul((ci & 1) ? src.c1 : src.c0, ci < 2 ? cf.alpha : cf.beta);
+        } else if (!inf && ci == 6) v = cf.gamma;
+        else if (inf && ci == 0) v = fp_one();
+        if (ci & 1) pool[l].c[ci >> 1].c1 = v; else pool[l].c[ci >> 1].c0 = v;
+    }
+    __syncthreads();
+    int n = nl;
+    while (n > 1) {
+        const int m = n >> 1;
+        for (int base = 0; base < m; base += MP_UNITS) {
+            const int k = base + unit;
+            if (k < m) mp_mul_products(units[unit], tu, pool[2 * k], pool[2 * k + 1]);
+            __syncthreads();
+            if (k < m) mp_mul_fold(units[unit], tu, pool[k]);
+            __syncthreads();
+        }
+        if (n & 1) {
+            if (threadIdx.x < 12) {
+                const int k = threadIdx.x >> 1;
+                if (threadIdx.x & 1) pool[m].c[k].c1 = pool[n - 1].c[k].c1; else pool[m].c[k].c0 = pool[n - 1].c[k].c0;
+            }
+            n = m + 1;
+            __syncthreads();
+        } else n = m;
+    }
+    if (threadIdx.x < 12) {
+        const int k = threadIdx.x >> 1;
+        Fp12& dst = part[s * MP_NG + grp];
+        if (threadIdx.x & 1) dst.c[k].c1 = pool[0].c[k].c1; else dst.c[k].c0 = pool[0].c[k].c0;
+    }
+}
+// F[it] = product of the partial products of iteration it (its doubling step and, where bit 62 - it of |x| is set, the
+// addition step that follows)
+__global__ void __launch_bounds__(128) k_mp_merge(const Fp12* __restrict__ part, Fp12* __restrict__ F) {
+    __shared__ MpUnit U;
+    __shared__ Fp12 acc, y;
+    const int it = blockIdx.x;
+    bool has_add;
+    const int s0 = mp_step_of_iter(it, has_add);
+    const int cnt = MP_NG * (has_add ? 2 : 1);
+    const Fp12* src = part + (size_t)s0 * MP_NG;          // the addition step's partials follow the doubling step's
+    if (threadIdx.x < 12) {
+        const int k = threadIdx.x >> 1;
+        if (threadIdx.x & 1) acc.c[k].c1 = src[0].c[k].c1; else acc.c[k].c0 = src[0].c[k].c0;
+    }
+    __syncthreads();
+    for (int i = 1; i < cnt; ++i) {
+        if (threadIdx.x < 12) {
+            const int k = threadIdx.x >> 1;
+            if (threadIdx.x & 1) y.c[k].c1 = src[i].c[k].c1; else y.c[k].c0 = src[i].c[k].c0;
+        }
+        __syncthreads();
+        mp_mul(U, acc, acc, y);
+    }
+    if (threadIdx.x < 12) {
+        const int k = threadIdx.x >> 1;
+        if (threadIdx.x & 1) F[it].c[k].c1 = acc.c[k].c1; else F[it].c[k].c0 = acc.c[k].c0;
+    }
+}
+// The serial part: Miller accumulation f <- f^2 F_it, conjugation (x < 0), inversion-free final check.
+__global__ void __launch_bounds__(128) k_mp_check(const Fp12* __restrict__ F, int* __restrict__ result) {
+    __shared__ MpScratch S;
+    const int t = threadIdx.x, k = t >> 1;
+    if (t < 12) { if (t & 1) S.f.c[k].c1 = F[0].c[k].c1; else S.f.c[k].c0 = F[0].c[k].c0; }
+    __syncthreads();
+    for (int it = 1; it < KZ_MP_ITERS; ++it) {
+        Fp pre;                                                       // next factor: the load hides under the squaring
+        if (t < 12) pre = (t & 1) ? F[it].c[k].c1 : F[it].c[k].c0;
+        mp_mul_products(S.U, t, S.f, S.f);
+        __syncthreads();
+        mp_mul_fold(S.U, t, S.f);
+        if (t < 12) { if (t & 1) S.fb.c[k].c1 = pre; else S.fb.c[k].c0 = pre; }
+        __syncthreads();
+        mp_mul_products(S.U, t, S.f, S.fb);
+        __syncthreads();
+        mp_mul_fold(S.U, t, S.f);
+        __syncthreads();
+    }
+    coop_conj(S.f, S.f);
+    mp_final_check(S);
+    if (t == 0) *result = S.result;
+}
+void launch_mp_check(cudaStream_t s, const G2Lines* tab, const MpCoef* coef, Fp12* part, Fp12* F, int* result) {
+    k_mp_lines<<<dim3(KZ_N_LINES, MP_NG), 128 * MP_UNITS, 0, s>>>(tab, coef, part);
+    KZ_COUNT_LAUNCH();
+    k_mp_merge<<<KZ_MP_ITERS, 128, 0, s>>>(part, F);
+    KZ_COUNT_LAUNCH();
+    k_mp_check<<<1, 128, 0, s>>>(F, result);
+    KZ_COUNT_LAUNCH();
+}
+// A = sum_t 2^(4t) (sum of the shards' A-side terms), B likewise from the B-side terms (already negated): artefacts only
+__global__ void __launch_bounds__(32) k_mp_ab(const G1Xyzz* __restrict__ terms_in, int n_shards, G1Jac* __restrict__ AB) {
+    __shared__ Fp qsm[8 * KZ_QUAD_SLOTS];
+    const int qi = threadIdx.x >> 2;
+    if (qi >= 2) return;
+    Quad q = quad_make(qsm, qi);
+    G1Xyzz acc = xyzz_inf();
+    for (int t = KZ_MP_TERMS - 1; t >= 0; --t) {
+        for (int u = 0; u < KZ_MP_G; ++u) acc = quad_xyzz_dbl(q, acc);
+        for (int g = 0; g < n_shards; ++g) acc = quad_xyzz_add(q, acc, terms_in[(size_t)g * KZ_MP_PAIRS + qi * KZ_MP_TERMS + t]);
+    }
+    if (q.ql == 0) AB[qi] = xyzz_to_jac(acc);
+}
+void launch_mp_ab(cudaStream_t s, const G1Xyzz* terms_in, int n_shards, G1Jac* AB) {
+    k_mp_ab<<<1, 32, 0, s>>>(terms_in, n_shards, AB);
+    KZ_COUNT_LAUNCH();
+}
+size_t mp_part_entries() { return (size_t)KZ_N_LINES * MP_NG; }

@@ -120,6 +120,22 @@ void launch_fr_to_be(cudaStream_t s, const uint32_t* in, uint8_t* out32) {
     KZ_COUNT_LAUNCH();
 }
 
+// out = sum of m canonical Fr values (8 limbs each) mod r
+__global__ void k_fr_sum(const u32* in, int m, u32* out) {
+    if (threadIdx.x) return;
+    Fr acc = fr_zero();
+    for (int i = 0; i < m; ++i) {
+        Fr v;
+        for (int k = 0; k < 8; ++k) v.v[k] = in[8 * i + k];
+        acc = fr_add(acc, v);
+    }
+    for (int k = 0; k < 8; ++k) out[k] = acc.v[k];
+}
+void launch_fr_sum(cudaStream_t s, const uint32_t* in, int m, uint32_t* out) {
+    k_fr_sum<<<1, 32, 0, s>>>(in, m, out);
+    KZ_COUNT_LAUNCH();
+}
+
 // Jacobian -> canonical affine bytes (one inversion per point; cold: stage exports only)
 __global__ void k_jac_to_affine_be(const G1Jac* __restrict__ in, int m, u8* __restrict__ out) {
     int t = threadIdx.x;

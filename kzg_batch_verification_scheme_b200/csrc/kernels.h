@@ -8,6 +8,7 @@
 
 #include "msm.cuh"
 #include "pairing.cuh"
+#include "mpair.cuh"
 
 extern std::atomic<uint64_t> g_kzgb_launches;      // counts every kernel launch of this library
 #define KZ_COUNT_LAUNCH() (g_kzgb_launches.fetch_add(1, std::memory_order_relaxed))
@@ -95,8 +96,23 @@ void launch_artifacts(cudaStream_t s, const G1Jac* s1, const G1Jac* s2p, const G
                       const Fp* g1_pt, uint8_t* out /*5*96 + 32*/);
 void launch_set_ab(cudaStream_t s, const G1Jac* a, const G1Jac* b, G1Jac* AB);
 void launch_fr_to_be(cudaStream_t s, const uint32_t* in, uint8_t* out32);
+void launch_fr_sum(cudaStream_t s, const uint32_t* in, int m, uint32_t* out);       // out = sum of m canonical Fr (8 limbs each)
 void launch_jac_to_affine_be(cudaStream_t s, const G1Jac* in, int m, uint8_t* out96);   // m <= 32
 void launch_pairing_debug(cudaStream_t s, int op, const G2Lines* lines, const uint8_t* in, uint8_t* out);
+
+// ---- k_mpair.cu (Horner-free pairing check, mpair.cuh)
+// one-time: chain[2][33] = [2^(4t)] of the two G2 points in g2_bytes (2 x 96 B compressed), tab[66] = their Miller lines;
+// status[0..1] = chain ok, status[2] = lines ok
+void launch_mp_setup(cudaStream_t s, const uint8_t* g2_bytes, G2Aff* chain, G2Lines* tab, int* status);
+// terms[0..33) = V_t(s1) + V_t(s2), terms[33..66) = -V_t(s3)
+void launch_mp_terms(cudaStream_t s, const MpSumDesc& s1, const MpSumDesc& s2, const MpSumDesc& s3, G1Xyzz* terms);
+// coef[66] from the terms of n_shards shards (terms_in[g * 66 + p])
+void launch_mp_coefs(cudaStream_t s, const G1Xyzz* terms_in, int n_shards, MpCoef* coef);
+// line products (all SMs), merge, serial check; part: mp_part_entries() Fp12, F: 63 Fp12; *result = 1 iff the product is one
+void launch_mp_check(cudaStream_t s, const G2Lines* tab, const MpCoef* coef, Fp12* part, Fp12* F, int* result);
+size_t mp_part_entries();
+// artefacts: AB[0] = A, AB[1] = B (Jacobian) by Horner over the shards' terms
+void launch_mp_ab(cudaStream_t s, const G1Xyzz* terms_in, int n_shards, G1Jac* AB);
 
 // ---- k_cells.cu (cell batch, BASELINE.json config[4])
 void launch_cell_twiddles(cudaStream_t s, Fr* W /*8192*/);

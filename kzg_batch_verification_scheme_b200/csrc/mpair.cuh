@@ -1,0 +1,192 @@
+// Pairing check without the Horner tail (device bodies; kernels in k_mpair.cu).
+//
+// The MSM stage ends with 129 slice sums U_0 .. U_128 per sum (msm.cuh: U_j = sum of the buckets whose magnitude has
+// bit j - c*w set, or the bucket of magnitude 2^k of window w), and the value of the sum is  S = sum_j 2^j U_j.
+// Finishing that on the G1 side is a serial chain of ~128 doublings (0.9 ms on one thread, 0.4 ms on a quad).  By
+// bilinearity the doublings can be pushed onto the FIXED G2 arguments instead:
+//
+//     e(sum_t 2^(4t) V_t, Q) = prod_t e(V_t, [2^(4t)] Q),      V_t = sum_{u<4} 2^u U_(4t+u)     (33 terms per sum)
+//
+// so the check  e(A, G2) e(B, [tau]G2) = 1  becomes a product of 66 pairings against 66 fixed G2 points whose line
+// coefficients are precomputed once per context (33 multiples of G2 and of [tau]G2; 0.86 MB).  Nothing on the G1
+// side is serial any more:
+//   k_mp_terms   3 short Horner chains per term (3 doublings + 4 additions, one quad each)          ~25 product rounds
+//   k_mp_coefs   sum of the shards' terms, then (ZZ ZZZ, X ZZZ, Y ZZ) per pair                        1 round (+ 4 per extra shard)
+//   k_mp_lines   for every Miller step the 66 line values and their product (a tree of Fp12 products, one block per
+//                (step, group), all SMs busy)                                                      ~10 product rounds of latency
+//   k_mp_merge   per Miller iteration: product of the groups' partial products (doubling and addition step)
+//   k_mp_check   the only serial kernel: f <- f^2 F_i over 63 iterations, then the final exponentiation as an
+//                inversion-free equality test (below)
+//
+// Final exponentiation without an inversion.  With u = |x|, m = f^(p^2+1) and 3(p^4-p^2+1)/r = H+ - H-,
+//     H+ = (u+1)^2 (p u^2 + p^3 + u) + 3,      H- = (u+1)^2 (p + u^3 + u p^2)
+// (tools/check_final_exp.py), f^(3(p^12-1)/r) = conj(h)/h for h = m^(H+) / m^(H-), so the product of pairings is one iff
+//     conj(X+) X-  ==  X+ conj(X-),        X+- = m^(H+-),
+// five exponentiations by u on general (non-unitary) elements and no Fp inversion at all.
+//
+// One Fp12 product = one "round": 108 threads each do ONE Montgomery product (Karatsuba parts of the 36 Fp2 partial
+// products), one barrier, then 96 threads fold them (12 outputs x 8 lanes, xor-shuffle tree).  Measured latencies
+// (profiles/r2_fp_latency.txt): product 1792 clk, modular add 80 clk, barrier 21 clk.
+#pragma once
+#include "msm.cuh"
+#include "pairing.cuh"
+#include "quad.cuh"
+
+#define KZ_MP_G 4                                    // bit positions per term
+#define KZ_MP_TERMS 33                               // ceil(129 / KZ_MP_G)
+#define KZ_MP_PAIRS (2 * KZ_MP_TERMS)                // A-side terms, then B-side terms
+#define KZ_MP_ITERS 63                               // Miller iterations (bits 62..0 of |x|)
+
+struct MpCoef { Fp alpha, beta, gamma; u32 inf, pad[3]; };      // line at P: a*alpha + (b*beta) w^2 + gamma w^3
+struct MpSumDesc { const G1Xyzz* slices; const G1Xyzz* buckets; int c, W, nbits; };     // slices == null: the zero sum
+struct MpUnit { Fp kar[108]; };                      // Karatsuba parts of one Fp12 product
+
+// U_j of a sum, j = absolute bit position 0 .. nbits
+KZ_HD G1Xyzz mp_slice(const MpSumDesc& d, int j) {
+    if (!d.slices || j > d.nbits) return xyzz_inf();
+    const int signed_bits = d.c * (d.W - 1);
+    if (j == d.nbits) {                              // magnitude 2^tb of the unsigned top window = the last bucket
+        const int tb = d.nbits - signed_bits;
+        return d.buckets[((size_t)(d.W - 1) << (d.c - 1)) + ((size_t)1 << tb) - 1];
+    }
+    if (j < signed_bits && (j % d.c) == d.c - 1)     // magnitude 2^(c-1) of a signed window
+        return d.buckets[(((size_t)(j / d.c) + 1) << (d.c - 1)) - 1];
+    return d.slices[j];
+}
+// V_t = sum_{u<4} 2^u U_(4t+u) by Horner (quad arithmetic)
+KZ_HD G1Xyzz mp_term(Quad& q, const MpSumDesc& d, int t) {
+    G1Xyzz acc = xyzz_inf();
+    for (int u = KZ_MP_G - 1; u >= 0; --u) {
+        acc = quad_xyzz_dbl(q, acc);
+        acc = quad_xyzz_add(q, acc, mp_slice(d, KZ_MP_G * t + u));
+    }
+    return acc;
+}
+// Miller step index of iteration it (bit 62 - it): doubling step, and whether an addition step follows it
+KZ_HD int mp_step_of_iter(int it, bool& has_add) {
+    const u64 k = ((u64)X_ABS_HI << 32) | X_ABS_LO;
+    int s = 0;
+    for (int i = 62; i > 62 - it; --i) s += 1 + (int)((k >> i) & 1);
+    has_add = (k >> (62 - it)) & 1;
+    return s;
+}
+
+// ------------------------------------------------------------------ one Fp12 product by a unit of 128 threads
+// phase 1 (t < 108): Karatsuba parts v0 = a0 b0, v1 = a1 b1, v2 = (a0+a1)(b0+b1) of the 36 Fp2 partial products
+KZ_HD void mp_mul_products(MpUnit& U, int t, const Fp12& x, const Fp12& y) {
+    if (t < 108) {
+        const int q = t / 3, part = t - 3 * q, i = q / 6, j = q - 6 * i;
+        Fp A, B;
+        if (part == 0) { A = x.c[i].c0; B = y.c[j].c0; }
+        else if (part == 1) { A = x.c[i].c1; B = y.c[j].c1; }
+        else { A = fp_add(x.c[i].c0, x.c[i].c1); B = fp_add(y.c[j].c0, y.c[j].c1); }
+        U.kar[t] = fp_mul(A, B);
+    }
+}
+// phase 2 (after a barrier; t < 96 = three full warps): output o = t / 8 (coefficient k = o / 2, real / imaginary part
+// h = o & 1), lane i = t & 7 holds the contribution of the partial product (i, j) with i + j = k (mod 6):
+//   i + j = k      real  v0 - v1            imaginary  v2 - v0 - v1
+//   i + j = k + 6  real  2 v0 - v2          imaginary  v2 - 2 v1          (times xi = 1 + u)
+// and a xor-shuffle tree adds the six contributions.  dst may alias the operands of phase 1.
+KZ_HD Fp mp_fold_contrib(const MpUnit& U, int o, int i) {
+    const int k = o >> 1, h = o & 1;
+    int j = k - i;
+    const bool hi = j < 0;
+    if (hi) j += 6;
+    const int q = 3 * (i * 6 + j);
+    const Fp v0 = U.kar[q], v1 = U.kar[q + 1], v2 = U.kar[q + 2];
+    // X - Y (+ v0 | - v0 | - v1 | nothing): one subtraction and one addition / subtraction, no divergent arithmetic
+    const Fp X = h ? v2 : v0;
+    const Fp Y = (!h && hi) ? v2 : v1;
+    const Fp T = (h && hi) ? v1 : v0;
+    const Fp d = fp_sub(X, Y), dp = fp_add(d, T), dm = fp_sub(d, T);
+    return h ? dm : (hi ? dp : d);
+}
+#if defined(KZGB_EMU)
+#define MP_TID() 0
+KZ_HD void mp_mul(MpUnit& U, Fp12& dst, const Fp12& x, const Fp12& y) {
+    for (int t = 0; t < 108; ++t) mp_mul_products(U, t, x, y);
+    for (int o = 0; o < 12; ++o) {
+        Fp r = fp_zero();
+        for (int i = 0; i < 6; ++i) r = fp_add(r, mp_fold_contrib(U, o, i));
+        if (o & 1) dst.c[o >> 1].c1 = r; else dst.c[o >> 1].c0 = r;
+    }
+}
+#else
+#define MP_TID() ((int)(threadIdx.x & 127u))
+KZ_HD void mp_mul_fold(const MpUnit& U, int t, Fp12& dst) {
+    if (t < 96) {
+        const int o = t >> 3, i = t & 7;
+        Fp r = i < 6 ? mp_fold_contrib(U, o, i) : fp_zero();
+        KZ_UNROLL for (int s = 4; s; s >>= 1) {
+            Fp ot;
+            KZ_UNROLL for (int l = 0; l < 12; ++l) ot.v[l] = __shfl_xor_sync(0xFFFFFFFFu, r.v[l], s);
+            r = fp_add(r, ot);
+        }
+        if (i == 0) { if (o & 1) dst.c[o >> 1].c1 = r; else dst.c[o >> 1].c0 = r; }
+    }
+}
+// whole product by a block that IS one unit (128 threads); out of line: the serial sequences call it ~500 times
+KZ_COLD void mp_mul(MpUnit& U, Fp12& dst, const Fp12& x, const Fp12& y) {
+    const int t = MP_TID();
+    mp_mul_products(U, t, x, y);
+    __syncthreads();
+    mp_mul_fold(U, t, dst);
+    __syncthreads();
+}
+#endif
+
+// ------------------------------------------------------------------ the serial part (one unit)
+struct MpScratch {
+    MpUnit U;
+    Fp12 f, fb, m, m1, m2, n, n1, n2, n3, t, a, b;
+    int result;
+};
+// dst = x^u, u = |x| = 0xd201000000010000 (63 squarings, 5 products); dst must not alias x; uses S.t
+KZ_COLD void mp_pow_u(MpScratch& S, Fp12& dst, const Fp12& x) {
+    const u64 k = ((u64)X_ABS_HI << 32) | X_ABS_LO;
+    coop_copy(S.t, x);
+    for (int i = 62; i >= 0; --i) {
+        mp_mul(S.U, S.t, S.t, S.t);
+        if ((k >> i) & 1) mp_mul(S.U, S.t, S.t, x);
+    }
+    coop_copy(dst, S.t);
+}
+// In: S.f = product of the Miller functions (already conjugated for x < 0).  Out: S.result = 1 iff f^((p^12-1)/r) == 1.
+KZ_COLD void mp_final_check(MpScratch& S) {
+    coop_frob2(S.a, S.f);
+    mp_mul(S.U, S.m, S.a, S.f);                  // m = f^(p^2+1)
+    mp_pow_u(S, S.m1, S.m);
+    mp_pow_u(S, S.m2, S.m1);
+    mp_mul(S.U, S.a, S.m1, S.m1);
+    mp_mul(S.U, S.a, S.a, S.m2);
+    mp_mul(S.U, S.n, S.a, S.m);                  // n = m^((u+1)^2)
+    mp_pow_u(S, S.n1, S.n);
+    mp_pow_u(S, S.n2, S.n1);
+    mp_pow_u(S, S.n3, S.n2);
+    // X+ = frob1(n2) * frob3(n) * n1 * m^3  -> S.m1
+    mp_mul(S.U, S.a, S.m, S.m);
+    mp_mul(S.U, S.a, S.a, S.m);                  // m^3
+    mp_mul(S.U, S.a, S.a, S.n1);
+    coop_frob1(S.b, S.n2);
+    mp_mul(S.U, S.a, S.a, S.b);
+    coop_frob2(S.b, S.n);
+    coop_frob1(S.m2, S.b);                       // n^(p^3)
+    mp_mul(S.U, S.m1, S.a, S.m2);
+    // X- = frob1(n) * n3 * frob2(n1)        -> S.m2
+    coop_frob1(S.a, S.n);
+    mp_mul(S.U, S.a, S.a, S.n3);
+    coop_frob2(S.b, S.n1);
+    mp_mul(S.U, S.m2, S.a, S.b);
+    // conj(X+) X-  ==  X+ conj(X-)
+    coop_conj(S.a, S.m1);
+    mp_mul(S.U, S.a, S.a, S.m2);
+    coop_conj(S.b, S.m2);
+    mp_mul(S.U, S.b, S.b, S.m1);
+    COOP_FOR(t, 1) {
+        bool same = true;
+        for (int k = 0; k < 6; ++k) same = same && fp2_eq(S.a.c[k], S.b.c[k]);
+        S.result = same ? 1 : 0;
+    }
+    COOP_SYNC();
+}
