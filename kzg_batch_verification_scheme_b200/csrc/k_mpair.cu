@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(128 * MP_UNITS) k_mp_lines(const G2Lines* __re
     const int s = blockIdx.x, grp = blockIdx.y;
     const int unit = threadIdx.x >> 7, tu = threadIdx.x & 127;
     const int nl = (KZ_MP_PAIRS - grp + MP_NG - 1) / MP_NG;
+    if (tu == 0) units[unit].zero = fp_zero();
     // line values as dense Fp12: l = a alpha + (b beta) w^2 + gamma w^3; a pair at infinity contributes 1
     for (int idx = threadIdx.x; idx < nl * 12; idx += blockDim.x) {
         const int l = idx / 12, ci = idx - 12 * l, p = grp + l * MP_NG;
@@ -128,48 +129,59 @@ __global__ void __launch_bounds__(128 * MP_UNITS) k_mp_lines(const G2Lines* __re
         if (threadIdx.x & 1) dst.c[k].c1 = pool[0].c[k].c1; else dst.c[k].c0 = pool[0].c[k].c0;
     }
 }
-// F[it] = product of the partial products of iteration it (its doubling step and, where bit 62 - it of |x| is set, the
-// addition step that follows)
-__global__ void __launch_bounds__(128) k_mp_merge(const Fp12* __restrict__ part, Fp12* __restrict__ F) {
+// Miller iterations are merged in chunks of MP_CHUNK: with F_it = product of the partial products of iteration it (its
+// doubling step and, where bit 62 - it of |x| is set, the addition step that follows),
+//     f <- f^(2^s) G_c,    G_c = ((F_a^2 F_(a+1))^2 ... )^2 F_(a+s-1)        (a = MP_CHUNK c, s = iterations in the chunk)
+// so the serial kernel spends s squarings and ONE product per chunk instead of s of each; the G_c are independent of f
+// and are formed here, one block per chunk.
+#define MP_CHUNK 4
+#define MP_NCHUNK ((KZ_MP_ITERS + MP_CHUNK - 1) / MP_CHUNK)
+__global__ void __launch_bounds__(128) k_mp_merge(const Fp12* __restrict__ part, Fp12* __restrict__ G) {
     __shared__ MpUnit U;
-    __shared__ Fp12 acc, y;
-    const int it = blockIdx.x;
-    bool has_add;
-    const int s0 = mp_step_of_iter(it, has_add);
-    const int cnt = MP_NG * (has_add ? 2 : 1);
-    const Fp12* src = part + (size_t)s0 * MP_NG;          // the addition step's partials follow the doubling step's
-    if (threadIdx.x < 12) {
-        const int k = threadIdx.x >> 1;
-        if (threadIdx.x & 1) acc.c[k].c1 = src[0].c[k].c1; else acc.c[k].c0 = src[0].c[k].c0;
-    }
-    __syncthreads();
-    for (int i = 1; i < cnt; ++i) {
-        if (threadIdx.x < 12) {
-            const int k = threadIdx.x >> 1;
-            if (threadIdx.x & 1) y.c[k].c1 = src[i].c[k].c1; else y.c[k].c0 = src[i].c[k].c0;
-        }
+    __shared__ Fp12 acc, fit, y;
+    const int c = blockIdx.x, t = threadIdx.x, k = t >> 1;
+    mp_unit_init(U);
+    const int it0 = c * MP_CHUNK, it1 = it0 + MP_CHUNK < KZ_MP_ITERS ? it0 + MP_CHUNK : KZ_MP_ITERS;
+    for (int it = it0; it < it1; ++it) {
+        bool has_add;
+        const int s0 = mp_step_of_iter(it, has_add);
+        const int cnt = MP_NG * (has_add ? 2 : 1);
+        const Fp12* src = part + (size_t)s0 * MP_NG;      // the addition step's partials follow the doubling step's
+        if (t < 12) { if (t & 1) fit.c[k].c1 = src[0].c[k].c1; else fit.c[k].c0 = src[0].c[k].c0; }
         __syncthreads();
-        mp_mul(U, acc, acc, y);
+        for (int i = 1; i < cnt; ++i) {
+            if (t < 12) { if (t & 1) y.c[k].c1 = src[i].c[k].c1; else y.c[k].c0 = src[i].c[k].c0; }
+            __syncthreads();
+            mp_mul(U, fit, fit, y);
+        }
+        if (it == it0) {
+            if (t < 12) { if (t & 1) acc.c[k].c1 = fit.c[k].c1; else acc.c[k].c0 = fit.c[k].c0; }
+            __syncthreads();
+        } else {
+            mp_mul(U, acc, acc, acc);
+            mp_mul(U, acc, acc, fit);
+        }
     }
-    if (threadIdx.x < 12) {
-        const int k = threadIdx.x >> 1;
-        if (threadIdx.x & 1) F[it].c[k].c1 = acc.c[k].c1; else F[it].c[k].c0 = acc.c[k].c0;
-    }
+    if (t < 12) { if (t & 1) G[c].c[k].c1 = acc.c[k].c1; else G[c].c[k].c0 = acc.c[k].c0; }
 }
-// The serial part: Miller accumulation f <- f^2 F_it, conjugation (x < 0), inversion-free final check.
-__global__ void __launch_bounds__(128) k_mp_check(const Fp12* __restrict__ F, int* __restrict__ result) {
+// The serial part: Miller accumulation f <- f^(2^s) G_c, conjugation (x < 0), inversion-free final check.
+__global__ void __launch_bounds__(128) k_mp_check(const Fp12* __restrict__ G, int* __restrict__ result) {
     __shared__ MpScratch S;
     const int t = threadIdx.x, k = t >> 1;
-    if (t < 12) { if (t & 1) S.f.c[k].c1 = F[0].c[k].c1; else S.f.c[k].c0 = F[0].c[k].c0; }
+    mp_unit_init(S.U);
+    if (t < 12) { if (t & 1) S.f.c[k].c1 = G[0].c[k].c1; else S.f.c[k].c0 = G[0].c[k].c0; }
     __syncthreads();
-    for (int it = 1; it < KZ_MP_ITERS; ++it) {
-        Fp pre;                                                       // next factor: the load hides under the squaring
-        if (t < 12) pre = (t & 1) ? F[it].c[k].c1 : F[it].c[k].c0;
-        mp_mul_products(S.U, t, S.f, S.f);
-        __syncthreads();
-        mp_mul_fold(S.U, t, S.f);
-        if (t < 12) { if (t & 1) S.fb.c[k].c1 = pre; else S.fb.c[k].c0 = pre; }
-        __syncthreads();
+    for (int c = 1; c < MP_NCHUNK; ++c) {
+        const int nsq = (c + 1) * MP_CHUNK <= KZ_MP_ITERS ? MP_CHUNK : KZ_MP_ITERS - c * MP_CHUNK;
+        Fp pre;                                                       // next factor: the load hides under the squarings
+        if (t < 12) pre = (t & 1) ? G[c].c[k].c1 : G[c].c[k].c0;
+        for (int q = 0; q < nsq; ++q) {
+            mp_mul_products(S.U, t, S.f, S.f);
+            __syncthreads();
+            mp_mul_fold(S.U, t, S.f);
+            if (q == 0 && t < 12) { if (t & 1) S.fb.c[k].c1 = pre; else S.fb.c[k].c0 = pre; }
+            __syncthreads();
+        }
         mp_mul_products(S.U, t, S.f, S.fb);
         __syncthreads();
         mp_mul_fold(S.U, t, S.f);
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(128) k_mp_check(const Fp12* __restrict__ F, in
 void launch_mp_check(cudaStream_t s, const G2Lines* tab, const MpCoef* coef, Fp12* part, Fp12* F, int* result) {
     k_mp_lines<<<dim3(KZ_N_LINES, MP_NG), 128 * MP_UNITS, 0, s>>>(tab, coef, part);
     KZ_COUNT_LAUNCH();
-    k_mp_merge<<<KZ_MP_ITERS, 128, 0, s>>>(part, F);
+    k_mp_merge<<<MP_NCHUNK, 128, 0, s>>>(part, F);
     KZ_COUNT_LAUNCH();
     k_mp_check<<<1, 128, 0, s>>>(F, result);
     KZ_COUNT_LAUNCH();

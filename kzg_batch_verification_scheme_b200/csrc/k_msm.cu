@@ -184,31 +184,45 @@ __global__ void __launch_bounds__(32 * WARPS) __maxnreg__(MAXREG) k_msm_chunk_pa
     }
 }
 
-__global__ void __launch_bounds__(128) k_msm_chunk_pass2(u32 T, G1Xyzz* __restrict__ buckets, ChunkRecs R) {
+__global__ void __launch_bounds__(128) k_msm_chunk_pass2_t(u32 T, G1Xyzz* __restrict__ buckets, ChunkRecs R) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     msm_chunk_pass2(T, t, buckets, R);
 }
+// Pass 2, one QUAD per (chunk, record kind): the partial records of a bucket that straddles chunks are added up by the
+// chunk where the bucket starts (msm_chunk_pass2 in msm.cuh is the one-thread form the emulation runs).  The additions
+// are a serial chain per bucket, so small sums run them on quads (n = 4096: accumulate stage 0.45 -> 0.37 ms); with many
+// chunks the one-thread form has the better throughput (n = 2^20: 15.2 vs 16.3 ms), see msm_accumulate_stage.
+__global__ void __launch_bounds__(128) k_msm_chunk_pass2(u32 T, G1Xyzz* __restrict__ buckets, ChunkRecs R) {
+    __shared__ Fp qsm[32 * KZ_QUAD_SLOTS];
+    const int qi = threadIdx.x >> 2;
+    const u32 job = blockIdx.x * 32u + (u32)qi, t = job >> 1, which = job & 1u;
+    if (t >= T) return;
+    u32 key;
+    G1Xyzz sum;
+    if (which == 0) {
+        key = R.tail_key[t];
+        if (key == KZ_KEY_NONE) return;
+        sum = R.tail[t];
+    } else {
+        key = R.head_key[t];
+        if (key == KZ_KEY_NONE) return;
+        const u32 f = R.head_flags[t];
+        if (!(f & 1u) || (f & 2u)) return;                  // does not start here, or already complete
+        sum = R.head[t];
+    }
+    Quad q = quad_make(qsm, qi);
+    for (u32 u = t + 1; u < T; ++u) {
+        if (R.head_key[u] != key) break;
+        sum = quad_xyzz_add(q, sum, R.head[u]);
+        if (R.head_flags[u] & 2u) break;
+    }
+    if (q.ql == 0) buckets[key] = sum;
+}
 
-// ---- bucket reduction (msm.cuh "bucket reduction through row / column totals")
-__global__ void __launch_bounds__(128) k_sg_pass1(const G1Xyzz* __restrict__ buckets, G1Xyzz* __restrict__ part, u32 stride,
-                                                   const __grid_constant__ MsmPlan plan) {
-    const int w = blockIdx.y;
-    const SgWin g = sg_win(plan, w);
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.jobs) return;
-    part[(size_t)w * stride + t] = sg_run_sum(buckets + plan.bucket_off[w], g, t);
-}
-__global__ void __launch_bounds__(128) k_sg_pass2(const G1Xyzz* __restrict__ part, u32 stride, G1Xyzz* __restrict__ tot, u32 tstride,
-                                                   const __grid_constant__ MsmPlan plan) {
-    const int w = blockIdx.y;
-    const SgWin g = sg_win(plan, w);
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.rows + g.cols) return;
-    tot[(size_t)w * tstride + t] = sg_total(part + (size_t)w * stride, g, t);
-}
-// ---- the same reduction with quad-lane point arithmetic (quad.cuh): latency-optimised, used while the bucket tables
-// are small enough for the reduction to be a serial chain rather than a throughput problem.
+// ---- bucket reduction through row / column totals (msm.cuh) with quad-lane point arithmetic (quad.cuh).  The run-sum
+// kernels of round 1 (one thread per run of 16 buckets) were measured no faster even at 2^15 buckets per window
+// (n = 2^20: 46.10 vs 46.14 ms) and 3x slower on small tables, and were dropped.
 // One block of KZ_RED_THREADS / 4 quads per row / column total: strided partial sums, then a tree over the quads.
 #define KZ_RED_THREADS 64
 __global__ void __launch_bounds__(KZ_RED_THREADS) k_red_totals(const G1Xyzz* __restrict__ buckets, G1Xyzz* __restrict__ tot, u32 tstride,
@@ -356,32 +370,16 @@ void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, si
                                                           ws.buckets, ws.recs);
     }
     KZ_COUNT_LAUNCH();
-    k_msm_chunk_pass2<<<(T + 127) / 128, 128, 0, s>>>(T, ws.buckets, ws.recs);
+    if (T <= 16384) k_msm_chunk_pass2<<<(2 * T + 31) / 32, 128, 0, s>>>(T, ws.buckets, ws.recs);
+    else k_msm_chunk_pass2_t<<<(T + 127) / 128, 128, 0, s>>>(T, ws.buckets, ws.recs);
     KZ_COUNT_LAUNCH();
 }
 // Slice sums of one sum: ws.slices[0 .. nbits) (sg_slice numbering).  want_all: also the "all" slices of the signed
-// windows (needed only by the batched subgroup check).  Tables of up to 2^KZGB_RED_QUAD_MAXK buckets per window are
-// reduced by the quad kernels (latency), larger ones by the run-sum kernels (throughput).
-static int red_quad_maxk() {
-    static const int v = [] { const char* e = getenv("KZGB_RED_QUAD_MAXK"); return e ? atoi(e) : 12; }();
-    return v;
-}
+// windows (needed only by the batched subgroup check).
 void msm_slices_stage(cudaStream_t s, const MsmPlan& plan, MsmWorkspace& ws, bool want_all) {
     const SgLayout L = sg_layout(plan);
-    G1Xyzz* part = ws.sg_work;
     G1Xyzz* tot = ws.sg_work + (size_t)plan.W * L.stride;
-    int kmax = plan.c - 1, tb = plan.nbits - plan.c * (plan.W - 1);
-    if (plan.W == 1 || tb > kmax) kmax = tb;
-    if (kmax <= red_quad_maxk()) {
-        k_red_totals<<<dim3(L.tstride, (unsigned)plan.W), KZ_RED_THREADS, 0, s>>>(ws.buckets, tot, L.tstride, plan);
-        KZ_COUNT_LAUNCH();
-        k_red_slices<<<(unsigned)plan.nbits, KZ_SLICE_THREADS, 0, s>>>(ws.buckets, tot, L.tstride, ws.slices, want_all ? 1 : 0, plan);
-        KZ_COUNT_LAUNCH();
-        return;
-    }
-    k_sg_pass1<<<dim3((L.stride + 127) / 128, (unsigned)plan.W), 128, 0, s>>>(ws.buckets, part, L.stride, plan);
-    KZ_COUNT_LAUNCH();
-    k_sg_pass2<<<dim3((L.tstride + 127) / 128, (unsigned)plan.W), 128, 0, s>>>(part, L.stride, tot, L.tstride, plan);
+    k_red_totals<<<dim3(L.tstride, (unsigned)plan.W), KZ_RED_THREADS, 0, s>>>(ws.buckets, tot, L.tstride, plan);
     KZ_COUNT_LAUNCH();
     k_red_slices<<<(unsigned)plan.nbits, KZ_SLICE_THREADS, 0, s>>>(ws.buckets, tot, L.tstride, ws.slices, want_all ? 1 : 0, plan);
     KZ_COUNT_LAUNCH();

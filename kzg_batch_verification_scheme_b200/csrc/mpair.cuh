@@ -39,7 +39,6 @@
 
 struct MpCoef { Fp alpha, beta, gamma; u32 inf, pad[3]; };      // line at P: a*alpha + (b*beta) w^2 + gamma w^3
 struct MpSumDesc { const G1Xyzz* slices; const G1Xyzz* buckets; int c, W, nbits; };     // slices == null: the zero sum
-struct MpUnit { Fp kar[108]; };                      // Karatsuba parts of one Fp12 product
 
 // U_j of a sum, j = absolute bit position 0 .. nbits
 KZ_HD G1Xyzz mp_slice(const MpSumDesc& d, int j) {
@@ -72,68 +71,74 @@ KZ_HD int mp_step_of_iter(int it, bool& has_add) {
 }
 
 // ------------------------------------------------------------------ one Fp12 product by a unit of 128 threads
-// phase 1 (t < 108): Karatsuba parts v0 = a0 b0, v1 = a1 b1, v2 = (a0+a1)(b0+b1) of the 36 Fp2 partial products
+// Measured per round on an idle SM (tools/microbench/mp_round.cu): products 1.9-2.3k clk, fold 0.8-1.1k clk, barriers 10 clk.
+struct MpUnit { Fp kar[108]; Fp zero; };             // Karatsuba parts of one Fp12 product; a zero operand
+// phase 1 (t < 108): Karatsuba parts v0 = a0 b0, v1 = a1 b1, v2 = (a0+a1)(b0+b1) of the 36 Fp2 partial products.
+// Uniform code: every lane adds two operands, the second one being the zero constant for v0 and v1.
 KZ_HD void mp_mul_products(MpUnit& U, int t, const Fp12& x, const Fp12& y) {
     if (t < 108) {
         const int q = t / 3, part = t - 3 * q, i = q / 6, j = q - 6 * i;
-        Fp A, B;
-        if (part == 0) { A = x.c[i].c0; B = y.c[j].c0; }
-        else if (part == 1) { A = x.c[i].c1; B = y.c[j].c1; }
-        else { A = fp_add(x.c[i].c0, x.c[i].c1); B = fp_add(y.c[j].c0, y.c[j].c1); }
-        U.kar[t] = fp_mul(A, B);
+        const Fp* a1 = part == 1 ? &x.c[i].c1 : &x.c[i].c0;
+        const Fp* a2 = part == 2 ? &x.c[i].c1 : &U.zero;
+        const Fp* b1 = part == 1 ? &y.c[j].c1 : &y.c[j].c0;
+        const Fp* b2 = part == 2 ? &y.c[j].c1 : &U.zero;
+        U.kar[t] = fp_mul(fp_add(*a1, *a2), fp_add(*b1, *b2));
     }
 }
-// phase 2 (after a barrier; t < 96 = three full warps): output o = t / 8 (coefficient k = o / 2, real / imaginary part
-// h = o & 1), lane i = t & 7 holds the contribution of the partial product (i, j) with i + j = k (mod 6):
-//   i + j = k      real  v0 - v1            imaginary  v2 - v0 - v1
-//   i + j = k + 6  real  2 v0 - v2          imaginary  v2 - 2 v1          (times xi = 1 + u)
-// and a xor-shuffle tree adds the six contributions.  dst may alias the operands of phase 1.
-KZ_HD Fp mp_fold_contrib(const MpUnit& U, int o, int i) {
-    const int k = o >> 1, h = o & 1;
+// phase 2 (after a barrier): coefficient k, real (h = 0) / imaginary (h = 1) part; lane i < 6 holds the contribution of
+// the partial product (i, j) with i + j = k (mod 6):
+//   i + j = k      real  v0 - v1            imaginary  v2 - v1 - v0
+//   i + j = k + 6  real  (v0 - v2) + v0     imaginary  v2 - v1 - v1       (times xi = 1 + u)
+KZ_HD Fp mp_fold_contrib(const MpUnit& U, int k, int h, int i) {
     int j = k - i;
     const bool hi = j < 0;
     if (hi) j += 6;
     const int q = 3 * (i * 6 + j);
-    const Fp v0 = U.kar[q], v1 = U.kar[q + 1], v2 = U.kar[q + 2];
-    // X - Y (+ v0 | - v0 | - v1 | nothing): one subtraction and one addition / subtraction, no divergent arithmetic
-    const Fp X = h ? v2 : v0;
-    const Fp Y = (!h && hi) ? v2 : v1;
-    const Fp T = (h && hi) ? v1 : v0;
-    const Fp d = fp_sub(X, Y), dp = fp_add(d, T), dm = fp_sub(d, T);
-    return h ? dm : (hi ? dp : d);
+    if (h == 0) {
+        const Fp X = U.kar[q], Y = U.kar[q + (hi ? 2 : 1)];
+        const Fp d = fp_sub(X, Y), dp = fp_add(d, X);
+        return hi ? dp : d;
+    }
+    const Fp X = U.kar[q + 2], Y = U.kar[q + 1], T = U.kar[q + (hi ? 1 : 0)];
+    return fp_sub(fp_sub(X, Y), T);
 }
 #if defined(KZGB_EMU)
 #define MP_TID() 0
+KZ_HD void mp_unit_init(MpUnit& U) { U.zero = fp_zero(); }
 KZ_HD void mp_mul(MpUnit& U, Fp12& dst, const Fp12& x, const Fp12& y) {
     for (int t = 0; t < 108; ++t) mp_mul_products(U, t, x, y);
     for (int o = 0; o < 12; ++o) {
         Fp r = fp_zero();
-        for (int i = 0; i < 6; ++i) r = fp_add(r, mp_fold_contrib(U, o, i));
+        for (int i = 0; i < 6; ++i) r = fp_add(r, mp_fold_contrib(U, o >> 1, o & 1, i));
         if (o & 1) dst.c[o >> 1].c1 = r; else dst.c[o >> 1].c0 = r;
     }
 }
+KZ_HD void mp_mul_cold(MpUnit& U, Fp12& dst, const Fp12& x, const Fp12& y) { mp_mul(U, dst, x, y); }
 #else
 #define MP_TID() ((int)(threadIdx.x & 127u))
+KZ_HD void mp_unit_init(MpUnit& U) { if (MP_TID() == 0) U.zero = fp_zero(); }       // followed by a barrier of the caller
+// Four warps: warps 0, 1 fold the real parts (warp-uniform arithmetic), warps 2, 3 the imaginary parts; 3 outputs per
+// warp x 8 lanes, xor-shuffle tree over the 6 contributions.  dst may alias the operands of phase 1.
 KZ_HD void mp_mul_fold(const MpUnit& U, int t, Fp12& dst) {
-    if (t < 96) {
-        const int o = t >> 3, i = t & 7;
-        Fp r = i < 6 ? mp_fold_contrib(U, o, i) : fp_zero();
-        KZ_UNROLL for (int s = 4; s; s >>= 1) {
-            Fp ot;
-            KZ_UNROLL for (int l = 0; l < 12; ++l) ot.v[l] = __shfl_xor_sync(0xFFFFFFFFu, r.v[l], s);
-            r = fp_add(r, ot);
-        }
-        if (i == 0) { if (o & 1) dst.c[o >> 1].c1 = r; else dst.c[o >> 1].c0 = r; }
+    const int w = t >> 5, l = t & 31, g = l >> 3, i = l & 7;
+    const int h = w >> 1, k = (w & 1) * 3 + (g < 3 ? g : 0);
+    Fp r = (g < 3 && i < 6) ? mp_fold_contrib(U, k, h, i) : fp_zero();
+    KZ_UNROLL for (int s = 4; s; s >>= 1) {
+        Fp ot;
+        KZ_UNROLL for (int m = 0; m < 12; ++m) ot.v[m] = __shfl_xor_sync(0xFFFFFFFFu, r.v[m], s);
+        r = fp_add(r, ot);
     }
+    if (g < 3 && i == 0) { if (h) dst.c[k].c1 = r; else dst.c[k].c0 = r; }
 }
-// whole product by a block that IS one unit (128 threads); out of line: the serial sequences call it ~500 times
-KZ_COLD void mp_mul(MpUnit& U, Fp12& dst, const Fp12& x, const Fp12& y) {
+// whole product by a block that IS one unit (128 threads)
+KZ_HD void mp_mul(MpUnit& U, Fp12& dst, const Fp12& x, const Fp12& y) {
     const int t = MP_TID();
     mp_mul_products(U, t, x, y);
     __syncthreads();
     mp_mul_fold(U, t, dst);
     __syncthreads();
 }
+KZ_COLD void mp_mul_cold(MpUnit& U, Fp12& dst, const Fp12& x, const Fp12& y) { mp_mul(U, dst, x, y); }
 #endif
 
 // ------------------------------------------------------------------ the serial part (one unit)
@@ -155,34 +160,34 @@ KZ_COLD void mp_pow_u(MpScratch& S, Fp12& dst, const Fp12& x) {
 // In: S.f = product of the Miller functions (already conjugated for x < 0).  Out: S.result = 1 iff f^((p^12-1)/r) == 1.
 KZ_COLD void mp_final_check(MpScratch& S) {
     coop_frob2(S.a, S.f);
-    mp_mul(S.U, S.m, S.a, S.f);                  // m = f^(p^2+1)
+    mp_mul_cold(S.U, S.m, S.a, S.f);                  // m = f^(p^2+1)
     mp_pow_u(S, S.m1, S.m);
     mp_pow_u(S, S.m2, S.m1);
-    mp_mul(S.U, S.a, S.m1, S.m1);
-    mp_mul(S.U, S.a, S.a, S.m2);
-    mp_mul(S.U, S.n, S.a, S.m);                  // n = m^((u+1)^2)
+    mp_mul_cold(S.U, S.a, S.m1, S.m1);
+    mp_mul_cold(S.U, S.a, S.a, S.m2);
+    mp_mul_cold(S.U, S.n, S.a, S.m);                  // n = m^((u+1)^2)
     mp_pow_u(S, S.n1, S.n);
     mp_pow_u(S, S.n2, S.n1);
     mp_pow_u(S, S.n3, S.n2);
     // X+ = frob1(n2) * frob3(n) * n1 * m^3  -> S.m1
-    mp_mul(S.U, S.a, S.m, S.m);
-    mp_mul(S.U, S.a, S.a, S.m);                  // m^3
-    mp_mul(S.U, S.a, S.a, S.n1);
+    mp_mul_cold(S.U, S.a, S.m, S.m);
+    mp_mul_cold(S.U, S.a, S.a, S.m);                  // m^3
+    mp_mul_cold(S.U, S.a, S.a, S.n1);
     coop_frob1(S.b, S.n2);
-    mp_mul(S.U, S.a, S.a, S.b);
+    mp_mul_cold(S.U, S.a, S.a, S.b);
     coop_frob2(S.b, S.n);
     coop_frob1(S.m2, S.b);                       // n^(p^3)
-    mp_mul(S.U, S.m1, S.a, S.m2);
+    mp_mul_cold(S.U, S.m1, S.a, S.m2);
     // X- = frob1(n) * n3 * frob2(n1)        -> S.m2
     coop_frob1(S.a, S.n);
-    mp_mul(S.U, S.a, S.a, S.n3);
+    mp_mul_cold(S.U, S.a, S.a, S.n3);
     coop_frob2(S.b, S.n1);
-    mp_mul(S.U, S.m2, S.a, S.b);
+    mp_mul_cold(S.U, S.m2, S.a, S.b);
     // conj(X+) X-  ==  X+ conj(X-)
     coop_conj(S.a, S.m1);
-    mp_mul(S.U, S.a, S.a, S.m2);
+    mp_mul_cold(S.U, S.a, S.a, S.m2);
     coop_conj(S.b, S.m2);
-    mp_mul(S.U, S.b, S.b, S.m1);
+    mp_mul_cold(S.U, S.b, S.b, S.m1);
     COOP_FOR(t, 1) {
         bool same = true;
         for (int k = 0; k < 6; ++k) same = same && fp2_eq(S.a.c[k], S.b.c[k]);
