@@ -1,11 +1,13 @@
 #!/usr/bin/env python3
 """bench.py -- verified KZG proofs/s (BASELINE.json metric) on 1..8 B200.
 
-A "step" is one batch verification (decompress + subgroup checks, Fiat-Shamir, three MSMs, pairing) of
-n proofs per GPU through the C ABI of libkzgb200.so.  `value` = device-resident inputs; `e2e` = pinned
-host buffers through verify_kzg_proof_batch (H2D inside the timed region).  N>1 (torchrun): weak
-scaling -- every rank owns a contiguous shard of n proofs of ONE batch of N*n proofs; only chunk
-digests, the root and 320-byte partials cross ranks (host, gloo); rank 0 combines and runs the pairing.
+A "step" is one batch verification (decompress + subgroup checks, Fiat-Shamir, three MSMs, pairing check) through
+the C ABI of libkzgb200.so.  `value` = device-resident inputs; `e2e` = plain (pageable) host buffers through
+verify_kzg_proof_batch, H2D inside the timed region (`e2e_pinned`: the same from pinned buffers).  N>1 (torchrun,
+one process per GPU): default STRONG scaling, BASELINE.json config[3] -- ONE batch of 2^n proofs cut into N
+contiguous shards; chunk digests, 66 pairing terms per shard and the verdicts cross the host through a
+shared-memory mailbox (no NCCL; gloo only for barriers and the timing scalar); rank 0 adds the terms and runs the
+pairing check.  The weak figure (2^n proofs per GPU in one batch) is measured as a second pass of the same line.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--n LOG2] [--impl reference]
 """
@@ -48,7 +50,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--n", type=int, default=20, help="log2 of proofs per GPU (default 20)")
     ap.add_argument("--impl", default="kzgb200", choices=["kzgb200", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong = one batch of 2^n proofs cut N ways (BASELINE.json config[3], default); weak = 2^n per GPU. "
+                         "The other mode is measured as a second pass of the same line.")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / msm / n=2^16 extras")
     return ap.parse_args()
 
@@ -156,8 +160,8 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    from kzg_batch_verification_scheme_b200.api import CHUNK, PARTIAL_BYTES, load
-    from kzg_batch_verification_scheme_b200.sharded import sharded_verify
+    from kzg_batch_verification_scheme_b200.api import CHUNK, PARTIAL_BYTES, TERMS_BYTES, load
+    from kzg_batch_verification_scheme_b200.sharded import HostMailbox, sharded_verify
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -165,24 +169,31 @@ def main():
     multi = world > 1
     torch.cuda.set_device(local)
     if multi:
-        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
-    n_total_cfg = 1 << args.n
-    n_local = n_total_cfg if args.scaling == "weak" else max(CHUNK, n_total_cfg // world)
-    n_total = n_local * world
+        # host-side plumbing only (barriers, the timing scalar, the name of the shared-memory mailbox): no NCCL anywhere
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    n_cfg = 1 << args.n
     lib = load()
-    ctx = lib.test_context(devices=[local], n_max=n_local)
+    ctx = lib.test_context(devices=[local], n_max=n_cfg)
+    box = HostMailbox(dist, rank, world, n_cfg) if multi else None
     stream = torch.cuda.current_stream().cuda_stream
 
-    # ---- synthetic inputs: generated ON the device, then mirrored into pinned host memory for e2e
-    dbuf = [torch.empty(s * n_local, dtype=torch.uint8, device="cuda") for s in (48, 32, 32, 48)]
-    ctx.synth_instance(SEED, rank * n_local, n_local, device_ptrs=tuple(t.data_ptr() for t in dbuf))
-    torch.cuda.synchronize()
-    hbuf = [torch.empty(s * n_local, dtype=torch.uint8).pin_memory() for s in (48, 32, 32, 48)]
-    for h, d in zip(hbuf, dbuf):
-        h.copy_(d)
-    torch.cuda.synchronize()
-    dptr = [t.data_ptr() for t in dbuf]
-    hptr = [t.data_ptr() for t in hbuf]
+    class Workload:
+        """Shard of this rank: device-resident bytes, a pinned and a plain (pageable) host mirror."""
+        def __init__(self, n_local):
+            self.n_local, self.n_total = n_local, n_local * world
+            self.dbuf = [torch.empty(s * n_local, dtype=torch.uint8, device="cuda") for s in (48, 32, 32, 48)]
+            ctx.synth_instance(SEED, rank * n_local, n_local, device_ptrs=tuple(t.data_ptr() for t in self.dbuf))
+            torch.cuda.synchronize()
+            self.pinned = [torch.empty(s * n_local, dtype=torch.uint8).pin_memory() for s in (48, 32, 32, 48)]
+            self.plain = [torch.empty(s * n_local, dtype=torch.uint8) for s in (48, 32, 32, 48)]       # malloc'ed, pageable
+            for h, d in zip(self.pinned, self.dbuf):
+                h.copy_(d)
+            torch.cuda.synchronize()
+            for h, q in zip(self.plain, self.pinned):
+                h.copy_(q)
+            self.dptr = [t.data_ptr() for t in self.dbuf]
+            self.pptr = [t.data_ptr() for t in self.pinned]
+            self.hptr = [t.data_ptr() for t in self.plain]
 
     def barrier():
         torch.cuda.synchronize()
@@ -190,57 +201,94 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(ptrs, on_device):
-        """one batch verification; returns the verdict (rank 0)"""
+    def step(w, ptrs, on_device):
+        """one batch verification; returns the verdict (the same on every rank)"""
         if not multi:
             if on_device:
-                rc, ok = ctx.verify_kzg_proof_batch_device(*ptrs, n_local, stream)
+                rc, ok = ctx.verify_kzg_proof_batch_device(*ptrs, w.n_local, stream)
             else:
-                rc, ok = ctx.verify_kzg_proof_batch(*ptrs, n_local)
-            assert rc == 0, rc
-            return ok
-        rc, ok = sharded_verify(ctx, dist, rank, world, *ptrs, n_local, on_device=on_device, stream=stream)
+                rc, ok = ctx.verify_kzg_proof_batch(*ptrs, w.n_local)
+        else:
+            rc, ok = sharded_verify(ctx, dist, rank, world, *ptrs, w.n_local, on_device=on_device, stream=stream, box=box)
         assert rc == 0, rc
-        return True if ok is None else ok
+        return ok
 
-    def timed(ptrs, on_device, steps, warmup):
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # 2 x the 126 MB L2
+
+    def timed(w, ptrs, on_device, steps, warmup):
+        """K steps, each bracketed by barrier + synchronize and timed with CUDA events; between steps the L2 is flushed
+        (untimed) by writing a 256 MB buffer, so no step finds its inputs or tables in cache."""
         for _ in range(warmup):
-            assert step(ptrs, on_device)
-        barrier()
-        l0 = ctx.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            assert step(w, ptrs, on_device)
         stage_acc = {}
-        e0.record()
+        ms, launches = 0.0, 0
         for _ in range(steps):
-            ok = step(ptrs, on_device)
+            flush_buf.fill_(1)
+            barrier()
+            l0 = ctx.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ok = step(w, ptrs, on_device)
+            e1.record()
+            barrier()
             assert ok, "batch must verify"
-            if not multi or rank == 0 or True:
-                for k, v in ctx.last_stage_ms().items():
-                    stage_acc[k] = stage_acc.get(k, 0.0) + v
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+            ms += e0.elapsed_time(e1)
+            launches += ctx.launch_count() - l0
+            for k, v in ctx.last_stage_ms().items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
         if multi:
-            t = torch.tensor([ms], device="cuda")
+            t = torch.tensor([ms], dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        launches = ctx.launch_count() - l0
+            t = torch.tensor([launches], dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            launches = int(t.item())
         return ms / steps, {k: v / steps for k, v in stage_acc.items()}, launches
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, stages, launches = timed(dptr, True, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
-    ms_e2e, stages_e2e, _ = timed(hptr, False, args.steps, max(1, args.warmup // 2))
+    def planted(w):
+        """a corrupted proof (on the LAST rank for N > 1) must be rejected -- on every rank"""
+        if rank == world - 1:
+            saved = w.dbuf[3][:48].clone()
+            w.dbuf[3][:48] = w.dbuf[3][48:96]
+            torch.cuda.synchronize()
+        if multi:
+            rc, ok = sharded_verify(ctx, dist, rank, world, *w.dptr, w.n_local, on_device=True, stream=stream, box=box)
+        else:
+            rc, ok = ctx.verify_kzg_proof_batch_device(*w.dptr, w.n_local, stream)
+        if rank == world - 1:
+            w.dbuf[3][:48] = saved
+            torch.cuda.synchronize()
+        good = (rc == 0 and not ok)
+        if multi:
+            t = torch.tensor([int(good)], dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            good = bool(t.item())
+        return good
 
-    # ---- correctness guard inside the bench: a corrupted proof must be rejected (single GPU)
-    reject_ok = None
-    if not multi:
-        saved = dbuf[3][:48].clone()
-        dbuf[3][:48] = dbuf[3][48:96]
-        rc, ok = ctx.verify_kzg_proof_batch_device(*dptr, n_local, stream)
-        reject_ok = (rc == 0 and not ok)
-        dbuf[3][:48] = saved
-        torch.cuda.synchronize()
+    # ---- the headline pass.  strong (BASELINE.json config[3]): ONE batch of 2^n proofs cut world ways;
+    # weak: every rank owns 2^n proofs of one batch of world * 2^n
+    n_local = n_cfg if args.scaling == "weak" else max(CHUNK, n_cfg // world)
+    w = Workload(n_local)
+    n_total = w.n_total
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, stages, launches = timed(w, w.dptr, True, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, stages_e2e, _ = timed(w, w.hptr, False, args.steps, max(1, args.warmup // 2))
+    ms_pin, stages_pin, _ = timed(w, w.pptr, False, args.steps, max(1, args.warmup // 2))
+    reject_ok = planted(w)
+    other = None
+    if multi:
+        # the other scaling mode as a second timed pass of the same line
+        n_other = n_cfg if args.scaling == "strong" else max(CHUNK, n_cfg // world)
+        del w.pinned, w.plain
+        w2 = Workload(n_other)
+        ms2, st2, _ = timed(w2, w2.dptr, True, args.steps, args.warmup)
+        ms2e, _, _ = timed(w2, w2.hptr, False, args.steps, 1)
+        other = {"scaling": "weak" if args.scaling == "strong" else "strong", "n_per_gpu": n_other, "n_total": w2.n_total,
+                 "value": w2.n_total / (ms2 * 1e-3), "unit": "proofs/s", "ms_per_step": ms2, "stage_ms": st2,
+                 "e2e": {"value": w2.n_total / (ms2e * 1e-3), "ms_per_step": ms2e}, "planted_invalid_rejected": planted(w2)}
+        del w2
+    dbuf, hbuf, dptr = w.dbuf, w.pinned, w.dptr
 
     value = n_total / (ms_dev * 1e-3)
     e2e_value = n_total / (ms_e2e * 1e-3)
@@ -406,24 +454,34 @@ def main():
             "metric": "verified KZG proofs/s", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"BLS12-381 KZG batch verify, n=2^{args.n} proofs per GPU ({n_total} total), compressed inputs incl. "
-                                   "decompression + subgroup checks, Fiat-Shamir, 3 MSMs, 2-pairing check",
+            "config": {"workload": (f"BLS12-381 KZG batch verify, ONE batch of n=2^{args.n} proofs" +
+                                    (f" cut into {world} contiguous shards (BASELINE.json config[3])" if multi and args.scaling == "strong" else
+                                     f" per GPU ({n_total} in one batch)" if multi else "") +
+                                    ", compressed inputs incl. decompression + subgroup checks, Fiat-Shamir, 3 MSMs, pairing check"),
                        "n_per_gpu": n_local, "n_total": n_total, "seed": hex(SEED),
-                       "l2": "inputs (160 B/proof) and intermediates exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"contiguous shards x{world}, host combine" if multi else "single GPU"},
+                       "l2": "L2 flushed between steps (256 MB write, outside the timed region); every step is timed on its own",
+                       "parallelism": (f"contiguous shards x{world}, one process per GPU; digests, pairing terms and verdicts cross the host "
+                                       "(shared-memory mailbox), no NCCL") if multi else "single GPU"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "proofs/s", "ms_per_step": ms_e2e, "stage_ms": stages_e2e, "h2d_bytes_per_step": 160 * n_local * world,
-                    "d2h_bytes_per_step": (32 * nch + PARTIAL_BYTES + 16) * world},
+            # e2e: PLAIN (pageable) host buffers through verify_kzg_proof_batch -- the library orders its copies and launches so
+            # that K1 starts after the first sixteenth of C; e2e_pinned: the same call on cudaMallocHost'ed buffers
+            "e2e": {"value": e2e_value, "unit": "proofs/s", "ms_per_step": ms_e2e, "host_memory": "pageable", "stage_ms": stages_e2e,
+                    "h2d_bytes_per_step": 160 * n_local * world,
+                    "d2h_bytes_per_step": (32 * nch + (TERMS_BYTES if multi else 0) + 16) * world},
+            "e2e_pinned": {"value": n_total / (ms_pin * 1e-3), "unit": "proofs/s", "ms_per_step": ms_pin, "host_memory": "pinned"},
             "gpu_launches": launches,
             "stage_ms": stages,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
             "planted_invalid_rejected": reject_ok,
             "extras": extras,
         }
+        if other:
+            line[other["scaling"]] = other
         print(json.dumps(line), flush=True)
     ctx.close()
     if multi:
         dist.barrier()
+        box.close()
         dist.destroy_process_group()
 
 

@@ -90,6 +90,20 @@ kzgb_ret kzgb_fs_root(uint8_t root_out[32], const uint8_t *chunk_digests, size_t
 kzgb_ret kzgb_shard_phase2(kzgb_ctx *ctx, int slot, const uint8_t root[32], uint64_t global_offset, void *stream,
                            uint8_t partial_out[KZGB_PARTIAL_BYTES]);
 kzgb_ret kzgb_combine_verify(kzgb_ctx *ctx, const uint8_t *partials /*320*G*/, int n_partials, bool *ok);
+/* Same exchange without the serial Horner tail on any shard (DESIGN.md "Horner-free pairing check"): instead of one
+ * 144-byte sum per side a shard returns 2 x 33 G1 terms V_t with A_shard = sum_t 2^(4t) V_t and B_shard =
+ * sum_t 2^(4t) V_(33+t); the combining side adds the shards' terms and pairs them with the fixed multiples
+ * [2^(4t)]G2, [2^(4t)][tau]G2.  Record = 66 x (X | Y | ZZ | ZZZ, 48 B big-endian canonical each; the point is
+ * (X/ZZ, Y/ZZZ), ZZ = 0 = infinity) | sum r_i y_i of the shard (32 B big-endian): KZGB_TERMS_BYTES.
+ * kzgb_shard_phase2_terms returns once the record is on the host; kzgb_shard_finish then reports the shard's input
+ * validation (KZGB_BADARGS and the counts if a point or scalar of the shard is malformed) -- the caller must
+ * collect it from every shard before trusting the verdict of kzgb_combine_verify_terms. */
+#define KZGB_N_TERMS 66u
+#define KZGB_TERMS_BYTES (KZGB_N_TERMS * 192u + 32u)
+kzgb_ret kzgb_shard_phase2_terms(kzgb_ctx *ctx, int slot, const uint8_t root[32], uint64_t global_offset, void *stream,
+                                 uint8_t terms_out[KZGB_TERMS_BYTES]);
+kzgb_ret kzgb_shard_finish(kzgb_ctx *ctx, int slot, uint32_t *n_bad_points_out, uint32_t *n_bad_scalars_out);
+kzgb_ret kzgb_combine_verify_terms(kzgb_ctx *ctx, const uint8_t *terms /*KZGB_TERMS_BYTES*G*/, int n_shards, bool *ok);
 
 /* ---- stage exports: artefacts for bit-exact GPU-vs-oracle diffs (BJ:5 "bit-exact ... every canonical
  * affine MSM output and every decompressed point") */

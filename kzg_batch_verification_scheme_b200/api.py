@@ -15,6 +15,8 @@ KZGB_OK, KZGB_BADARGS, KZGB_ERROR, KZGB_MALLOC = 0, 1, 2, 3
 ST_OK, ST_BAD_FLAGS, ST_X_GE_P, ST_NOT_ON_CURVE, ST_NOT_IN_G1 = 0, 1, 2, 3, 4
 CHUNK = 128
 PARTIAL_BYTES = 320
+N_TERMS = 66
+TERMS_BYTES = N_TERMS * 192 + 32
 N_STAGES = 10
 STAGE_NAMES = ["h2d", "decompress", "hash", "root_host", "challenges", "msm_sort", "msm_accumulate",
                "msm_reduce", "pairing", "total"]
@@ -76,6 +78,9 @@ class KzgLib:
             "kzgb_fs_root": [vp, vp, sz, u64],
             "kzgb_shard_phase2": [vp, i32, vp, u64, vp, vp],
             "kzgb_combine_verify": [vp, vp, i32, C.POINTER(C.c_bool)],
+            "kzgb_shard_phase2_terms": [vp, i32, vp, u64, vp, vp],
+            "kzgb_shard_finish": [vp, i32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
+            "kzgb_combine_verify_terms": [vp, vp, i32, C.POINTER(C.c_bool)],
             "kzgb_g1_decompress_batch": [vp, vp, vp, sz, vp],
             "kzgb_fs_challenges": [vp, vp, vp, vp, vp, vp, sz, vp],
             "kzgb_g1_msm": [vp, vp, vp, sz, i32, vp],
@@ -103,7 +108,7 @@ class KzgLib:
 
     EXPORTS = ["kzgb_ctx_create", "kzgb_ctx_free", "verify_kzg_proof", "verify_kzg_proof_batch",
                "verify_kzg_proof_batch_device", "verify_cell_kzg_proof_batch", "kzgb_shard_phase1", "kzgb_fs_root", "kzgb_shard_phase2",
-               "kzgb_combine_verify", "kzgb_g1_decompress_batch", "kzgb_fs_challenges", "kzgb_g1_msm",
+               "kzgb_combine_verify", "kzgb_shard_phase2_terms", "kzgb_shard_finish", "kzgb_combine_verify_terms", "kzgb_g1_decompress_batch", "kzgb_fs_challenges", "kzgb_g1_msm",
                "kzgb_g1_msm_times", "kzgb_pairing_check", "kzgb_last_artifacts", "kzgb_synth_instance",
                "kzgb_synth_setup", "kzgb_debug_op", "kzgb_imad_peak", "kzgb_imad32_peak", "kzgb_last_stage_ms", "kzgb_launch_count", "kzgb_set_threads",
                "kzgb_set_subgroup_batch_min", "verify_blob_kzg_proof_batch", "kzgb_blob_challenges_evals", "kzgb_blob_eval", "kzgb_version"]
@@ -214,6 +219,24 @@ class Context:
     def combine_verify(self, partials: bytes):
         ok = C.c_bool(False)
         rc = self.lib.kzgb_combine_verify(self.h, _ptr(partials), len(partials) // PARTIAL_BYTES, C.byref(ok))
+        return rc, bool(ok.value)
+
+    def shard_phase2_terms(self, slot, root: bytes, global_offset: int, stream=0, out=None):
+        """(rc, record): the shard's 66 pairing terms + sum r_i y_i (TERMS_BYTES); `out` = writable buffer to fill in place."""
+        buf = out if out is not None else C.create_string_buffer(TERMS_BYTES)
+        rc = self.lib.kzgb_shard_phase2_terms(self.h, slot, _ptr(root), global_offset, C.c_void_p(stream), _ptr(buf))
+        return rc, (buf if out is not None else buf.raw)
+
+    def shard_finish(self, slot=0):
+        """(rc, n_bad_points, n_bad_scalars) of the shard's input validation; rc = 1 if any element is malformed."""
+        bp, bs = C.c_uint32(0), C.c_uint32(0)
+        rc = self.lib.kzgb_shard_finish(self.h, slot, C.byref(bp), C.byref(bs))
+        return rc, bp.value, bs.value
+
+    def combine_verify_terms(self, terms, n_shards=None):
+        n_shards = len(terms) // TERMS_BYTES if n_shards is None else n_shards
+        ok = C.c_bool(False)
+        rc = self.lib.kzgb_combine_verify_terms(self.h, _ptr(terms), n_shards, C.byref(ok))
         return rc, bool(ok.value)
 
     # ---- stage exports

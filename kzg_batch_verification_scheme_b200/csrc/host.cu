@@ -99,7 +99,7 @@ struct DeviceSlot {
     uint8_t* h_digests = nullptr;      // 32 * ceil(n_max/KZGB_CHUNK)
     uint32_t* h_small = nullptr;       // 64 words: [0..2] counters, [8..15] root words, [16] result
     uint8_t* h_partial = nullptr;      // 320 * 64
-    cudaEvent_t ev[24] = {};
+    cudaEvent_t ev[28] = {};
     // current shard (between phase 1 and phase 2)
     const uint8_t *cur_C = nullptr, *cur_z = nullptr, *cur_y = nullptr, *cur_pi = nullptr;
     size_t cur_n = 0;
@@ -278,7 +278,7 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     CK(dmalloc(s.mp_chain, KZ_MP_PAIRS)); CK(dmalloc(s.mp_tab, KZ_MP_PAIRS));
     CK(dmalloc(s.mp_terms, KZ_MP_PAIRS)); CK(dmalloc(s.mp_terms_in, 64 * KZ_MP_PAIRS)); CK(dmalloc(s.mp_coef, KZ_MP_PAIRS));
     CK(dmalloc(s.mp_part, mp_part_entries())); CK(dmalloc(s.mp_F, KZ_MP_ITERS));
-    CK(cudaMallocHost((void**)&s.h_terms, sizeof(G1Xyzz) * 64 * KZ_MP_PAIRS));
+    CK(cudaMallocHost((void**)&s.h_terms, (size_t)KZGB_TERMS_BYTES * 64));
     { const char* e = getenv("KZGB_CLASSIC"); s.classic = e && atoi(e) != 0; }
     // trusted setup: decompress + check on the device, precompute the G2 lines
     CK(cudaMemcpyAsync(s.scratch, g2m, 192, cudaMemcpyHostToDevice, s.stream));
@@ -380,70 +380,81 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
     CK(cudaEventRecord(s.ev[14], st));
     CK(cudaStreamWaitEvent(s2, s.ev[14], 0));
     s.sg_batch = s.sg_min && n >= s.sg_min && n >= 2;   // subgroup membership through the bucket slices of S1 and S3
-    // host buffers, large batch: only the first eighth of the commitments is copied ahead of K1; the rest of C,
-    // then pi, z, y follow on the side stream, one transfer at a time, while K1 already runs
-    const size_t head = (!on_device && s.sg_batch && n >= 65536) ? (n / 8) & ~(size_t)127 : 0;
-    s.head_mode = head != 0;
-    if (!on_device) {
-        if (head) {
-            // all transfers on ONE stream, in the order K1 needs them (copies of the high-priority side stream
-            // overtake a copy queued on the main stream: measured, the head then arrived last)
-            CK(cudaMemcpyAsync(s.dC, C, 48 * head, cudaMemcpyHostToDevice, s2));
-            CK(cudaEventRecord(s.ev[17], s2));
-            CK(cudaStreamWaitEvent(st, s.ev[17], 0));
-            CK(cudaMemcpyAsync(s.dC + 48 * head, C + 48 * head, 48 * (n - head), cudaMemcpyHostToDevice, s2));
-            CK(cudaEventRecord(s.ev[1], s2));               // C resident (together with ev[17])
-        } else {
-            CK(cudaMemcpyAsync(s.dC, C, 48 * n, cudaMemcpyHostToDevice, s2));
-            CK(cudaEventRecord(s.ev[1], s2));               // C resident
-            CK(cudaStreamWaitEvent(st, s.ev[1], 0));
-        }
-        CK(cudaMemcpyAsync(s.dpi, pi, 48 * n, cudaMemcpyHostToDevice, s2));
-        CK(cudaMemcpyAsync(s.dz, z, 32 * n, cudaMemcpyHostToDevice, s2));
-        CK(cudaMemcpyAsync(s.dy, y, 32 * n, cudaMemcpyHostToDevice, s2));
-        s.cur_C = s.dC; s.cur_z = s.dz; s.cur_y = s.dy; s.cur_pi = s.dpi;
-    } else {
-        s.cur_C = C; s.cur_z = z; s.cur_y = y; s.cur_pi = pi;
-    }
     s.cur_n = n;
     s.have_sums = false;
     s.sums_pending = false;
     s.have_ab = false;
-    if (on_device) CK(cudaEventRecord(s.ev[1], st));    // inputs already resident
-    CK(cudaEventRecord(s.ev[13], s2));                  // pi, z, y resident
-    // side stream: hashes (need all four arrays) start before K1 fills the SMs
-    if (on_device) CK(cudaStreamWaitEvent(s2, s.ev[1], 0));
-    launch_leaf_hash(s2, s.cur_C, s.cur_z, s.cur_y, s.cur_pi, n, s.leaves, s.counters);
-    launch_chunk_hash(s2, s.leaves, n, s.digests);
+    s.head_mode = false;
+    if (on_device) {
+        s.cur_C = C; s.cur_z = z; s.cur_y = y; s.cur_pi = pi;
+        CK(cudaEventRecord(s.ev[1], st));                // inputs already resident
+        CK(cudaEventRecord(s.ev[13], s2));
+        CK(cudaStreamWaitEvent(s2, s.ev[1], 0));
+        // side stream: hashes start before K1 fills the SMs
+        launch_leaf_hash(s2, C, z, y, pi, n, s.leaves, s.counters);
+        launch_chunk_hash(s2, s.leaves, n, s.digests);
+        if (s.sg_batch) {
+            // ONE launch over both arrays: every launch boundary costs the idle tail of a partial wave (2n points are
+            // 36.9 waves of 148 x 384 threads at n = 2^20, two launches of n points 2 x 18.5 -> 38)
+            launch_decompress_sqrt(st, C, pi, n, s.pts, s.status, s.counters);
+        } else {
+            launch_decompress(st, C, pi, n, s.pts, s.k1_tmp, s.status, s.counters);
+        }
+    } else {
+        // Host buffers (pinned or pageable -- the library stages nothing itself: a cudaMemcpyAsync from pageable memory
+        // returns once the driver has staged the data, so every K1 launch is issued BEFORE the copies it does not depend
+        // on).  All transfers go on ONE stream in the order K1 consumes them: C in growing pieces, pi, then z and y
+        // (copies on the high-priority side stream overtake a copy queued on the main stream: measured).
+        s.cur_C = s.dC; s.cur_z = s.dz; s.cur_y = s.dy; s.cur_pi = s.dpi;
+        size_t cut[4] = {0, 0, 0, n};                    // C is copied (and decompressed) in the pieces [cut[j], cut[j+1])
+        int ncut = 1;
+        if (s.sg_batch && n >= 65536) {
+            cudaPointerAttributes at;
+            bool pageable = cudaPointerGetAttributes(&at, C) != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+            cudaGetLastError();
+            if (pageable) { cut[1] = (n / 16) & ~(size_t)127; cut[2] = (n / 4) & ~(size_t)127; ncut = 3; }
+            else { cut[1] = (n / 8) & ~(size_t)127; cut[2] = n; ncut = 2; }
+            s.head_mode = true;
+        } else {
+            cut[1] = n; cut[2] = n;
+        }
+        for (int j = 0; j < ncut; ++j) {
+            const size_t a = cut[j], m = cut[j + 1] - a;
+            CK(cudaMemcpyAsync(s.dC + 48 * a, C + 48 * a, 48 * m, cudaMemcpyHostToDevice, s2));
+            cudaEvent_t e = j == 0 ? (s.head_mode ? s.ev[17] : s.ev[1]) : (j + 1 == ncut ? s.ev[1] : s.ev[23]);
+            CK(cudaEventRecord(e, s2));
+            if (s.head_mode) {
+                // pieces alternate between two streams: the next piece starts in the idle tail of the previous one
+                cudaStream_t ks = (j & 1) ? s.stream5 : st;
+                if (j == 1) CK(cudaStreamWaitEvent(ks, s.ev[14], 0));          // after the counters' memset
+                CK(cudaStreamWaitEvent(ks, e, 0));
+                launch_decompress_sqrt_points(ks, s.dC + 48 * a, m, s.pts + 2 * a, s.status + a, s.counters);
+            }
+        }
+        CK(cudaMemcpyAsync(s.dpi, pi, 48 * n, cudaMemcpyHostToDevice, s2));
+        CK(cudaEventRecord(s.ev[22], s2));               // pi resident
+        CK(cudaStreamWaitEvent(st, s.ev[1], 0));
+        CK(cudaStreamWaitEvent(st, s.ev[22], 0));
+        if (s.head_mode) {
+            cudaStream_t ks = (ncut & 1) ? s.stream5 : st;
+            if (ks != st) CK(cudaStreamWaitEvent(ks, s.ev[22], 0));
+            launch_decompress_sqrt_points(ks, s.dpi, n, s.pts + 2 * n, s.status + n, s.counters);
+            CK(cudaEventRecord(s.ev[25], s.stream5));
+            CK(cudaStreamWaitEvent(st, s.ev[25], 0));   // every piece has finished before the main stream goes on
+        } else if (s.sg_batch) {
+            launch_decompress_sqrt(st, s.dC, s.dpi, n, s.pts, s.status, s.counters);
+        } else {
+            launch_decompress(st, s.dC, s.dpi, n, s.pts, s.k1_tmp, s.status, s.counters);
+        }
+        CK(cudaMemcpyAsync(s.dz, z, 32 * n, cudaMemcpyHostToDevice, s2));
+        CK(cudaMemcpyAsync(s.dy, y, 32 * n, cudaMemcpyHostToDevice, s2));
+        CK(cudaEventRecord(s.ev[13], s2));               // all four arrays resident
+        launch_leaf_hash(s2, s.dC, s.dz, s.dy, s.dpi, n, s.leaves, s.counters);
+        launch_chunk_hash(s2, s.leaves, n, s.digests);
+    }
     size_t nch = (n + KZGB_CHUNK - 1) / KZGB_CHUNK;
     CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, s2));
     CK(cudaEventRecord(s.ev[2], s2));
-    if (s.sg_batch) {
-        // K1a only; commitments first, then (once pi is resident) proofs -- hides the H2D copy
-        if (head) {
-            launch_decompress_sqrt_points(st, s.cur_C, head, s.pts, s.status, s.counters);
-            CK(cudaStreamWaitEvent(st, s.ev[1], 0));
-            launch_decompress_sqrt_points(st, s.cur_C + 48 * head, n - head, s.pts + 2 * head, s.status + head, s.counters);
-            CK(cudaStreamWaitEvent(st, s.ev[13], 0));
-            launch_decompress_sqrt_points(st, s.cur_pi, n, s.pts + 2 * n, s.status + n, s.counters);
-        } else if (n >= 65536) {
-            launch_decompress_sqrt_points(st, s.cur_C, n, s.pts, s.status, s.counters);
-            CK(cudaStreamWaitEvent(st, s.ev[13], 0));
-            launch_decompress_sqrt_points(st, s.cur_pi, n, s.pts + 2 * n, s.status + n, s.counters);
-        } else {
-            // small batch: one launch over both arrays (two would be two serial latencies of the square-root chain)
-            CK(cudaStreamWaitEvent(st, s.ev[13], 0));
-            launch_decompress_sqrt(st, s.cur_C, s.cur_pi, n, s.pts, s.status, s.counters);
-        }
-    } else if (!on_device && n >= 32768) {
-        // K1 in two halves: commitments, then (once pi is resident) proofs -- hides most of the H2D copy
-        launch_decompress_points(st, s.cur_C, n, s.pts, s.k1_tmp, s.status, s.counters);
-        CK(cudaStreamWaitEvent(st, s.ev[13], 0));
-        launch_decompress_points(st, s.cur_pi, n, s.pts + 2 * n, s.k1_tmp + 3 * n, s.status + n, s.counters);
-    } else {
-        CK(cudaStreamWaitEvent(st, s.ev[13], 0));
-        launch_decompress(st, s.cur_C, s.cur_pi, n, s.pts, s.k1_tmp, s.status, s.counters);
-    }
     // the setup point G joins the GLV-split sum with scalar -(sum r_i y_i): point slot 2n; then phi(pi_i), phi(G)
     CK(cudaMemcpyAsync(s.pts + 2 * (2 * n), s.g1_pt, 2 * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     launch_endo_points(st, s.pts + 2 * n, n + 1, s.pts + 2 * (2 * n + 1));
@@ -807,6 +818,64 @@ kzgb_ret kzgb_shard_phase2(kzgb_ctx* ctx, int slot, const uint8_t root[32], uint
     ctx->art.n_bad_points = s.h_small[0];
     ctx->art.n_bad_scalars = s.h_small[1];
     return (s.h_small[0] || s.h_small[1]) ? KZGB_BADARGS : KZGB_OK;
+}
+// Shard-level entry points of the Horner-free pairing check: the shard's 66 pairing terms (mpair.cuh) instead of the
+// 320-byte partial -- no serial Horner chain on any shard.  The call returns as soon as the terms are on the host; the
+// verdict of the shard's input validation (malformed points / scalars, batched subgroup check) is collected by
+// kzgb_shard_finish, which can be called after the terms have been handed on.
+kzgb_ret kzgb_shard_phase2_terms(kzgb_ctx* ctx, int slot, const uint8_t root[32], uint64_t global_offset, void*,
+                                 uint8_t terms_out[KZGB_TERMS_BYTES]) {
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size() || !root || !terms_out) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[slot];
+    kzgb_ret rc = phase2(s, root, global_offset, false, false);
+    if (rc) return rc;
+    uint8_t* wire = s.scratch + 16384;
+    launch_mp_terms_to_wire(s.stream, s.mp_terms, s.sum_ry, wire);
+    CK(cudaMemcpyAsync(s.h_terms, wire, KZGB_TERMS_BYTES, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaEventRecord(s.ev[7], s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    CK(cudaGetLastError());
+    memcpy(terms_out, s.h_terms, KZGB_TERMS_BYTES);
+    fill_stage_ms(ctx->art, s, 0.0f);
+    return KZGB_OK;
+}
+kzgb_ret kzgb_shard_finish(kzgb_ctx* ctx, int slot, uint32_t* n_bad_points, uint32_t* n_bad_scalars) {
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[slot];
+    if (!s.cur_n) return KZGB_BADARGS;
+    CK(cudaSetDevice(s.device));
+    CK(cudaStreamSynchronize(s.stream));                // per-point path: the counters were copied on the main stream
+    if (kzgb_ret rc = finish_subgroup(s)) return rc;
+    ctx->art.n_bad_points = s.h_small[0];
+    ctx->art.n_bad_scalars = s.h_small[1];
+    if (n_bad_points) *n_bad_points = s.h_small[0];
+    if (n_bad_scalars) *n_bad_scalars = s.h_small[1];
+    return (s.h_small[0] || s.h_small[1]) ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret kzgb_combine_verify_terms(kzgb_ctx* ctx, const uint8_t* terms, int n_shards, bool* ok) {
+    if (!ctx || !terms || !ok) return KZGB_BADARGS;
+    *ok = false;
+    if (n_shards < 1 || n_shards > 64) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    CK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
+    // second half of the pinned mailbox: the first record may still hold this slot's own outgoing terms
+    uint8_t* stage = s.h_terms;
+    memcpy(stage, terms, (size_t)KZGB_TERMS_BYTES * n_shards);
+    uint8_t* wire = s.scratch + 65536;
+    uint32_t* bad = (uint32_t*)(s.scratch + 32768);
+    CK(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st));
+    CK(cudaMemcpyAsync(wire, stage, (size_t)KZGB_TERMS_BYTES * n_shards, cudaMemcpyHostToDevice, st));
+    launch_mp_terms_from_wire(st, wire, n_shards, s.mp_terms_in, s.sum_ry, bad);
+    CK(cudaMemcpyAsync(s.h_small + 20, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    kzgb_ret rc = mp_finish(s, s.mp_terms_in, n_shards, s.mp_tab, ok);
+    s.have_sums = false; s.sums_pending = false; s.have_ab = false;
+    ctx->terms_combined = false;
+    if (rc || s.h_small[20]) { *ok = false; return rc ? rc : KZGB_BADARGS; }
+    ctx->terms_combined = true;
+    ctx->ab_terms = s.mp_terms_in; ctx->ab_shards = n_shards; ctx->ab_gather_sum_ry = false;
+    ctx->art.stage_ms[8] = ev_ms(s.ev[7], s.ev[8]);
+    return KZGB_OK;
 }
 kzgb_ret kzgb_combine_verify(kzgb_ctx* ctx, const uint8_t* partials, int n_partials, bool* ok) {
     if (!ctx || !partials || !ok) return KZGB_BADARGS;

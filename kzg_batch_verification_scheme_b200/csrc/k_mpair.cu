@@ -217,3 +217,45 @@ void launch_mp_ab(cudaStream_t s, const G1Xyzz* terms_in, int n_shards, G1Jac* A
     KZ_COUNT_LAUNCH();
 }
 size_t mp_part_entries() { return (size_t)KZ_N_LINES * MP_NG; }
+
+// ------------------------------------------------------------------ wire format of a shard's terms (kzgb200.h KZGB_TERMS_BYTES)
+// 66 terms x (X | Y | ZZ | ZZZ), 48 B big-endian canonical each, then sum r_i y_i of the shard (32 B big-endian).
+__global__ void __launch_bounds__(128) k_mp_terms_to_wire(const G1Xyzz* __restrict__ terms, const u32* __restrict__ sum_ry, u8* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4 * KZ_MP_PAIRS) fp_to_be(out + 48 * i, (&terms[0].X)[i]);
+    else if (i == 4 * KZ_MP_PAIRS) {
+        Fr v;
+        for (int k = 0; k < 8; ++k) v.v[k] = sum_ry[k];
+        fr_raw_to_be(out + 48 * 4 * KZ_MP_PAIRS, v);
+    }
+}
+void launch_mp_terms_to_wire(cudaStream_t s, const G1Xyzz* terms, const uint32_t* sum_ry, uint8_t* out) {
+    k_mp_terms_to_wire<<<(4 * KZ_MP_PAIRS + 1 + 127) / 128, 128, 0, s>>>(terms, sum_ry, out);
+    KZ_COUNT_LAUNCH();
+}
+// n_shards wire records -> terms_in[g * 66 + p] (Montgomery), sum_ry_total = sum of the shards' sum r_i y_i;
+// *bad += coordinates >= p or scalars >= r
+__global__ void __launch_bounds__(128) k_mp_terms_from_wire(const u8* __restrict__ in, int n_shards, G1Xyzz* __restrict__ terms,
+                                                             u32* __restrict__ sum_ry_total, u32* __restrict__ bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, per = 4 * KZ_MP_PAIRS;
+    if (i < per * n_shards) {
+        const int g = i / per, k = i - g * per;
+        Fp v;
+        if (!fp_from_be(v, in + (size_t)g * (48 * per + 32) + 48 * k)) { atomicAdd(bad, 1u); v = fp_zero(); }
+        (&terms[(size_t)g * KZ_MP_PAIRS].X)[k] = v;
+    } else if (i == per * n_shards) {
+        Fr acc = fr_zero();
+        for (int g = 0; g < n_shards; ++g) {
+            Fr v;
+            fr_raw_from_be(v, in + (size_t)g * (48 * per + 32) + 48 * per);
+            if (!fr_raw_is_canonical(v)) { atomicAdd(bad, 1u); continue; }
+            acc = fr_add(acc, v);
+        }
+        for (int k = 0; k < 8; ++k) sum_ry_total[k] = acc.v[k];
+    }
+}
+void launch_mp_terms_from_wire(cudaStream_t s, const uint8_t* in, int n_shards, G1Xyzz* terms, uint32_t* sum_ry_total, uint32_t* bad) {
+    const int n = 4 * KZ_MP_PAIRS * n_shards + 1;
+    k_mp_terms_from_wire<<<(n + 127) / 128, 128, 0, s>>>(in, n_shards, terms, sum_ry_total, bad);
+    KZ_COUNT_LAUNCH();
+}

@@ -113,6 +113,9 @@ void launch_mp_check(cudaStream_t s, const G2Lines* tab, const MpCoef* coef, Fp1
 size_t mp_part_entries();
 // artefacts: AB[0] = A, AB[1] = B (Jacobian) by Horner over the shards' terms
 void launch_mp_ab(cudaStream_t s, const G1Xyzz* terms_in, int n_shards, G1Jac* AB);
+// wire format of the shard-level ABI (KZGB_TERMS_BYTES per shard): canonical big-endian coordinates + sum r_i y_i
+void launch_mp_terms_to_wire(cudaStream_t s, const G1Xyzz* terms, const uint32_t* sum_ry, uint8_t* out);
+void launch_mp_terms_from_wire(cudaStream_t s, const uint8_t* in, int n_shards, G1Xyzz* terms, uint32_t* sum_ry_total, uint32_t* bad);
 
 // ---- k_cells.cu (cell batch, BASELINE.json config[4])
 void launch_cell_twiddles(cudaStream_t s, Fr* W /*8192*/);

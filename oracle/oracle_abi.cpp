@@ -168,6 +168,69 @@ kzgb_ret kzgb_combine_verify(kzgb_ctx* c, const uint8_t* parts, int np, bool* ok
     return KZGB_OK;
 }
 
+// Terms exchange (kzgb200.h KZGB_TERMS_BYTES): any 2 x 33 points with sum_t 2^(4t) V_t = A_shard resp. B_shard are a valid
+// record.  The oracle has no bucket slices to read terms from, so it sends V_0 = A_shard, V_33 = -S3_shard and
+// infinity elsewhere; its combine accepts arbitrary records (the CUDA library's included) and evaluates
+// A = sum_t 2^(4t) sum_g V_t^g by Horner before the ordinary two-pairing check.
+kzgb_ret kzgb_shard_phase2_terms(kzgb_ctx* c, int slot, const uint8_t root[32], uint64_t off, void*, uint8_t out[KZGB_TERMS_BYTES]) {
+    if (!c || slot < 0 || slot >= (int)c->shards.size() || !root || !out) return KZGB_BADARGS;
+    Partial p = shard_phase2(c->shards[slot], root, off, c->threads);
+    u64 k[4];
+    p.sum_ry.to_raw(k);
+    G1J a = p.s1.add(p.s2).add(c->setup.g1.jac().mul(k, 4).neg());
+    memset(out, 0, KZGB_TERMS_BYTES);
+    auto put = [](uint8_t* o, const G1J& j) {                 // XYZZ of a Jacobian point: (X, Y, Z^2, Z^3)
+        if (j.is_inf()) return;
+        Fp zz = j.Z.sqr();
+        j.X.to_bytes_be(o); j.Y.to_bytes_be(o + 48); zz.to_bytes_be(o + 96); (zz * j.Z).to_bytes_be(o + 144);
+    };
+    put(out, a);
+    put(out + 192 * (KZGB_N_TERMS / 2), p.s3.neg());
+    p.sum_ry.to_bytes_be(out + 192 * KZGB_N_TERMS);
+    return KZGB_OK;
+}
+kzgb_ret kzgb_shard_finish(kzgb_ctx* c, int slot, uint32_t* bad_points, uint32_t* bad_scalars) {
+    if (!c || slot < 0 || slot >= (int)c->shards.size()) return KZGB_BADARGS;
+    const Shard& sh = c->shards[slot];
+    if (bad_points) *bad_points = sh.bad_points;
+    if (bad_scalars) *bad_scalars = sh.bad_scalars;
+    return (sh.bad_points || sh.bad_scalars) ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret kzgb_combine_verify_terms(kzgb_ctx* c, const uint8_t* terms, int ns, bool* ok) {
+    if (!c || !terms || ns < 1 || ns > 64 || !ok) return KZGB_BADARGS;
+    *ok = false;
+    const int T = KZGB_N_TERMS / 2;
+    G1J side[2] = {G1J::inf(), G1J::inf()};
+    Fr sry = Fr::zero();
+    for (int sd = 0; sd < 2; ++sd)
+        for (int t = T - 1; t >= 0; --t) {
+            for (int u = 0; u < 4; ++u) side[sd] = side[sd].dbl();
+            for (int g = 0; g < ns; ++g) {
+                const uint8_t* b = terms + (size_t)KZGB_TERMS_BYTES * g + 192 * (sd * T + t);
+                Fp X, Y, ZZ, ZZZ;
+                if (!Fp::from_bytes_be(X, b) || !Fp::from_bytes_be(Y, b + 48) || !Fp::from_bytes_be(ZZ, b + 96) ||
+                    !Fp::from_bytes_be(ZZZ, b + 144))
+                    return KZGB_BADARGS;
+                if (ZZ.is_zero()) continue;
+                side[sd] = side[sd].add(G1J{X * ZZ, Y * ZZZ, ZZ});       // (X/ZZ, Y/ZZZ) with Z = ZZ, as ZZ^3 = ZZZ^2
+            }
+        }
+    for (int g = 0; g < ns; ++g) {
+        Fr v;
+        if (!Fr::from_bytes_be(v, terms + (size_t)KZGB_TERMS_BYTES * g + 192 * KZGB_N_TERMS)) return KZGB_BADARGS;
+        sry = sry + v;
+    }
+    c->art = Artifacts();
+    c->art.S1 = c->art.S2 = c->art.S3 = G1A::infinity();
+    c->art.A = g1_affine(side[0]);
+    c->art.B = g1_affine(side[1]);
+    c->art.sum_ry = sry;
+    G1A P[2] = {c->art.A, c->art.B};
+    G2A Q[2] = {c->setup.g2_0, c->setup.g2_1};
+    *ok = pairing_product_is_one(P, Q, 2);
+    return KZGB_OK;
+}
+
 kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, const uint32_t* ci, const uint32_t* xi,
                                      const uint8_t* cells, const uint8_t* proofs, size_t m, kzgb_ctx* c) {
     if (!ok) return KZGB_BADARGS;

@@ -140,6 +140,11 @@ def test_gpu_config_n65536_planted_invalid(gpu_lib, oracle_lib):
     art = ctx.last_artifacts()
     assert oracle_lib.lib.kzgb_oracle_tau_shortcut(art["A"], art["B"]) == 1
     assert octx.pairing_check(art["A"], art["B"]) == (0, True)
+    # byte-exact diff of every artefact against the oracle at the size the metric is quoted on (window width c = 13 here)
+    assert octx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    oart = octx.last_artifacts()
+    for key in ("S1", "S2", "S3", "A", "B", "sum_ry", "root"):
+        assert art[key] == oart[key], key
     # spot parity of the oracle generator on a slice of the same stream
     assert octx.synth_instance(seed, 12345, 64) == tuple(x[s * 12345:s * (12345 + 64)] for x, s in ((C, 48), (Z, 32), (Y, 32), (PI, 48)))
     j = oracle_lib.lib.kzgb_oracle_plant_index(ctypes.c_uint64(seed), ctypes.c_uint64(n))
@@ -148,6 +153,13 @@ def test_gpu_config_n65536_planted_invalid(gpu_lib, oracle_lib):
     assert ctx.verify_kzg_proof_batch(C, Z, Y, bytes(bad), n) == (0, False)
     art = ctx.last_artifacts()
     assert oracle_lib.lib.kzgb_oracle_tau_shortcut(art["A"], art["B"]) == 0
+    # the planted batch against the oracle: same verdict, same sums and pairing inputs, and the oracle's pairing on the
+    # CUDA library's A, B rejects as well
+    assert octx.verify_kzg_proof_batch(C, Z, Y, bytes(bad), n) == (0, False)
+    oart = octx.last_artifacts()
+    for key in ("S1", "S2", "S3", "A", "B", "sum_ry", "root"):
+        assert art[key] == oart[key], key
+    assert octx.pairing_check(art["A"], art["B"]) == (0, False)
     # an off-subgroup point anywhere in the batch is BADARGS
     bad2 = bytearray(C)
     bad2[48 * 777:48 * 778] = b.g1_compress((0, 2))
@@ -333,6 +345,14 @@ def test_gpu_full_size_2p20_properties(gpu_lib, oracle_lib):
     assert oracle_lib.lib.kzgb_oracle_tau_shortcut(ab["A"], ab["B"]) == 0
     # a slice of the device generator's stream equals the oracle generator's bytes
     octx = oracle_lib.test_context()
+    # byte-exact diff of every artefact against the oracle at the benchmarked size (c = 16): ~25 s of CPU on 16 threads
+    assert one.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    a1 = one.last_artifacts()
+    assert octx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    ao = octx.last_artifacts()
+    for key in ("S1", "S2", "S3", "A", "B", "sum_ry", "root"):
+        assert a1[key] == ao[key], key
+    assert a2["A"] == ao["A"] and a2["B"] == ao["B"] and a2["sum_ry"] == ao["sum_ry"]      # two shards vs oracle
     assert octx.synth_instance(seed, 777777, 32) == tuple(x[w * 777777:w * (777777 + 32)] for x, w in ((C, 48), (Z, 32), (Y, 32), (PI, 48)))
     # MSM linearity at full size: MSM(k) + MSM(k') == MSM(k + k') over 2^20 points
     rc, aff, st = one.g1_decompress_batch(C)
@@ -356,3 +376,40 @@ def test_gpu_full_size_2p20_properties(gpu_lib, oracle_lib):
     unit = (1).to_bytes(32, "big")
     assert one.g1_msm(r1[1] + r2[1], unit + unit, 255) == (0, r3[1]) and r3[1] != bytes(96)
     one.close(); ctx.close(); octx.close()
+
+
+def test_gpu_in_process_multi_device_equals_single(gpu_lib, oracle_lib):
+    """The in-process multi-device path of the C ABI (kzgb_ctx_create(devices = {0..G-1}) -> verify_kzg_proof_batch,
+    BASELINE.json:5 "combined on the host, no NCCL") on every physical device of the box: verdict, A, B, sum_ry and
+    root equal the one-device run and the oracle; a planted wrong proof in the LAST shard is rejected; an
+    off-subgroup point in a middle shard is BADARGS with the oracle's count."""
+    import torch
+    G = torch.cuda.device_count()
+    if G < 2:
+        pytest.skip("needs at least 2 physical GPUs (run with gpurun --gpus 2)")
+    n, seed = (1 << 17) + 4321, 0x4B5A4731
+    one = gpu_lib.test_context(devices=[0], n_max=n)
+    octx = oracle_lib.test_context()
+    C, Z, Y, PI = one.synth_instance(seed, 0, n)
+    assert one.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    a1 = one.last_artifacts()
+    assert octx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+    ao = octx.last_artifacts()
+    bad = bytearray(PI)
+    bad[48 * (n - 2):48 * (n - 1)], bad[48 * (n - 1):48 * n] = PI[48 * (n - 1):48 * n], PI[48 * (n - 2):48 * (n - 1)]
+    off = bytearray(C)
+    off[48 * (n // 2):48 * (n // 2 + 1)] = b.g1_compress((0, 2))
+    counts = sorted({2, G} | ({4} if G >= 4 else set()))
+    for g in counts:
+        ctx = gpu_lib.test_context(devices=list(range(g)), n_max=n)
+        for _ in range(2):                                      # second call: every slot's workspaces are reused
+            assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+            ag = ctx.last_artifacts()
+            for key in ("A", "B", "sum_ry", "root"):
+                assert ag[key] == a1[key] == ao[key], (g, key)
+        assert ctx.verify_kzg_proof_batch(C, Z, Y, bytes(bad), n) == (0, False)
+        assert ctx.verify_kzg_proof_batch(bytes(off), Z, Y, PI, n) == (1, False)
+        assert ctx.last_artifacts()["n_bad_points"] == 1
+        assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
+        ctx.close()
+    one.close(); octx.close()

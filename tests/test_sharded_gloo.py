@@ -20,30 +20,47 @@ dist.init_process_group(backend="gloo", rank=rank, world_size=world)
 lib = KzgLib(os.path.join(os.environ["KZGB_ROOT"], "oracle", "libkzgb_oracle.so"))
 ctx = lib.test_context()
 ctx.set_threads(2)
+from kzg_batch_verification_scheme_b200.sharded import HostMailbox
 n_local, seed = 1024, 0x4B5A4705
-C, Z, Y, PI = ctx.synth_instance(seed, rank * n_local, n_local)
-rc, ok = sharded_verify(ctx, dist, rank, world, C, Z, Y, PI, n_local)
-assert rc == 0
+mailbox = HostMailbox(dist, rank, world, 2 * n_local, tag="test%d" % world)
+full = lib.test_context()
+for box, mode in ((None, "terms"), (None, "partials"), (mailbox, "terms"), (mailbox, "partials")):
+    C, Z, Y, PI = ctx.synth_instance(seed, rank * n_local, n_local)
+    rc, ok = sharded_verify(ctx, dist, rank, world, C, Z, Y, PI, n_local, box=box, mode=mode)
+    assert (rc, ok) == (0, True), (rc, ok, mode)              # every rank returns the verdict
+    if rank == 0:
+        art = ctx.last_artifacts()
+        Cf, Zf, Yf, PIf = full.synth_instance(seed, 0, n_local * world)
+        assert full.verify_kzg_proof_batch(Cf, Zf, Yf, PIf, n_local * world) == (0, True)
+        ref = full.last_artifacts()
+        assert art["A"] == ref["A"] and art["B"] == ref["B"] and art["sum_ry"] == ref["sum_ry"]
+    # a wrong proof on the LAST rank must flip the verdict everywhere
+    if rank == world - 1:
+        PI = PI[:48] + PI[:48] + PI[96:]
+    assert sharded_verify(ctx, dist, rank, world, C, Z, Y, PI, n_local, box=box, mode=mode) == (0, False)
+    # a malformed element on rank 1 is BADARGS everywhere
+    if rank == min(1, world - 1):
+        Z = bytes([0xFF]) * 32 + Z[32:]
+    rc, ok = sharded_verify(ctx, dist, rank, world, C, Z, Y, PI, n_local, box=box, mode=mode)
+    assert (rc, ok) == (1, False), rc
+# shards of different sizes (the last one ragged): offsets are the prefix sums of the gathered sizes
+sizes = [256 * (r + 1) for r in range(world - 1)] + [333]
+off, n_r, n_total = sum(sizes[:rank]), sizes[rank], sum(sizes)
+C, Z, Y, PI = ctx.synth_instance(seed + 1, off, n_r)
+assert sharded_verify(ctx, dist, rank, world, C, Z, Y, PI, n_r, box=mailbox) == (0, True)
 if rank == 0:
-    assert ok is True
     art = ctx.last_artifacts()
-    full = lib.test_context()
-    Cf, Zf, Yf, PIf = full.synth_instance(seed, 0, n_local * world)
-    assert full.verify_kzg_proof_batch(Cf, Zf, Yf, PIf, n_local * world) == (0, True)
+    Cf, Zf, Yf, PIf = full.synth_instance(seed + 1, 0, n_total)
+    assert full.verify_kzg_proof_batch(Cf, Zf, Yf, PIf, n_total) == (0, True)
     ref = full.last_artifacts()
     assert art["A"] == ref["A"] and art["B"] == ref["B"] and art["sum_ry"] == ref["sum_ry"]
-# a wrong proof on the LAST rank must flip the verdict on rank 0
-if rank == world - 1:
-    PI = PI[:48] + PI[:48] + PI[96:]
-rc, ok = sharded_verify(ctx, dist, rank, world, C, Z, Y, PI, n_local)
-assert rc == 0
-if rank == 0:
-    assert ok is False
-# a malformed element on rank 1 is BADARGS everywhere
-if rank == min(1, world - 1):
-    Z = bytes([0xFF]) * 32 + Z[32:]
-rc, ok = sharded_verify(ctx, dist, rank, world, C, Z, Y, PI, n_local)
-assert rc == 1, rc
+assert sharded_verify(ctx, dist, rank, world, C, Z, Y, PI, n_r) == (0, True)          # same over gloo tensors
+# a shard boundary off the 128-proof chunk grid is refused on every rank
+if world > 1:
+    n_bad = 100 if rank == 0 else 128
+    Cb, Zb, Yb, PIb = ctx.synth_instance(seed + 2, 0, n_bad)
+    assert sharded_verify(ctx, dist, rank, world, Cb, Zb, Yb, PIb, n_bad, box=mailbox, n_max_local=2 * n_local) == (1, False)
+mailbox.close()
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
