@@ -195,6 +195,8 @@ def main():
             self.pptr = [t.data_ptr() for t in self.pinned]
             self.hptr = [t.data_ptr() for t in self.plain]
 
+    host_trace = {}
+
     def barrier():
         torch.cuda.synchronize()
         if multi:
@@ -209,7 +211,7 @@ def main():
             else:
                 rc, ok = ctx.verify_kzg_proof_batch(*ptrs, w.n_local)
         else:
-            rc, ok = sharded_verify(ctx, dist, rank, world, *ptrs, w.n_local, on_device=on_device, stream=stream, box=box)
+            rc, ok = sharded_verify(ctx, dist, rank, world, *ptrs, w.n_local, on_device=on_device, stream=stream, box=box, trace=host_trace)
         assert rc == 0, rc
         return ok
 
@@ -273,6 +275,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev, stages, launches = timed(w, w.dptr, True, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
+    host_phase_ms = {k: v / (args.steps + args.warmup) for k, v in host_trace.items()}     # rank 0's host wall time per phase
     ms_e2e, stages_e2e, _ = timed(w, w.hptr, False, args.steps, max(1, args.warmup // 2))
     ms_pin, stages_pin, _ = timed(w, w.pptr, False, args.steps, max(1, args.warmup // 2))
     reject_ok = planted(w)
@@ -280,7 +283,7 @@ def main():
     if multi:
         # the other scaling mode as a second timed pass of the same line
         n_other = n_cfg if args.scaling == "strong" else max(CHUNK, n_cfg // world)
-        del w.pinned, w.plain
+        w.pinned = w.plain = None                            # free the host mirrors of the first pass
         w2 = Workload(n_other)
         ms2, st2, _ = timed(w2, w2.dptr, True, args.steps, args.warmup)
         ms2e, _, _ = timed(w2, w2.hptr, False, args.steps, 1)
@@ -477,6 +480,7 @@ def main():
         }
         if other:
             line[other["scaling"]] = other
+            line["host_phase_ms"] = host_phase_ms
         print(json.dumps(line), flush=True)
     ctx.close()
     if multi:

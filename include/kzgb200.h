@@ -125,8 +125,8 @@ kzgb_ret kzgb_last_artifacts(kzgb_ctx *ctx, kzgb_artifacts *out);
  * the device and (out_on_device != 0) leaves the bytes in the given device buffers. */
 kzgb_ret kzgb_synth_instance(kzgb_ctx *ctx, uint64_t seed, uint64_t offset, size_t n, uint8_t *C, uint8_t *z,
                              uint8_t *y, uint8_t *pi, int out_on_device);
-/* insecure test setup from the documented tau (g1: n1*48 B, g2: n2*96 B); no ctx needed */
-kzgb_ret kzgb_synth_setup(uint8_t *g1_monomial, size_t n1, uint8_t *g2_monomial, size_t n2);
+/* (The insecure test setup itself -- [tau^i]G1, [tau^i]G2 from the documented tau -- needs G2 scalar multiplication, which
+ * the verification path never uses: it is generated by the oracle library only, include/kzgb200_testing.h.) */
 
 /* ---- primitive-level debug operator (tests only): applies op to `count` records of canonical
  * big-endian operands; see KZGB_OP_* for record layouts. */
@@ -149,9 +149,7 @@ enum {
     KZGB_OP_FP12_INV = 16,   /* in 576 out 576 */
     KZGB_OP_FINAL_EXP = 17,  /* in 576 out 576 : f^(3(p^12-1)/r) */
     KZGB_OP_MILLER_FE = 18,  /* in 192 (A|B affine) out 576 : final_exp(miller(A,G2) miller(B,[tau]G2)) */
-    KZGB_OP_SHA256_64 = 19,  /* in 64 out 32 : SHA-256 of a 64-byte message */
-    KZGB_OP_FPD_MUL = 20,    /* in 96 (a|b) out 48 : a*b through the FP64-limb multiplier (fpd.cuh); equals FP_MUL */
-    KZGB_OP_FPD_SQR_CHAIN = 21 /* in 48 out 48 : a^(2^64) by 64 lazy FP64-limb squarings, reduced once at the end */
+    KZGB_OP_SHA256_64 = 19   /* in 64 out 32 : SHA-256 of a 64-byte message */
 };
 kzgb_ret kzgb_debug_op(kzgb_ctx *ctx, int op, const uint8_t *in, uint8_t *out, size_t count);
 

@@ -23,7 +23,8 @@ STAGE_NAMES = ["h2d", "decompress", "hash", "root_host", "challenges", "msm_sort
 
 OP = dict(FP_MUL=1, FP_SQR=2, FP_ADD=3, FP_SUB=4, FP_INV=5, FP_SQRT_CAND=6, FR_MUL=7, FR_ADD=8, G1_ADD=9,
           G1_DBL=10, G1_MUL=11, G1_MUL_XSQ=12, FP12_MUL=13, FP12_FROB1=14, FP12_FROB2=15, FP12_INV=16,
-          FINAL_EXP=17, MILLER_FE=18, SHA256_64=19, FPD_MUL=20, FPD_SQR_CHAIN=21)
+          FINAL_EXP=17, MILLER_FE=18, SHA256_64=19,
+          FPD_MUL=20, FPD_SQR_CHAIN=21)      # 20, 21: FP64-limb multiplier of tools/microbench/fpd.cuh -- tests/emu only, not in the product
 OP_SIZES = {1: (96, 48), 2: (48, 48), 3: (96, 48), 4: (96, 48), 5: (48, 48), 6: (48, 48), 7: (64, 32), 8: (64, 32),
             9: (192, 96), 10: (96, 96), 11: (128, 96), 12: (96, 96), 13: (1152, 576), 14: (576, 576),
             15: (576, 576), 16: (576, 576), 17: (576, 576), 18: (192, 576), 19: (64, 32), 20: (96, 48), 21: (48, 48)}
@@ -88,7 +89,6 @@ class KzgLib:
             "kzgb_pairing_check": [C.POINTER(C.c_bool), vp, vp, vp],
             "kzgb_last_artifacts": [vp, C.POINTER(Artifacts)],
             "kzgb_synth_instance": [vp, u64, u64, sz, vp, vp, vp, vp, i32],
-            "kzgb_synth_setup": [vp, sz, vp, sz],
             "kzgb_debug_op": [vp, i32, vp, vp, sz],
             "kzgb_imad_peak": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
             "kzgb_imad32_peak": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
@@ -105,18 +105,23 @@ class KzgLib:
         lib.kzgb_launch_count.argtypes, lib.kzgb_launch_count.restype = [vp], u64
         lib.kzgb_set_threads.argtypes, lib.kzgb_set_threads.restype = [vp, i32], i32
         lib.kzgb_version.argtypes, lib.kzgb_version.restype = [], C.c_char_p
+        if hasattr(lib, "kzgb_synth_setup"):                 # oracle library only (include/kzgb200_testing.h)
+            lib.kzgb_synth_setup.argtypes, lib.kzgb_synth_setup.restype = [vp, sz, vp, sz], i32
 
     EXPORTS = ["kzgb_ctx_create", "kzgb_ctx_free", "verify_kzg_proof", "verify_kzg_proof_batch",
                "verify_kzg_proof_batch_device", "verify_cell_kzg_proof_batch", "kzgb_shard_phase1", "kzgb_fs_root", "kzgb_shard_phase2",
                "kzgb_combine_verify", "kzgb_shard_phase2_terms", "kzgb_shard_finish", "kzgb_combine_verify_terms", "kzgb_g1_decompress_batch", "kzgb_fs_challenges", "kzgb_g1_msm",
                "kzgb_g1_msm_times", "kzgb_pairing_check", "kzgb_last_artifacts", "kzgb_synth_instance",
-               "kzgb_synth_setup", "kzgb_debug_op", "kzgb_imad_peak", "kzgb_imad32_peak", "kzgb_last_stage_ms", "kzgb_launch_count", "kzgb_set_threads",
+               "kzgb_debug_op", "kzgb_imad_peak", "kzgb_imad32_peak", "kzgb_last_stage_ms", "kzgb_launch_count", "kzgb_set_threads",
                "kzgb_set_subgroup_batch_min", "verify_blob_kzg_proof_batch", "kzgb_blob_challenges_evals", "kzgb_blob_eval", "kzgb_version"]
 
     def version(self) -> str:
         return self.lib.kzgb_version().decode()
 
     def synth_setup(self, n1=1, n2=2):
+        """INSECURE test setup (known tau) -- exported by the oracle library only (include/kzgb200_testing.h)."""
+        if not hasattr(self.lib, "kzgb_synth_setup"):
+            raise KzgError("kzgb_synth_setup is test infrastructure of the oracle library; the product does not export it")
         g1, g2 = C.create_string_buffer(48 * n1), C.create_string_buffer(96 * n2)
         rc = self.lib.kzgb_synth_setup(_ptr(g1), n1, _ptr(g2), n2)
         if rc:

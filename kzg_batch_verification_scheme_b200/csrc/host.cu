@@ -1323,22 +1323,17 @@ kzgb_ret kzgb_synth_instance(kzgb_ctx* ctx, uint64_t seed, uint64_t offset, size
     CK(cudaGetLastError());
     return KZGB_OK;
 }
-// The insecure test setup needs [tau]G2, i.e. G2 arithmetic that the verification path never uses; the
-// product library therefore does not carry it.  Tests and bench take the setup bytes from
-// tests/golden/test_setup.bin (generated by the oracle) or from the oracle library.
-kzgb_ret kzgb_synth_setup(uint8_t*, size_t, uint8_t*, size_t) { return KZGB_ERROR; }
-
 kzgb_ret kzgb_debug_op(kzgb_ctx* ctx, int op, const uint8_t* in, uint8_t* out, size_t count) {
     if (!ctx || !in || !out) return KZGB_BADARGS;
-    static const int isz[] = {0, 96, 48, 96, 96, 48, 48, 64, 64, 192, 96, 128, 96, 1152, 576, 576, 576, 576, 192, 64, 96, 48};
-    static const int osz[] = {0, 48, 48, 48, 48, 48, 48, 32, 32, 96, 96, 96, 96, 576, 576, 576, 576, 576, 576, 32, 48, 48};
-    if (op < 1 || op > 21 || op == 19) return KZGB_BADARGS;      // SHA256_64 is exercised through the FS stage exports
+    static const int isz[] = {0, 96, 48, 96, 96, 48, 48, 64, 64, 192, 96, 128, 96, 1152, 576, 576, 576, 576, 192, 64};
+    static const int osz[] = {0, 48, 48, 48, 48, 48, 48, 32, 32, 96, 96, 96, 96, 576, 576, 576, 576, 576, 576, 32};
+    if (op < 1 || op >= 19) return KZGB_BADARGS;                 // SHA256_64 is exercised through the FS stage exports
     DeviceSlot& s = ctx->slots[0];
     CK(cudaSetDevice(s.device));
     uint8_t *d_in = nullptr, *d_out = nullptr;
     CK(cudaMalloc((void**)&d_in, (size_t)isz[op] * count + 16)); CK(cudaMalloc((void**)&d_out, (size_t)osz[op] * count + 16));
     CK(cudaMemcpyAsync(d_in, in, (size_t)isz[op] * count, cudaMemcpyHostToDevice, s.stream));
-    if (op <= 12 || op >= 20) launch_debug_op(s.stream, op, d_in, d_out, count);
+    if (op <= 12) launch_debug_op(s.stream, op, d_in, d_out, count);
     else for (size_t i = 0; i < count; ++i) launch_pairing_debug(s.stream, op, s.lines, d_in + (size_t)isz[op] * i, d_out + (size_t)osz[op] * i);
     CK(cudaMemcpyAsync(out, d_out, (size_t)osz[op] * count, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));

@@ -7,7 +7,6 @@
 #include <cstdlib>
 
 #include "kernels.h"
-#include "fpd.cuh"
 
 std::atomic<uint64_t> g_kzgb_launches{0};
 
@@ -171,20 +170,6 @@ __global__ void k_debug_op(int op, const u8* __restrict__ in, u8* __restrict__ o
             fr_raw_from_be(k, in + 128 * i + 96);
             G1Jac r = jac_mul_limbs(jac_from_aff(p), k.v, 8);
             aff_to_be96(out + 96 * i, jac_to_aff(r));
-            break;
-        }
-        case 20: {                                      // FP64-limb multiplier (fpd.cuh) against the integer one
-            Fp a, b;
-            fp_from_be(a, in + 96 * i); fp_from_be(b, in + 96 * i + 48);
-            fp_to_be(out + 48 * i, fpd_to_fp(fpd_mul(fpd_from_fp(a), fpd_from_fp(b))));
-            break;
-        }
-        case 21: {
-            Fp a;
-            fp_from_be(a, in + 48 * i);
-            FpD x = fpd_from_fp(a);
-            for (int k = 0; k < 64; ++k) x = fpd_sqr(x);
-            fp_to_be(out + 48 * i, fpd_to_fp(x));
             break;
         }
         default: break;

@@ -125,11 +125,18 @@ class _GlooBox:
 
 
 def sharded_verify(ctx, dist, rank: int, world: int, C, z, y, pi, n_local: int, on_device: bool = False, stream: int = 0,
-                   slot: int = 0, box=None, mode: str = "terms", n_max_local: int | None = None):
+                   slot: int = 0, box=None, mode: str = "terms", n_max_local: int | None = None, trace: dict | None = None):
     """Returns (rc, ok) -- the same pair on every rank.  `ctx` is an api.Context of any library that exports
     include/kzgb200.h; `dist` is torch.distributed (initialised) or None when world == 1; `box` a HostMailbox
     (default: the gloo group).  mode "terms": Horner-free exchange of pairing terms; "partials": the 320-byte partials
     of BASELINE.json:5.  Shards may have different sizes; all but the last must be multiples of 128 proofs."""
+    t_last = [time.perf_counter()]
+
+    def mark(name):                                          # host wall time per phase (ms), accumulated into `trace`
+        if trace is not None:
+            now = time.perf_counter()
+            trace[name] = trace.get(name, 0.0) + (now - t_last[0]) * 1e3
+            t_last[0] = now
     if box is None:
         box = _GlooBox(dist, rank, world)
     nch_max = ((n_max_local or n_local) + CHUNK - 1) // CHUNK
@@ -141,8 +148,10 @@ def sharded_verify(ctx, dist, rank: int, world: int, C, z, y, pi, n_local: int, 
         nch_max = (int(t.item()) + CHUNK - 1) // CHUNK
     # ---- phase 1 + digests
     rc1, dig, _ = ctx.shard_phase1(slot, C, z, y, pi, n_local, on_device=on_device, stream=stream)
+    mark("phase1")
     seq = box.post(0, _HDR.pack(rc1, n_local, 0, 0, 0, 0) + dig)
     got = box.collect(0, seq, box.slot if isinstance(box, HostMailbox) else _HDR.size + 32 * nch_max)
+    mark("digest_exchange")
     hdrs = [_HDR.unpack_from(g, 0) for g in got]
     sizes = [h[1] for h in hdrs]
     rc = max(h[0] for h in hdrs)
@@ -154,6 +163,7 @@ def sharded_verify(ctx, dist, rank: int, world: int, C, z, y, pi, n_local: int, 
     offset = sum(sizes[:rank])
     digs = b"".join(bytes(g[_HDR.size:_HDR.size + 32 * ((s + CHUNK - 1) // CHUNK)]) for g, s in zip(got, sizes))
     root = ctx.fs_root(digs, n_total)
+    mark("root")
     # ---- phase 2 + terms / partials to rank 0
     if mode == "terms":
         rc2, rec = ctx.shard_phase2_terms(slot, root, offset)
@@ -161,20 +171,25 @@ def sharded_verify(ctx, dist, rank: int, world: int, C, z, y, pi, n_local: int, 
     else:
         rc2, rec = ctx.shard_phase2(slot, root, offset)
         rec_bytes = PARTIAL_BYTES
+    mark("phase2")
     seq = box.post(1, _HDR.pack(rc2, n_local, 0, 0, 0, 0) + rec)
     rc_c, ok = 0, False
     if rank == 0 or not isinstance(box, HostMailbox):
         got = box.collect(1, seq, _HDR.size + rec_bytes)
+        mark("terms_exchange")
         if rank == 0 and not any(_HDR.unpack_from(g, 0)[0] for g in got):
             blob = b"".join(bytes(g[_HDR.size:_HDR.size + rec_bytes]) for g in got)
             rc_c, ok = ctx.combine_verify_terms(blob, world) if mode == "terms" else ctx.combine_verify(blob)
+            mark("combine_pairing")
     # ---- every shard's input validation + rank 0's verdict
     if mode == "terms" and rc2 == 0:
         rc3, badp, bads = ctx.shard_finish(slot)
     else:
         rc3, badp, bads = rc2, 0, 0
+    mark("finish")
     seq = box.post(2, _HDR.pack(max(rc2, rc3), n_local, badp, bads, rc_c, int(ok)))
     fin = [_HDR.unpack_from(g, 0) for g in box.collect(2, seq, _HDR.size)]
+    mark("verdict_exchange")
     rc = max(max(f[0] for f in fin), fin[0][4])
     if rc:
         return rc, False

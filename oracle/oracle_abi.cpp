@@ -10,7 +10,7 @@
 #include <mutex>
 
 #include "blobs.hpp"
-#include "../include/kzgb200.h"
+#include "../include/kzgb200_testing.h"
 
 using namespace orc;
 

@@ -14,7 +14,7 @@
 #include "../../kzg_batch_verification_scheme_b200/csrc/pairing.cuh"
 #include "../../kzg_batch_verification_scheme_b200/csrc/sha256.cuh"
 #include "../../kzg_batch_verification_scheme_b200/csrc/cells.cuh"
-#include "../../kzg_batch_verification_scheme_b200/csrc/fpd.cuh"
+#include "../../tools/microbench/fpd.cuh"     // recorded negative result (FP64-limb multiplier): emulation test only, not in the product
 #include "../../kzg_batch_verification_scheme_b200/csrc/blob.cuh"
 
 struct kzgb_ctx {
@@ -548,8 +548,10 @@ kzgb_ret kzgb_shard_phase1(kzgb_ctx*, int, const uint8_t*, const uint8_t*, const
 kzgb_ret kzgb_fs_root(uint8_t*, const uint8_t*, size_t, uint64_t) { return KZGB_ERROR; }
 kzgb_ret kzgb_shard_phase2(kzgb_ctx*, int, const uint8_t*, uint64_t, void*, uint8_t*) { return KZGB_ERROR; }
 kzgb_ret kzgb_combine_verify(kzgb_ctx*, const uint8_t*, int, bool*) { return KZGB_ERROR; }
+kzgb_ret kzgb_shard_phase2_terms(kzgb_ctx*, int, const uint8_t*, uint64_t, void*, uint8_t*) { return KZGB_ERROR; }
+kzgb_ret kzgb_shard_finish(kzgb_ctx*, int, uint32_t*, uint32_t*) { return KZGB_ERROR; }
+kzgb_ret kzgb_combine_verify_terms(kzgb_ctx*, const uint8_t*, int, bool*) { return KZGB_ERROR; }
 kzgb_ret kzgb_g1_msm_times(float*, kzgb_ctx*) { return KZGB_ERROR; }
-kzgb_ret kzgb_synth_setup(uint8_t*, size_t, uint8_t*, size_t) { return KZGB_ERROR; }
 kzgb_ret kzgb_imad_peak(kzgb_ctx*, double*, double*) { return KZGB_ERROR; }
 kzgb_ret kzgb_imad32_peak(kzgb_ctx*, double*, double*) { return KZGB_ERROR; }
 kzgb_ret kzgb_last_stage_ms(kzgb_ctx*, float*) { return KZGB_ERROR; }

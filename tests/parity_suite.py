@@ -39,7 +39,7 @@ def check_field_ops(ctx, oracle, n_random=200):
 
 
 def check_fpd_ops(ctx, oracle):
-    """FP64-limb multiplier (csrc/fpd.cuh): same bits as the integer Montgomery product, lazy [0, 2p) chains included."""
+    """FP64-limb multiplier (tools/microbench/fpd.cuh; emulation only): same bits as the integer Montgomery product, lazy [0, 2p) chains included."""
     rnd = random.Random(131)
     vals = edge_fps() + [(1 << 48) - 1, 1 << 48, (1 << 96) - 1, (1 << 336) - 1, P - (1 << 48)] + [rnd.randrange(P) for _ in range(60)]
     pairs = [(x, y) for x in vals[:18] for y in vals[:18]] + [(rnd.randrange(P), rnd.randrange(P)) for _ in range(400)]

@@ -12,7 +12,7 @@
 // unbiased; low halves are summed as doubles (< 30 * 2^48 < 2^53 per column, see fpd_mul).
 // R > 4p, so operands below 2p give a result below 2p with no conditional subtraction ("lazy" Montgomery).
 #pragma once
-#include "field.cuh"
+#include "../../kzg_batch_verification_scheme_b200/csrc/field.cuh"
 
 struct FpD { double v[8]; };
 

@@ -6,7 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
-#include "../../kzg_batch_verification_scheme_b200/csrc/fpd.cuh"
+#include "fpd.cuh"
 
 __device__ unsigned long long g_probe[4];
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); return v; }
