@@ -74,6 +74,19 @@ kzgb_ret verify_cell_kzg_proof_batch(bool *ok, const uint8_t *commitments /*48 n
                                      const uint32_t *commitment_indices /*m*/, const uint32_t *cell_indices /*m*/,
                                      const uint8_t *cells /*2048 m*/, const uint8_t *proofs /*48 m*/, size_t m, kzgb_ctx *ctx);
 
+/* ---- pipelined form of verify_kzg_proof_batch: up to `depth` batches in flight on device 0 of the context, each on its
+ * own workspace (depth x the memory of one) and host thread, so the latency-bound tail of one batch (bucket reduction,
+ * pairing: ~1 ms) runs under the decompression kernel of the next.  kzgb_pipeline_init once (1 <= depth <= 8; changing
+ * the depth needs every ticket collected); submit returns a ticket at once -- KZGB_BADARGS if `depth` batches are
+ * already in flight; wait blocks until that batch is done and returns what verify_kzg_proof_batch would have.  The
+ * input buffers (host or, inputs_on_device != 0, device pointers valid on the context's device) must stay untouched
+ * until wait returns.  Every ticket is collected exactly once, in any order.  kzgb_last_artifacts does not cover
+ * pipelined batches. */
+kzgb_ret kzgb_pipeline_init(kzgb_ctx *ctx, int depth);
+kzgb_ret verify_kzg_proof_batch_submit(uint64_t *ticket_out, const uint8_t *C, const uint8_t *z, const uint8_t *y,
+                                       const uint8_t *pi, size_t n, int inputs_on_device, kzgb_ctx *ctx);
+kzgb_ret verify_kzg_proof_batch_wait(bool *ok, uint64_t ticket, kzgb_ctx *ctx);
+
 /* ---- same batch check with inputs already resident in device memory of ctx device 0 (used for the
  * device-resident throughput figure; `stream` is a cudaStream_t or NULL).  Oracle: host pointers. */
 kzgb_ret verify_kzg_proof_batch_device(bool *ok, const uint8_t *dC, const uint8_t *dz, const uint8_t *dy,

@@ -75,6 +75,9 @@ class KzgLib:
             "verify_kzg_proof_batch": [C.POINTER(C.c_bool), vp, vp, vp, vp, sz, vp],
             "verify_kzg_proof_batch_device": [C.POINTER(C.c_bool), vp, vp, vp, vp, sz, vp, vp],
             "verify_cell_kzg_proof_batch": [C.POINTER(C.c_bool), vp, sz, vp, vp, vp, vp, sz, vp],
+            "kzgb_pipeline_init": [vp, i32],
+            "verify_kzg_proof_batch_submit": [C.POINTER(u64), vp, vp, vp, vp, sz, i32, vp],
+            "verify_kzg_proof_batch_wait": [C.POINTER(C.c_bool), u64, vp],
             "kzgb_shard_phase1": [vp, i32, vp, vp, vp, vp, sz, i32, vp, vp, C.POINTER(C.c_uint32)],
             "kzgb_fs_root": [vp, vp, sz, u64],
             "kzgb_shard_phase2": [vp, i32, vp, u64, vp, vp],
@@ -109,7 +112,8 @@ class KzgLib:
             lib.kzgb_synth_setup.argtypes, lib.kzgb_synth_setup.restype = [vp, sz, vp, sz], i32
 
     EXPORTS = ["kzgb_ctx_create", "kzgb_ctx_free", "verify_kzg_proof", "verify_kzg_proof_batch",
-               "verify_kzg_proof_batch_device", "verify_cell_kzg_proof_batch", "kzgb_shard_phase1", "kzgb_fs_root", "kzgb_shard_phase2",
+               "verify_kzg_proof_batch_device", "verify_cell_kzg_proof_batch", "kzgb_pipeline_init", "verify_kzg_proof_batch_submit",
+               "verify_kzg_proof_batch_wait", "kzgb_shard_phase1", "kzgb_fs_root", "kzgb_shard_phase2",
                "kzgb_combine_verify", "kzgb_shard_phase2_terms", "kzgb_shard_finish", "kzgb_combine_verify_terms", "kzgb_g1_decompress_batch", "kzgb_fs_challenges", "kzgb_g1_msm",
                "kzgb_g1_msm_times", "kzgb_pairing_check", "kzgb_last_artifacts", "kzgb_synth_instance",
                "kzgb_debug_op", "kzgb_imad_peak", "kzgb_imad32_peak", "kzgb_last_stage_ms", "kzgb_launch_count", "kzgb_set_threads",
@@ -136,10 +140,11 @@ class KzgLib:
                            "test_context(), whose tau is public")
         return Context(self, g1_monomial, g2_monomial, devices, n_max)
 
-    def test_context(self, devices=None, n_max=1 << 16):
+    def test_context(self, devices=None, n_max=1 << 16, cells=False):
         """INSECURE: context over the repository's test setup, whose tau is derivable by anyone
-        (SHA256("kzgb200/insecure-test-tau") mod r) -- forged proofs verify against it.  Tests and bench only."""
-        g1, g2 = test_setup()
+        (SHA256("kzgb200/insecure-test-tau") mod r) -- forged proofs verify against it.  Tests and bench only.
+        cells=True: the extended setup ([tau^j]G1 j < 64, [tau^j]G2 j <= 64) the cell batch needs."""
+        g1, g2 = test_setup(cells)
         return Context(self, g1, g2, devices, n_max)
 
 
@@ -189,6 +194,21 @@ class Context:
         ok = C.c_bool(False)
         rc = self.lib.verify_kzg_proof_batch_device(C.byref(ok), _ptr(dC), _ptr(dz), _ptr(dy), _ptr(dpi), n, self.h,
                                                     C.c_void_p(stream))
+        return rc, bool(ok.value)
+
+    def pipeline_init(self, depth: int) -> int:
+        """Allocate `depth` workspaces for verify_kzg_proof_batch_submit / _wait (batches in flight on device 0)."""
+        return int(self.lib.kzgb_pipeline_init(self.h, depth))
+
+    def verify_kzg_proof_batch_submit(self, Cb, z, y, pi, n, on_device=False):
+        """(rc, ticket).  The buffers must stay alive and untouched until verify_kzg_proof_batch_wait(ticket) returns."""
+        t = C.c_uint64(0)
+        rc = self.lib.verify_kzg_proof_batch_submit(C.byref(t), _ptr(Cb), _ptr(z), _ptr(y), _ptr(pi), n, int(on_device), self.h)
+        return rc, int(t.value)
+
+    def verify_kzg_proof_batch_wait(self, ticket: int):
+        ok = C.c_bool(False)
+        rc = self.lib.verify_kzg_proof_batch_wait(C.byref(ok), ticket, self.h)
         return rc, bool(ok.value)
 
     def verify_cell_kzg_proof_batch(self, commitments: bytes, commitment_indices, cell_indices, cells: bytes, proofs: bytes):
@@ -353,8 +373,12 @@ class Context:
 PKG_DIR = Path(__file__).resolve().parent
 
 
-def test_setup():
-    """The insecure TEST trusted setup (known tau; tools/gen_test_setup.py): ([tau^0]G1, [tau^0..1]G2)."""
+def test_setup(cells=False):
+    """The insecure TEST trusted setup (known tau; tools/gen_test_setup.py): ([tau^0]G1, [tau^0..1]G2), or with
+    cells=True ([tau^j]G1 j < 64, [tau^j]G2 j <= 64)."""
+    if cells:
+        blob = (PKG_DIR / "data" / "test_setup_cells.bin").read_bytes()
+        return blob[:64 * 48], blob[64 * 48:]
     blob = (PKG_DIR / "data" / "test_setup.bin").read_bytes()
     return blob[:48], blob[48:240]
 

@@ -168,9 +168,31 @@ private:
     std::vector<std::unique_ptr<Worker>> workers_;
 };
 
+// One lane of the submit / wait pipeline: a complete workspace (DeviceSlot) on device 0 of the context and a host
+// thread that drives one batch at a time through it, so the serial tail of batch k (bucket reduction, pairing) runs
+// under K1 of batch k+1.
+struct Lane {
+    DeviceSlot slot;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    enum State { IDLE, RUNNING, DONE } state = IDLE;
+    bool quit = false;
+    const uint8_t *C = nullptr, *z = nullptr, *y = nullptr, *pi = nullptr;
+    size_t n = 0;
+    bool on_device = false;
+    uint64_t ticket = 0;
+    kzgb_ret rc = KZGB_OK;
+    bool ok = false;
+};
+
 struct kzgb_ctx {
     std::vector<DeviceSlot> slots;
     SlotPool pool;
+    std::vector<uint8_t> setup_g1, setup_g2;     // the caller's setup bytes (further workspaces are initialised from them)
+    std::vector<std::unique_ptr<Lane>> lanes;
+    uint64_t next_ticket = 0;
+    std::mutex lane_mu;
     kzgb_artifacts art;
     float msm_ms[4] = {0, 0, 0, 0};
     uint64_t launches_at_create = 0;
@@ -728,6 +750,40 @@ kzgb_ret verify_common(bool* ok, const uint8_t* C, const uint8_t* z, const uint8
     return KZGB_OK;
 }
 
+// One batch on ONE workspace, start to verdict (the path a lane thread runs; same steps as verify_common with one slot).
+kzgb_ret verify_on_slot(DeviceSlot& s, bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
+                        bool on_device) {
+    *ok = false;
+    if (!C || !z || !y || !pi || n == 0) return KZGB_BADARGS;
+    const size_t nch = (n + KZGB_CHUNK - 1) / KZGB_CHUNK;
+    std::vector<uint8_t> digests(32 * nch);
+    if (kzgb_ret rc = phase1(s, C, z, y, pi, n, on_device, digests.data())) return rc;
+    uint8_t root[32];
+    host_sha256_root(root, digests.data(), nch, n);
+    if (kzgb_ret rc = phase2(s, root, 0, false, false)) return rc;
+    kzgb_ret rc = mp_finish(s, s.mp_terms, 1, s.mp_tab, ok);
+    if (!rc) rc = finish_subgroup(s);
+    const bool bad = s.h_small[0] || s.h_small[1];
+    s.have_sums = false; s.sums_pending = false; s.have_ab = false;
+    if (rc || bad) { *ok = false; return rc ? rc : KZGB_BADARGS; }
+    return KZGB_OK;
+}
+
+void lane_main(Lane* L) {
+    std::unique_lock<std::mutex> lk(L->mu);
+    for (;;) {
+        L->cv.wait(lk, [L] { return L->state == Lane::RUNNING || L->quit; });
+        if (L->quit) return;
+        lk.unlock();
+        bool ok = false;
+        kzgb_ret rc = verify_on_slot(L->slot, &ok, L->C, L->z, L->y, L->pi, L->n, L->on_device);
+        lk.lock();
+        L->rc = rc; L->ok = ok;
+        L->state = Lane::DONE;
+        L->cv.notify_all();
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -753,6 +809,8 @@ kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const ui
         if (rc) { kzgb_ctx_free(c); return rc; }
     }
     memset(&c->art, 0, sizeof c->art);
+    c->setup_g1.assign(g1m, g1m + 48 * n1);
+    c->setup_g2.assign(g2m, g2m + 96 * n2);
     if (nd > 1) c->pool.start((size_t)nd - 1);
     c->launches_at_create = g_kzgb_launches.load();
     *out = c;
@@ -761,6 +819,13 @@ kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const ui
 void kzgb_ctx_free(kzgb_ctx* c) {
     if (!c) return;
     c->pool.stop();
+    for (auto& L : c->lanes) {
+        { std::lock_guard<std::mutex> lk(L->mu); L->quit = true; }
+        L->cv.notify_all();
+        if (L->th.joinable()) L->th.join();
+        slot_free(L->slot);
+    }
+    c->lanes.clear();
     for (auto& s : c->slots) slot_free(s);
     delete c;
 }
@@ -783,6 +848,75 @@ kzgb_ret verify_kzg_proof_batch_device(bool* ok, const uint8_t* dC, const uint8_
         CK(cudaStreamWaitEvent(s.stream, s.ev[15], 0));
     }
     return verify_common(ok, dC, dz, dy, dpi, n, ctx, true, false);
+}
+
+// ---- submit / wait: up to `depth` batches in flight on device 0 of the context, one workspace + host thread each
+kzgb_ret kzgb_pipeline_init(kzgb_ctx* ctx, int depth) {
+    if (!ctx || depth < 1 || depth > 8) return KZGB_BADARGS;
+    std::lock_guard<std::mutex> g(ctx->lane_mu);
+    if ((int)ctx->lanes.size() == depth) return KZGB_OK;
+    for (auto& L : ctx->lanes) {
+        std::lock_guard<std::mutex> lk(L->mu);
+        if (L->state != Lane::IDLE) return KZGB_BADARGS;           // batches in flight: wait for them first
+    }
+    while ((int)ctx->lanes.size() > depth) {
+        auto& L = ctx->lanes.back();
+        { std::lock_guard<std::mutex> lk(L->mu); L->quit = true; }
+        L->cv.notify_all();
+        L->th.join();
+        slot_free(L->slot);
+        ctx->lanes.pop_back();
+    }
+    while ((int)ctx->lanes.size() < depth) {
+        std::unique_ptr<Lane> L(new (std::nothrow) Lane());
+        if (!L) return KZGB_MALLOC;
+        const DeviceSlot& s0 = ctx->slots[0];
+        kzgb_ret rc = slot_init(L->slot, s0.device, s0.n_max, ctx->setup_g1.data(), 1, ctx->setup_g2.data(), 2);
+        if (rc) { slot_free(L->slot); return rc; }
+        L->slot.sg_min = s0.sg_min;
+        Lane* raw = L.get();
+        L->th = std::thread(lane_main, raw);
+        ctx->lanes.push_back(std::move(L));
+    }
+    return KZGB_OK;
+}
+kzgb_ret verify_kzg_proof_batch_submit(uint64_t* ticket_out, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi,
+                                       size_t n, int inputs_on_device, kzgb_ctx* ctx) {
+    if (!ticket_out || !ctx || !C || !z || !y || !pi || n == 0) return KZGB_BADARGS;
+    std::lock_guard<std::mutex> g(ctx->lane_mu);
+    if (ctx->lanes.empty()) return KZGB_BADARGS;                   // kzgb_pipeline_init first
+    const uint64_t t = ctx->next_ticket;
+    Lane* L = ctx->lanes[t % ctx->lanes.size()].get();
+    if (n > L->slot.n_max) return KZGB_BADARGS;
+    {
+        std::lock_guard<std::mutex> lk(L->mu);
+        if (L->state != Lane::IDLE) return KZGB_BADARGS;           // `depth` batches already in flight: wait for ticket t - depth
+        L->C = C; L->z = z; L->y = y; L->pi = pi; L->n = n; L->on_device = inputs_on_device != 0;
+        L->ticket = t;
+        L->state = Lane::RUNNING;
+    }
+    L->cv.notify_all();
+    ctx->next_ticket = t + 1;
+    *ticket_out = t;
+    return KZGB_OK;
+}
+kzgb_ret verify_kzg_proof_batch_wait(bool* ok, uint64_t ticket, kzgb_ctx* ctx) {
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!ctx) return KZGB_BADARGS;
+    Lane* L;
+    {
+        std::lock_guard<std::mutex> g(ctx->lane_mu);
+        if (ctx->lanes.empty() || ticket >= ctx->next_ticket) return KZGB_BADARGS;
+        L = ctx->lanes[ticket % ctx->lanes.size()].get();
+    }
+    std::unique_lock<std::mutex> lk(L->mu);
+    if (L->state == Lane::IDLE || L->ticket != ticket) return KZGB_BADARGS;       // unknown or already collected
+    L->cv.wait(lk, [L] { return L->state == Lane::DONE; });
+    const kzgb_ret rc = L->rc;
+    *ok = rc == KZGB_OK && L->ok;
+    L->state = Lane::IDLE;
+    return rc;
 }
 
 kzgb_ret kzgb_shard_phase1(kzgb_ctx* ctx, int slot, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi,

@@ -22,6 +22,11 @@ struct kzgb_ctx {
     Artifacts art;
     float stage_ms[KZGB_N_STAGES] = {0};
     float msm_ms[4] = {0};
+    // submit / wait: the oracle has no device to overlap with -- a submitted batch is verified at once and its result
+    // parked until it is collected (same ticket rules as the product: at most `depth` uncollected tickets)
+    struct Parked { bool used = false; uint64_t ticket = 0; kzgb_ret rc = KZGB_OK; bool ok = false; };
+    std::vector<Parked> parked;
+    uint64_t next_ticket = 0;
 };
 
 static double now_ms() {
@@ -121,6 +126,34 @@ kzgb_ret verify_kzg_proof_batch(bool* ok, const uint8_t* C, const uint8_t* z, co
 kzgb_ret verify_kzg_proof_batch_device(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi,
                                        size_t n, kzgb_ctx* c, void*) {
     return verify_impl(ok, C, z, y, pi, n, c, false);
+}
+
+kzgb_ret kzgb_pipeline_init(kzgb_ctx* c, int depth) {
+    if (!c || depth < 1 || depth > 8) return KZGB_BADARGS;
+    for (auto& p : c->parked) if (p.used) return KZGB_BADARGS;
+    c->parked.assign(depth, kzgb_ctx::Parked());
+    return KZGB_OK;
+}
+kzgb_ret verify_kzg_proof_batch_submit(uint64_t* ticket, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi,
+                                       size_t n, int, kzgb_ctx* c) {
+    if (!ticket || !c || !C || !z || !y || !pi || n == 0 || c->parked.empty()) return KZGB_BADARGS;
+    kzgb_ctx::Parked& p = c->parked[c->next_ticket % c->parked.size()];
+    if (p.used) return KZGB_BADARGS;
+    p.used = true;
+    p.ticket = c->next_ticket;
+    p.rc = verify_impl(&p.ok, C, z, y, pi, n, c, false);
+    *ticket = c->next_ticket++;
+    return KZGB_OK;
+}
+kzgb_ret verify_kzg_proof_batch_wait(bool* ok, uint64_t ticket, kzgb_ctx* c) {
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!c || c->parked.empty() || ticket >= c->next_ticket) return KZGB_BADARGS;
+    kzgb_ctx::Parked& p = c->parked[ticket % c->parked.size()];
+    if (!p.used || p.ticket != ticket) return KZGB_BADARGS;
+    p.used = false;
+    *ok = p.rc == KZGB_OK && p.ok;
+    return p.rc;
 }
 
 kzgb_ret kzgb_shard_phase1(kzgb_ctx* c, int slot, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi,

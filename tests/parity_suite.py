@@ -443,3 +443,36 @@ def check_blob_batch(ctx, oracle, inst):
     assert r1 == r2 and r1[0] == 0
     assert r1[1][:32] == blobs[32 * 3:32 * 4]
 
+
+
+def check_pipeline(ctx, oracle, depth=3, sizes=(700, 64, 3000, 1, 129, 2048, 5, 1500), seed=0x4B5A4761):
+    """verify_kzg_proof_batch_submit / _wait: interleaved batches of different sizes, some with a planted wrong proof or a
+    malformed element, `depth` in flight; every ticket returns what the oracle's plain call returns; ticket rules."""
+    assert ctx.pipeline_init(depth) == 0
+    jobs = []
+    for k, n in enumerate(sizes):
+        C, Z, Y, PI = oracle.synth_instance(seed + k, 0, n)
+        if k % 3 == 1 and n >= 2:
+            PI = PI[48:96] + PI[:48] + PI[96:]                      # two proofs swapped: well-formed, wrong
+        if k % 4 == 2:
+            Z = Z[:32 * (n // 2)] + b"\xff" * 32 + Z[32 * (n // 2 + 1):]      # scalar >= r: malformed
+        jobs.append((C, Z, Y, PI, n))
+    want = [oracle.verify_kzg_proof_batch(*j) for j in jobs]
+    assert {w for w in want} >= {(0, True), (0, False), (1, False)}
+    got, tickets = [None] * len(jobs), []
+    for k, j in enumerate(jobs):
+        if len(tickets) == depth:                                   # the pipeline is full: a further submit is refused
+            assert ctx.verify_kzg_proof_batch_submit(*j)[0] == 1
+            t, kk = tickets.pop(0)
+            got[kk] = ctx.verify_kzg_proof_batch_wait(t)
+            assert ctx.verify_kzg_proof_batch_wait(t) == (1, False)     # a ticket is collected once
+        rc, t = ctx.verify_kzg_proof_batch_submit(*j)
+        assert rc == 0
+        tickets.append((t, k))
+    for t, kk in reversed(tickets):                                 # the rest in reverse order
+        got[kk] = ctx.verify_kzg_proof_batch_wait(t)
+    assert got == want, (got, want)
+    assert ctx.verify_kzg_proof_batch_wait(10 ** 6) == (1, False)   # unknown ticket
+    # the plain entry point still works beside the pipeline
+    assert ctx.verify_kzg_proof_batch(*jobs[0]) == want[0]
+    assert ctx.pipeline_init(1) == 0

@@ -7,6 +7,11 @@ from oracle.pymodel import bls12_381 as b
 from oracle.pymodel import kzg_model as k
 
 
+def test_committed_cell_setup_equals_oracle_generator(oracle_lib):
+    from kzg_batch_verification_scheme_b200.api import test_setup
+    assert test_setup(cells=True) == oracle_lib.synth_setup(64, 65)
+
+
 def synth_cells(oracle_lib, seed, n_blobs, cells_per_blob, ncoef, threads=0):
     m = n_blobs * cells_per_blob
     comms = ctypes.create_string_buffer(48 * n_blobs)

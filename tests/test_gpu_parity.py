@@ -74,6 +74,32 @@ def test_gpu_product_has_no_fpd_ops(gpu_ctx):
     assert gpu_ctx.debug_op("FPD_MUL", bytes(96))[0] == 1
 
 
+def test_gpu_pipeline_submit_wait(gpu_lib, oracle_ctx):
+    """Library-level pipelining (kzgb_pipeline_init / submit / wait): interleaved batches against the oracle."""
+    ctx = gpu_lib.test_context(n_max=4096)
+    ps.check_pipeline(ctx, oracle_ctx, depth=3)
+    ps.check_pipeline(ctx, oracle_ctx, depth=2, sizes=(4096, 4096, 4095, 4096, 2, 4096), seed=0x4B5A4771)
+    # device-resident inputs through the pipeline
+    import torch
+    n = 4096
+    bufs = [[torch.empty(s * n, dtype=torch.uint8, device="cuda") for s in (48, 32, 32, 48)] for _ in range(4)]
+    for k, b_ in enumerate(bufs):
+        ctx.synth_instance(0x4B5A4781 + k, 0, n, device_ptrs=tuple(t.data_ptr() for t in b_))
+    bufs[2][3][:48] = bufs[2][3][48:96]
+    torch.cuda.synchronize()
+    assert ctx.pipeline_init(2) == 0
+    res, pend = [], []
+    for b_ in bufs:
+        if len(pend) == 2:
+            res.append(ctx.verify_kzg_proof_batch_wait(pend.pop(0)))
+        rc, t = ctx.verify_kzg_proof_batch_submit(*[t.data_ptr() for t in b_], n, on_device=True)
+        assert rc == 0
+        pend.append(t)
+    res += [ctx.verify_kzg_proof_batch_wait(t) for t in pend]
+    assert res == [(0, True), (0, True), (0, False), (0, True)]
+    ctx.close()
+
+
 def test_gpu_g1_ops(gpu_ctx, oracle_ctx):
     ps.check_g1_ops(gpu_ctx, oracle_ctx)
 

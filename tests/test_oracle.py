@@ -219,3 +219,14 @@ def test_config0_real_polynomials_n64(oracle_lib, oracle_ctx):
     assert oracle_ctx.verify_kzg_proof_batch(C, Z, Ybad, PI, n) == (0, False)
     for i in (0, 63):
         assert oracle_ctx.verify_kzg_proof(C[48 * i:48 * i + 48], Z[32 * i:32 * i + 32], Y[32 * i:32 * i + 32], PI[48 * i:48 * i + 48]) == (0, True)
+
+
+def test_pipeline_ticket_rules(oracle_lib):
+    """submit / wait of the ABI on the oracle (verified at submit, parked until collected): the ticket rules the GPU
+    test relies on -- refusal when `depth` tickets are uncollected, single collection, any order."""
+    from tests import parity_suite as ps
+    ctx = oracle_lib.test_context()
+    full = oracle_lib.test_context()
+    assert ctx.verify_kzg_proof_batch_submit(b"\0" * 48, b"\0" * 32, b"\0" * 32, b"\0" * 48, 1)[0] == 1      # no pipeline yet
+    ps.check_pipeline(ctx, full, depth=3, sizes=(70, 64, 130, 1, 129, 33, 5, 150))
+    ctx.close(); full.close()

@@ -14,3 +14,9 @@ assert len(blob) == 240
 for p in (ROOT / "kzg_batch_verification_scheme_b200" / "data" / "test_setup.bin", ROOT / "tests" / "golden" / "test_setup.bin"):
     p.write_bytes(blob)
     print("wrote", p)
+# extended test setup for the cell batch (BASELINE.json config[4]): [tau^j]G1 j < 64 | [tau^j]G2 j <= 64
+ext = k.setup_g1(64) + k.setup_g2(65)
+assert len(ext) == 64 * 48 + 65 * 96 and ext[:48] == blob[:48] and ext[64 * 48:64 * 48 + 192] == blob[48:]
+p = ROOT / "kzg_batch_verification_scheme_b200" / "data" / "test_setup_cells.bin"
+p.write_bytes(ext)
+print("wrote", p)
