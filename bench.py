@@ -291,6 +291,40 @@ def main():
                  "value": w2.n_total / (ms2 * 1e-3), "unit": "proofs/s", "ms_per_step": ms2, "stage_ms": st2,
                  "e2e": {"value": w2.n_total / (ms2e * 1e-3), "ms_per_step": ms2e}, "planted_invalid_rejected": planted(w2)}
         del w2
+        # the same 2^n batch through the IN-PROCESS multi-device path of the C ABI: ONE context over all N devices, one call
+        # of verify_kzg_proof_batch on pinned host buffers (one host thread per device inside the library, terms combined
+        # on the host).  Rank 0 drives it; the other ranks wait.
+        inproc = None
+        if rank == 0:
+            try:
+                ictx = lib.test_context(devices=list(range(world)), n_max=max(CHUNK, (n_cfg + world - 1) // world + CHUNK))
+                full = [torch.empty(s * n_cfg, dtype=torch.uint8).pin_memory() for s in (48, 32, 32, 48)]
+                tmp = [torch.empty(s * n_cfg, dtype=torch.uint8, device="cuda") for s in (48, 32, 32, 48)]
+                ctx.synth_instance(SEED, 0, n_cfg, device_ptrs=tuple(t.data_ptr() for t in tmp))
+                torch.cuda.synchronize()
+                for h, d in zip(full, tmp):
+                    h.copy_(d)
+                del tmp
+                fptr = [t.data_ptr() for t in full]
+                for _ in range(args.warmup):
+                    assert ictx.verify_kzg_proof_batch(*fptr, n_cfg) == (0, True)
+                times = []
+                for _ in range(args.steps):
+                    t0 = time.perf_counter()
+                    assert ictx.verify_kzg_proof_batch(*fptr, n_cfg) == (0, True)
+                    times.append((time.perf_counter() - t0) * 1e3)
+                full[3][:48] = full[3][48:96]
+                rej = ictx.verify_kzg_proof_batch(*fptr, n_cfg) == (0, False)
+                ms_i = sum(times) / len(times)
+                inproc = {"n_total": n_cfg, "devices": world, "ms_per_step": ms_i, "value": n_cfg / (ms_i * 1e-3), "unit": "proofs/s",
+                          "host_memory": "pinned", "timing": "host wall clock around the blocking call (H2D on every device inside)",
+                          "planted_invalid_rejected": rej}
+                ictx.close()
+            except Exception as ex:                                  # noqa: BLE001
+                inproc = {"error": repr(ex)}
+        barrier()
+        if other is not None:
+            other_in = inproc
     dbuf, hbuf, dptr = w.dbuf, w.pinned, w.dptr
 
     value = n_total / (ms_dev * 1e-3)
@@ -524,6 +558,7 @@ def main():
         if other:
             line[other["scaling"]] = other
             line["host_phase_ms"] = host_phase_ms
+            line["in_process_multi_device"] = other_in
         print(json.dumps(line), flush=True)
     ctx.close()
     if multi:

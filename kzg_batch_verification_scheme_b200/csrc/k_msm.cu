@@ -189,28 +189,18 @@ __global__ void __launch_bounds__(128) k_msm_chunk_pass2_t(u32 T, G1Xyzz* __rest
     if (t >= T) return;
     msm_chunk_pass2(T, t, buckets, R);
 }
-// Pass 2, one QUAD per (chunk, record kind): the partial records of a bucket that straddles chunks are added up by the
+// Pass 2, one QUAD per chunk: the partial records of a bucket that straddles chunks are added up by the
 // chunk where the bucket starts (msm_chunk_pass2 in msm.cuh is the one-thread form the emulation runs).  The additions
 // are a serial chain per bucket, so small sums run them on quads (n = 4096: accumulate stage 0.45 -> 0.37 ms); with many
 // chunks the one-thread form has the better throughput (n = 2^20: 15.2 vs 16.3 ms), see msm_accumulate_stage.
 __global__ void __launch_bounds__(128) k_msm_chunk_pass2(u32 T, G1Xyzz* __restrict__ buckets, ChunkRecs R) {
     __shared__ Fp qsm[32 * KZ_QUAD_SLOTS];
     const int qi = threadIdx.x >> 2;
-    const u32 job = blockIdx.x * 32u + (u32)qi, t = job >> 1, which = job & 1u;
+    const u32 t = blockIdx.x * 32u + (u32)qi;
     if (t >= T) return;
     u32 key;
     G1Xyzz sum;
-    if (which == 0) {
-        key = R.tail_key[t];
-        if (key == KZ_KEY_NONE) return;
-        sum = R.tail[t];
-    } else {
-        key = R.head_key[t];
-        if (key == KZ_KEY_NONE) return;
-        const u32 f = R.head_flags[t];
-        if (!(f & 1u) || (f & 2u)) return;                  // does not start here, or already complete
-        sum = R.head[t];
-    }
+    if (!msm_chunk_owned(R, t, key, sum)) return;
     Quad q = quad_make(qsm, qi);
     for (u32 u = t + 1; u < T; ++u) {
         if (R.head_key[u] != key) break;
@@ -351,7 +341,30 @@ static u32 msm_chunk_len_plan(const MsmPlan& plan, size_t m) {
     double heavy = (double)m / (double)(nb_min ? nb_min : 1);
     u32 L = 4;
     while (L < 32 && (double)L * (double)L < 1.4 * heavy) L <<= 1;
-    return L > base ? L : base;
+    L = L > base ? L : base;
+    // Wave quantisation: pass 1 runs ceil(T / 128) blocks, `per_wave` of them at a time (2 per SM at 232 registers), every
+    // block for L mixed additions -- 2.16 waves cost as much as 3.  For sums of up to a few waves pick, in [L, 2L), the
+    // length with the fewest (waves x L) (n = 2^17: 640 blocks of 16 entries = 3 x 16 -> 569 blocks of 18 = 2 x 18).
+    static const u32 per_wave = [] {
+        int dev = 0, sms = 148, occ = 2;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_msm_chunk_pass1_staged<KZ_ACC_WARPS, 232>, 32 * KZ_ACC_WARPS, 0);
+        return (u32)(sms * (occ > 0 ? occ : 1));
+    }();
+    static const int tune = [] { const char* e = getenv("KZGB_ACC_WAVE_TUNE"); return e ? atoi(e) : 1; }();
+    const size_t N = m * (size_t)plan.W;
+    if (tune && N / L / 128 < 12 * (size_t)per_wave) {
+        u32 bestL = L;
+        double best = 1e300;
+        for (u32 l = L; l < 2 * L; ++l) {
+            const size_t blocks = ((N + l - 1) / l + 127) / 128;
+            const double cost = (double)((blocks + per_wave - 1) / per_wave) * (double)l;
+            if (cost < best - 1e-9) { best = cost; bestL = l; }
+        }
+        L = bestL;
+    }
+    return L;
 }
 
 void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, size_t m, MsmWorkspace& ws) {
@@ -370,7 +383,7 @@ void msm_accumulate_stage(cudaStream_t s, const MsmPlan& plan, const Fp* pts, si
                                                           ws.buckets, ws.recs);
     }
     KZ_COUNT_LAUNCH();
-    if (T <= 16384) k_msm_chunk_pass2<<<(2 * T + 31) / 32, 128, 0, s>>>(T, ws.buckets, ws.recs);
+    if (T <= 16384) k_msm_chunk_pass2<<<(T + 31) / 32, 128, 0, s>>>(T, ws.buckets, ws.recs);
     else k_msm_chunk_pass2_t<<<(T + 127) / 128, 128, 0, s>>>(T, ws.buckets, ws.recs);
     KZ_COUNT_LAUNCH();
 }

@@ -196,30 +196,29 @@ KZ_HD void msm_chunk_pass1(const Fp* pts, const u32* keys, const u32* vals, u32 
         acc = xyzz_madd(acc, p);
     }
 }
+// The spanning bucket a chunk owns, if any.  Owner = the chunk where the bucket starts: its tail run, or a head run that
+// starts the bucket and covers the whole chunk.  The two cases exclude each other (a head that covers the whole chunk
+// is also the chunk's last run, so there is no separate tail), hence at most ONE owned bucket per chunk.
+KZ_HD bool msm_chunk_owned(const ChunkRecs& R, u32 t, u32& key, G1Xyzz& sum) {
+    key = R.tail_key[t];
+    if (key != KZ_KEY_NONE) { sum = R.tail[t]; return true; }
+    key = R.head_key[t];
+    if (key == KZ_KEY_NONE) return false;
+    const u32 f = R.head_flags[t];
+    if (!(f & 1u) || (f & 2u)) return false;                  // does not start here, or already complete
+    sum = R.head[t];
+    return true;
+}
 KZ_HD void msm_chunk_pass2(u32 T, u32 t, G1Xyzz* buckets, const ChunkRecs& R) {
-    // owner of a spanning bucket = the chunk where it starts: either its tail run, or a head run that
-    // starts the bucket and covers the whole chunk
-    for (int which = 0; which < 2; ++which) {
-        u32 key;
-        G1Xyzz sum;
-        if (which == 0) {
-            key = R.tail_key[t];
-            if (key == KZ_KEY_NONE) continue;
-            sum = R.tail[t];
-        } else {
-            key = R.head_key[t];
-            if (key == KZ_KEY_NONE) continue;
-            u32 f = R.head_flags[t];
-            if (!(f & 1u) || (f & 2u)) continue;              // does not start here, or already complete
-            sum = R.head[t];
-        }
-        for (u32 u = t + 1; u < T; ++u) {
-            if (R.head_key[u] != key) break;
-            sum = xyzz_add(sum, R.head[u]);
-            if (R.head_flags[u] & 2u) break;
-        }
-        buckets[key] = sum;
+    u32 key;
+    G1Xyzz sum;
+    if (!msm_chunk_owned(R, t, key, sum)) return;
+    for (u32 u = t + 1; u < T; ++u) {
+        if (R.head_key[u] != key) break;
+        sum = xyzz_add(sum, R.head[u]);
+        if (R.head_flags[u] & 2u) break;
     }
+    buckets[key] = sum;
 }
 
 // Horner over window sums: result = sum_w 2^(c w) * win[w].  The chain of c(W-1) doublings is serial, so it
