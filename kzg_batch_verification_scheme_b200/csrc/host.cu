@@ -26,6 +26,15 @@
         }                                                                                             \
     } while (0)
 
+// Every entry point leaves the calling thread's current CUDA device as it found it (the library switches devices
+// internally; a caller such as PyTorch keeps allocating on "its" device afterwards).
+struct ApiDeviceGuard {
+    int dev = -1;
+    ApiDeviceGuard() { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; cudaGetLastError(); } }
+    ~ApiDeviceGuard() { if (dev >= 0) cudaSetDevice(dev); }
+};
+#define KZ_API_GUARD ApiDeviceGuard api_device_guard_
+
 static_assert(KZGB_CHUNK == KZ_FS_CHUNK, "chunk size of the public header and of the device hash must agree");
 
 namespace {
@@ -792,6 +801,7 @@ const char* kzgb_version(void) { return "kzgb200-cuda-sm100a 0.1"; }
 
 kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const uint8_t* g2m, size_t n2, const int* devices,
                          int n_devices, size_t n_max) {
+    KZ_API_GUARD;
     if (!out || !g1m || !g2m || n1 < 1 || n2 < 2 || n_max < 1 || n_devices < 0 || n_devices > 64) return KZGB_BADARGS;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
@@ -817,6 +827,7 @@ kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const ui
     return KZGB_OK;
 }
 void kzgb_ctx_free(kzgb_ctx* c) {
+    KZ_API_GUARD;
     if (!c) return;
     c->pool.stop();
     for (auto& L : c->lanes) {
@@ -832,14 +843,17 @@ void kzgb_ctx_free(kzgb_ctx* c) {
 
 kzgb_ret verify_kzg_proof(bool* ok, const uint8_t C[48], const uint8_t z[32], const uint8_t y[32], const uint8_t pi[48],
                           kzgb_ctx* ctx) {
+    KZ_API_GUARD;
     return verify_common(ok, C, z, y, pi, 1, ctx, false, true);
 }
 kzgb_ret verify_kzg_proof_batch(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
                                 kzgb_ctx* ctx) {
+    KZ_API_GUARD;
     return verify_common(ok, C, z, y, pi, n, ctx, false, false);
 }
 kzgb_ret verify_kzg_proof_batch_device(bool* ok, const uint8_t* dC, const uint8_t* dz, const uint8_t* dy, const uint8_t* dpi,
                                        size_t n, kzgb_ctx* ctx, void* stream) {
+    KZ_API_GUARD;
     // inputs may have been produced on the caller's stream: order our stream after it
     if (ctx && !ctx->slots.empty()) {
         DeviceSlot& s = ctx->slots[0];
@@ -852,6 +866,7 @@ kzgb_ret verify_kzg_proof_batch_device(bool* ok, const uint8_t* dC, const uint8_
 
 // ---- submit / wait: up to `depth` batches in flight on device 0 of the context, one workspace + host thread each
 kzgb_ret kzgb_pipeline_init(kzgb_ctx* ctx, int depth) {
+    KZ_API_GUARD;
     if (!ctx || depth < 1 || depth > 8) return KZGB_BADARGS;
     std::lock_guard<std::mutex> g(ctx->lane_mu);
     if ((int)ctx->lanes.size() == depth) return KZGB_OK;
@@ -921,6 +936,7 @@ kzgb_ret verify_kzg_proof_batch_wait(bool* ok, uint64_t ticket, kzgb_ctx* ctx) {
 
 kzgb_ret kzgb_shard_phase1(kzgb_ctx* ctx, int slot, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi,
                            size_t n_local, int on_device, void* stream, uint8_t* digests_out, uint32_t* n_bad_out) {
+    KZ_API_GUARD;
     if (!ctx || slot < 0 || slot >= (int)ctx->slots.size() || !C || !z || !y || !pi || !digests_out) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[slot];
     if (on_device) {
@@ -939,6 +955,7 @@ kzgb_ret kzgb_fs_root(uint8_t root_out[32], const uint8_t* chunk_digests, size_t
 }
 kzgb_ret kzgb_shard_phase2(kzgb_ctx* ctx, int slot, const uint8_t root[32], uint64_t global_offset, void*,
                            uint8_t partial_out[KZGB_PARTIAL_BYTES]) {
+    KZ_API_GUARD;
     if (!ctx || slot < 0 || slot >= (int)ctx->slots.size() || !root || !partial_out) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[slot];
     kzgb_ret rc = phase2(s, root, global_offset, false, true);
@@ -959,6 +976,7 @@ kzgb_ret kzgb_shard_phase2(kzgb_ctx* ctx, int slot, const uint8_t root[32], uint
 // kzgb_shard_finish, which can be called after the terms have been handed on.
 kzgb_ret kzgb_shard_phase2_terms(kzgb_ctx* ctx, int slot, const uint8_t root[32], uint64_t global_offset, void*,
                                  uint8_t terms_out[KZGB_TERMS_BYTES]) {
+    KZ_API_GUARD;
     if (!ctx || slot < 0 || slot >= (int)ctx->slots.size() || !root || !terms_out) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[slot];
     kzgb_ret rc = phase2(s, root, global_offset, false, false);
@@ -974,6 +992,7 @@ kzgb_ret kzgb_shard_phase2_terms(kzgb_ctx* ctx, int slot, const uint8_t root[32]
     return KZGB_OK;
 }
 kzgb_ret kzgb_shard_finish(kzgb_ctx* ctx, int slot, uint32_t* n_bad_points, uint32_t* n_bad_scalars) {
+    KZ_API_GUARD;
     if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[slot];
     if (!s.cur_n) return KZGB_BADARGS;
@@ -987,6 +1006,7 @@ kzgb_ret kzgb_shard_finish(kzgb_ctx* ctx, int slot, uint32_t* n_bad_points, uint
     return (s.h_small[0] || s.h_small[1]) ? KZGB_BADARGS : KZGB_OK;
 }
 kzgb_ret kzgb_combine_verify_terms(kzgb_ctx* ctx, const uint8_t* terms, int n_shards, bool* ok) {
+    KZ_API_GUARD;
     if (!ctx || !terms || !ok) return KZGB_BADARGS;
     *ok = false;
     if (n_shards < 1 || n_shards > 64) return KZGB_BADARGS;
@@ -1012,6 +1032,7 @@ kzgb_ret kzgb_combine_verify_terms(kzgb_ctx* ctx, const uint8_t* terms, int n_sh
     return KZGB_OK;
 }
 kzgb_ret kzgb_combine_verify(kzgb_ctx* ctx, const uint8_t* partials, int n_partials, bool* ok) {
+    KZ_API_GUARD;
     if (!ctx || !partials || !ok) return KZGB_BADARGS;
     *ok = false;
     DeviceSlot& s = ctx->slots[0];
@@ -1059,6 +1080,7 @@ static kzgb_ret blob_zy(DeviceSlot& s, const uint8_t* blobs, const uint8_t* comm
 }
 kzgb_ret kzgb_blob_challenges_evals(uint8_t* z_out, uint8_t* y_out, const uint8_t* blobs, const uint8_t* comms, size_t m,
                                     kzgb_ctx* ctx) {
+    KZ_API_GUARD;
     if (!z_out || !y_out || !blobs || !comms || !ctx || m == 0) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[0];
     uint32_t bad = 0;
@@ -1073,6 +1095,7 @@ kzgb_ret kzgb_blob_challenges_evals(uint8_t* z_out, uint8_t* y_out, const uint8_
     return bad ? KZGB_BADARGS : KZGB_OK;
 }
 kzgb_ret kzgb_blob_eval(uint8_t* y_out, const uint8_t* blobs, const uint8_t* z_in, size_t m, kzgb_ctx* ctx) {
+    KZ_API_GUARD;
     if (!y_out || !blobs || !z_in || !ctx || m == 0) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[0];
     uint32_t bad = 0;
@@ -1084,6 +1107,7 @@ kzgb_ret kzgb_blob_eval(uint8_t* y_out, const uint8_t* blobs, const uint8_t* z_i
 }
 kzgb_ret verify_blob_kzg_proof_batch(bool* ok, const uint8_t* blobs, const uint8_t* comms, const uint8_t* proofs, size_t m,
                                      kzgb_ctx* ctx) {
+    KZ_API_GUARD;
     if (!ok) return KZGB_BADARGS;
     *ok = false;
     if (!ctx || !blobs || !comms || !proofs || m == 0) return KZGB_BADARGS;
@@ -1103,6 +1127,7 @@ kzgb_ret verify_blob_kzg_proof_batch(bool* ok, const uint8_t* blobs, const uint8
 }
 
 kzgb_ret kzgb_g1_decompress_batch(uint8_t* affine_out, uint8_t* status_out, const uint8_t* in, size_t m, kzgb_ctx* ctx) {
+    KZ_API_GUARD;
     if (!affine_out || !status_out || !in || !ctx) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[0];
     CK(cudaSetDevice(s.device));
@@ -1131,6 +1156,7 @@ kzgb_ret kzgb_g1_decompress_batch(uint8_t* affine_out, uint8_t* status_out, cons
 
 kzgb_ret kzgb_fs_challenges(uint8_t root_out[32], uint8_t* r_out, const uint8_t* C, const uint8_t* z, const uint8_t* y,
                             const uint8_t* pi, size_t n, kzgb_ctx* ctx) {
+    KZ_API_GUARD;
     if (!root_out || !r_out || !C || !z || !y || !pi || !ctx || n == 0) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[0];
     if (n > s.n_max) return KZGB_BADARGS;
@@ -1153,6 +1179,7 @@ kzgb_ret kzgb_fs_challenges(uint8_t root_out[32], uint8_t* r_out, const uint8_t*
 
 kzgb_ret kzgb_g1_msm(uint8_t affine_out[96], const uint8_t* points_affine, const uint8_t* scalars, size_t m, int nbits,
                      kzgb_ctx* ctx) {
+    KZ_API_GUARD;
     if (!affine_out || !points_affine || !scalars || !ctx || (nbits != 255 && nbits != 128)) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[0];
     if (m > s.n_max) return KZGB_BADARGS;
@@ -1219,6 +1246,7 @@ kzgb_ret kzgb_g1_msm_times(float ms_out[4], kzgb_ctx* ctx) {
 // Cell batch (BASELINE.json config[4]).  Single device (slot 0): 2^14 openings are ~2 ms of work.
 kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, const uint32_t* ci, const uint32_t* xi,
                                      const uint8_t* cells, const uint8_t* proofs, size_t m, kzgb_ctx* ctx) {
+    KZ_API_GUARD;
     if (!ok) return KZGB_BADARGS;
     *ok = false;
     if (!ctx || !comms || !ci || !xi || !cells || !proofs || m == 0 || nc == 0) return KZGB_BADARGS;
@@ -1357,6 +1385,7 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
 }
 
 kzgb_ret kzgb_pairing_check(bool* ok, const uint8_t A_affine[96], const uint8_t B_affine[96], kzgb_ctx* ctx) {
+    KZ_API_GUARD;
     if (!ok || !A_affine || !B_affine || !ctx) return KZGB_BADARGS;
     *ok = false;
     DeviceSlot& s = ctx->slots[0];
@@ -1381,6 +1410,7 @@ kzgb_ret kzgb_pairing_check(bool* ok, const uint8_t A_affine[96], const uint8_t 
 }
 
 kzgb_ret kzgb_last_artifacts(kzgb_ctx* ctx, kzgb_artifacts* out) {
+    KZ_API_GUARD;
     if (!ctx || !out) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[0];
     if (s.sums_pending) { if (kzgb_ret rc = deferred_sums(s)) return rc; }
@@ -1430,6 +1460,7 @@ kzgb_ret kzgb_last_artifacts(kzgb_ctx* ctx, kzgb_artifacts* out) {
 
 kzgb_ret kzgb_synth_instance(kzgb_ctx* ctx, uint64_t seed, uint64_t offset, size_t n, uint8_t* C, uint8_t* z, uint8_t* y,
                              uint8_t* pi, int out_on_device) {
+    KZ_API_GUARD;
     if (!ctx || !C || !z || !y || !pi) return KZGB_BADARGS;
     DeviceSlot& s = ctx->slots[0];
     CK(cudaSetDevice(s.device));
@@ -1458,6 +1489,7 @@ kzgb_ret kzgb_synth_instance(kzgb_ctx* ctx, uint64_t seed, uint64_t offset, size
     return KZGB_OK;
 }
 kzgb_ret kzgb_debug_op(kzgb_ctx* ctx, int op, const uint8_t* in, uint8_t* out, size_t count) {
+    KZ_API_GUARD;
     if (!ctx || !in || !out) return KZGB_BADARGS;
     static const int isz[] = {0, 96, 48, 96, 96, 48, 48, 64, 64, 192, 96, 128, 96, 1152, 576, 576, 576, 576, 192, 64};
     static const int osz[] = {0, 48, 48, 48, 48, 48, 48, 32, 32, 96, 96, 96, 96, 576, 576, 576, 576, 576, 576, 32};
@@ -1497,10 +1529,12 @@ static kzgb_ret imad_rate(DeviceSlot& s, int mode, double* rate, double* ms_out)
     return KZGB_OK;
 }
 kzgb_ret kzgb_imad_peak(kzgb_ctx* ctx, double* imad_per_sec_out, double* ms_out) {
+    KZ_API_GUARD;
     if (!ctx || !imad_per_sec_out) return KZGB_BADARGS;
     return imad_rate(ctx->slots[0], 0, imad_per_sec_out, ms_out);
 }
 kzgb_ret kzgb_imad32_peak(kzgb_ctx* ctx, double* imad_per_sec_out, double* ms_out) {
+    KZ_API_GUARD;
     if (!ctx || !imad_per_sec_out) return KZGB_BADARGS;
     return imad_rate(ctx->slots[0], 1, imad_per_sec_out, ms_out);
 }

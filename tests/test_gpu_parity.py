@@ -429,6 +429,8 @@ def test_gpu_in_process_multi_device_equals_single(gpu_lib, oracle_lib):
     counts = sorted({2, G} | ({4} if G >= 4 else set()))
     for g in counts:
         ctx = gpu_lib.test_context(devices=list(range(g)), n_max=n)
+        # the library leaves the caller's current device alone (PyTorch allocates on cudaGetDevice())
+        assert torch.empty(1, device="cuda").device.index == torch.cuda.current_device() == 0
         for _ in range(2):                                      # second call: every slot's workspaces are reused
             assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
             ag = ctx.last_artifacts()
