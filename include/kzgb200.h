@@ -88,7 +88,10 @@ kzgb_ret verify_kzg_proof_batch_submit(uint64_t *ticket_out, const uint8_t *C, c
 kzgb_ret verify_kzg_proof_batch_wait(bool *ok, uint64_t ticket, kzgb_ctx *ctx);
 
 /* ---- same batch check with inputs already resident in device memory of ctx device 0 (used for the
- * device-resident throughput figure; `stream` is a cudaStream_t or NULL).  Oracle: host pointers. */
+ * device-resident throughput figure; `stream` is a cudaStream_t or NULL).  The four device arrays are read with
+ * 128-bit loads: each base pointer must be 16-byte aligned (cudaMalloc'ed memory is), else KZGB_BADARGS -- this holds
+ * for every entry point that takes device pointers (kzgb_shard_phase1 with inputs_on_device, the submit form).
+ * Oracle: host pointers. */
 kzgb_ret verify_kzg_proof_batch_device(bool *ok, const uint8_t *dC, const uint8_t *dz, const uint8_t *dy,
                                        const uint8_t *dpi, size_t n, kzgb_ctx *ctx, void *stream);
 

@@ -399,11 +399,26 @@ void be_to_words(uint32_t* w, const uint8_t* in, size_t nw) {
     for (size_t i = 0; i < nw; ++i) w[i] = (uint32_t)in[4 * i] << 24 | in[4 * i + 1] << 16 | in[4 * i + 2] << 8 | in[4 * i + 3];
 }
 
+// Do the workspaces of this slot hold a shard of n proofs?  (They are sized at context creation from the plans of 64
+// sampled sizes up to n_max plus slack; this is the exact check, done before anything is launched.)
+bool shard_fits(const DeviceSlot& s, size_t n) {
+    const MsmPlan pr = msm_make_plan(n, 128), pz = msm_make_plan(2 * (n + 1), 128);
+    return (size_t)pr.W * n <= s.sortR.capacity && (size_t)pz.W * 2 * (n + 1) <= s.sortZ.capacity &&
+           pr.total_buckets <= s.max_bucketsR + 512 && pz.total_buckets <= s.max_bucketsZ + 512 &&
+           sg_work_entries(pr) + 256 <= s.sg_cap && sg_work_entries(pz) + 256 <= s.sg_cap;
+}
+
 // Phase 1: [H2D] -> leaf + chunk hashes -> digests D2H -> K1 decompress (left running).
 // Returns after the digests are on the host.  `stream_override`: caller's stream or null.
 kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
                 bool on_device, uint8_t* digests_out) {
     if (n == 0 || n > s.n_max) return KZGB_BADARGS;
+    if (!shard_fits(s, n)) {                             // a workspace shortfall is the library's fault, not malformed input
+        fprintf(stderr, "[kzgb200] workspace too small for a shard of %zu proofs (n_max %zu)\n", n, s.n_max);
+        return KZGB_ERROR;
+    }
+    // 128-bit loads on the inputs: device-resident arrays must be 16-byte aligned (kzgb200.h)
+    if (on_device && ((((uintptr_t)C) | ((uintptr_t)z) | ((uintptr_t)y) | ((uintptr_t)pi)) & 15u)) return KZGB_BADARGS;
     CK(cudaSetDevice(s.device));
     cudaStream_t st = s.stream, s2 = s.stream2;        // s2: high priority side stream
     CK(cudaEventRecord(s.ev[0], st));
@@ -512,10 +527,7 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     CK(cudaEventRecord(s.ev[4], s2));
     s.planR = msm_make_plan(n, 128);
     s.planZ = msm_make_plan(2 * (n + 1), 128);
-    if ((size_t)s.planR.W * n > s.sortR.capacity || (size_t)s.planZ.W * 2 * (n + 1) > s.sortZ.capacity ||
-        s.planR.total_buckets > s.max_bucketsR + 512 || s.planZ.total_buckets > s.max_bucketsZ + 512 ||
-        sg_work_entries(s.planR) + 256 > s.sg_cap || sg_work_entries(s.planZ) + 256 > s.sg_cap)
-        return KZGB_BADARGS;
+    if (!shard_fits(s, n)) return KZGB_ERROR;            // checked in phase 1 already; never reached after a successful phase 1
     MsmWorkspace wr = make_ws(s, s.sortR, s.bucketsA), wz = make_ws(s, s.sortZ, s.bucketsC);
     msm_sort_stage(s2, s.planR, s.r, 4, n, wr);
     msm_sort_stage(s2, s.planZ, s.zs, 4, 2 * (n + 1), wz);
@@ -1199,7 +1211,7 @@ kzgb_ret kzgb_g1_msm(uint8_t affine_out[96], const uint8_t* points_affine, const
     MsmPlan plan = msm_make_plan(mm, 128);
     if ((size_t)plan.W * mm > s.sortZ.capacity || plan.total_buckets > s.max_bucketsZ + 512 || sg_work_entries(plan) + 256 > s.sg_cap) {
         cudaFree(d_pts); cudaFree(d_sc);
-        return KZGB_BADARGS;
+        return KZGB_ERROR;
     }
     MsmWorkspace ws = make_ws(s, s.sortZ, s.bucketsC);
     CK(cudaEventRecord(s.ev[0], st));
@@ -1253,6 +1265,13 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     DeviceSlot& s = ctx->slots[0];
     const size_t M = m + nc + 64;                      // points of the A-side sum: proofs | commitments | [tau^j]G1
     if (!s.cell_ready || M > s.n_max || nc > 0xFFFFFFFFull) return KZGB_BADARGS;
+    // both sums' plans against the workspaces, before anything is launched
+    const MsmPlan planB = msm_make_plan(m, 128), planA = msm_make_plan(2 * M, 128);
+    if ((size_t)planB.W * m > s.sortR.capacity || planB.total_buckets > s.max_bucketsR + 512 || sg_work_entries(planB) + 256 > s.sg_cap ||
+        (size_t)planA.W * 2 * M > s.sortZ.capacity || planA.total_buckets > s.max_bucketsZ + 512 || sg_work_entries(planA) + 256 > s.sg_cap) {
+        fprintf(stderr, "[kzgb200] workspace too small for a cell batch of %zu openings (n_max %zu)\n", m, s.n_max);
+        return KZGB_ERROR;
+    }
     CK(cudaSetDevice(s.device));
     cudaStream_t st = s.stream;
     if (m > s.cell_cap) {
@@ -1307,11 +1326,8 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     CK(cudaMemsetAsync(s.sum_ry, 0, 8 * sizeof(uint32_t), st));
     CK(cudaEventRecord(s.ev[11], st));
     // B-side: sum r_k pi_k, 128-bit scalars, on a side stream beside the A-side sum
-    MsmPlan planB = msm_make_plan(m, 128);
     MsmWorkspace wsB = make_ws(s, s.sortR, s.bucketsA);
     {
-        if ((size_t)planB.W * m > s.sortR.capacity || planB.total_buckets > s.max_bucketsR + 512 || sg_work_entries(planB) + 256 > s.sg_cap)
-            return KZGB_BADARGS;
         cudaStream_t sb = s.stream3;
         CK(cudaStreamWaitEvent(sb, s.ev[11], 0));
         wsB.recs = s.recsA;
@@ -1330,9 +1346,6 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     }
     // A-side: sum (r_k h^64) pi_k + sum w_i C_i - sum S_j [tau^j]G1, 255-bit scalars, GLV-split
     size_t mm = 2 * M;
-    MsmPlan planA = msm_make_plan(mm, 128);
-    if ((size_t)planA.W * mm > s.sortZ.capacity || planA.total_buckets > s.max_bucketsZ + 512 || sg_work_entries(planA) + 256 > s.sg_cap)
-        return KZGB_BADARGS;
     MsmWorkspace wsA = make_ws(s, s.sortZ, s.bucketsC);
     launch_glv_split(st, s.rz, M, s.zs);
     launch_endo_points(st, s.pts, M, s.pts + 2 * M);
