@@ -359,23 +359,32 @@ def main():
             per_point = K1A_IMAD_PER_POINT if sg_batch else K1_IMAD_PER_POINT
             k1_imad = 2 * n_local * per_point
             ach = k1_imad / (k1_ms * 1e-3)
-            kernel = ("K1 = k_decompress_sqrt (2 launches: commitments, proofs); subgroup membership is established on 128 bucket-slice "
-                      "sums per MSM (batched check), not per point") if sg_batch else \
+            kernel = ("K1 = k_decompress_sqrt (one launch over commitments and proofs; the stage also carries the side-stream hashes, challenges "
+                      "and sorts that run under it); subgroup membership is established on 128 bucket-slice sums per MSM (batched check), "
+                      "not per point") if sg_batch else \
                 "K1 = k_decompress_sqrt + k_subgroup_chain1 + k_subgroup_chain2 (one stage, 3 launches)"
             roofline = {"bound": "imad", "kernel": kernel,
                         "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T wide-IMAD/s", "frac": ach / imad_peak,
-                        # dram__bytes_read+write per launch from the ncu --set full captures of the three K1 kernels at
-                        # n = 65536 (profiles/r1_k1[abc]_*: 22.2 + 12.7 + 31.6 MB for 131072 points = 507 B/point), scaled to this n
-                        "traffic": 2 * n_local * (169 if sg_batch else 507),
+                        # dram__bytes_read.sum + dram__bytes_write.sum of k_decompress_sqrt from the ncu --set full capture of THIS build
+                        # at the benchmarked n = 2^20 (profiles/r2_k1a_decompress_sqrt_ncu_full_n1048576.txt: 103.7 + 186.1 MB for
+                        # 2^21 points = 138.2 B/point; algorithmic 48 + 96 + 1 = 145 B/point), scaled by n.  Per-point chains:
+                        # r1 capture at n = 65536, 507 B/point
+                        "traffic": int(2 * n_local * (138.2 if sg_batch else 507)),
+                        "traffic_source": "ncu capture at n = 2^20 committed under profiles/ (bench.py cannot run ncu inside the timed run); scaled by n",
                         "peak_source": peak_src + ": carry-chained mad.lo.cc/madc.hi.cc (SASS IMAD.WIDE.U32.X) on all SMs, measured in this "
                                        "run; 32 lanes/clk/SM on B200 (148 x 32 x 1.965 GHz = 9.31 T/s nominal)",
                         "imad32_issue_peak": imad32_peak / 1e12,
+                        "frac_vs_imad32_issue_peak": ach / imad32_peak,      # SURVEY.md 8(d)'s a-priori denominator (64 plain IMAD/clk/SM)
+                        "kernel_alone_ms_ncu": 27.61 if (sg_batch and n_local == 1 << 20) else None,   # same capture: the kernel without the side streams
                         "algorithmic_per_launch": k1_imad, "launch_ms": k1_ms,
                         "formula": (f"2n x ({K1A_M_PER_POINT} M x 300 + {K1A_S_PER_POINT} S x 234)" if sg_batch else
                                     f"2n x ({K1_M_PER_POINT} M x 300 + {K1_S_PER_POINT} S x 234)") +
                                    " wide multiply-adds; stage time from CUDA events on the library's stream",
                         "subgroup_check": "batched (bucket slices)" if sg_batch else "per point",
-                        "whole_batch_frac": (n_local * (2 * per_point + MSM_FPMUL_PER_PROOF * 300)) / (stages.get("total", ms_dev) * 1e-3) / imad_peak}
+                        "whole_batch_frac": (n_local * (2 * per_point + MSM_FPMUL_PER_PROOF * 300)) / (ms_dev * 1e-3) / imad_peak,
+                        # the same batch against SURVEY.md 8(d)'s work model (per-point subgroup chains: 2 x 447.6 k + 111 k
+                        # multiply-adds per proof): > 1 means the batched subgroup check beats the model's own "100 %" bound
+                        "whole_batch_frac_survey_model": (n_local * (2 * K1_IMAD_PER_POINT_SURVEY + MSM_FPMUL_PER_PROOF * 300)) / (ms_dev * 1e-3) / imad_peak}
             if not sg_batch:
                 roofline["frac_survey_model"] = 2 * n_local * K1_IMAD_PER_POINT_SURVEY / (k1_ms * 1e-3) / imad_peak
             k1_bytes = 2 * n_local * ((48 + 96 + 1) if sg_batch else (48 + 96 + 1 + 2 * 144 + 2 * 96))
