@@ -197,6 +197,25 @@ kzgb_ret kzgb_blob_challenges_evals(uint8_t *z_out, uint8_t *y_out, const uint8_
 kzgb_ret kzgb_blob_eval(uint8_t *y_out, const uint8_t *blobs, const uint8_t *z_in, size_t m, kzgb_ctx *ctx);
 #define KZGB_BLOB_BYTES 131072
 
+/* ---- EIP-4844 / c-kzg-4844 transcript mode (DESIGN.md "EIP-4844 mode").  Same inputs, same
+ * verdict semantics and return codes as verify_kzg_proof_batch, but the random linear combination is c-kzg's:
+ *   r = int_be(SHA256("RCKZGBATCH___V1_" | u64be(4096) | u64be(n) | C_0 | z_0 | y_0 | pi_0 | C_1 | ...)) mod r_BLS,
+ *   coefficients r^0 .. r^(n-1);  accept  <=>  e(sum r^i (C_i - y_i G1) + sum r^i z_i pi_i, G2) e(-sum r^i pi_i, [tau]G2) = 1.
+ * The transcript hash is serial (host, SHA extensions: ~0.5 ms per 1000 proofs); every point gets the per-point
+ * subgroup check.  Needs 2(n+1) <= n_max of the context; single device (slot 0).  kzgb_last_artifacts gives A, B,
+ * sum_ry and, as `root`, the transcript digest.
+ * Blob form: z_j = int_be(SHA256("FSBLOBVERIFY_V1_" | u128be(4096) | blob_j | C_j)) mod r_BLS, y_j = p_j(z_j) over the
+ * bit-reversed 4096-th roots of unity of 7^((r-1)/4096), then the batch above. */
+kzgb_ret verify_kzg_proof_batch_eip4844(bool *ok, const uint8_t *C, const uint8_t *z, const uint8_t *y, const uint8_t *pi,
+                                        size_t n, kzgb_ctx *ctx);
+kzgb_ret verify_blob_kzg_proof_batch_eip4844(bool *ok, const uint8_t *blobs, const uint8_t *commitments,
+                                             const uint8_t *proofs, size_t m, kzgb_ctx *ctx);
+kzgb_ret kzgb_blob_challenges_evals_eip4844(uint8_t *z_out, uint8_t *y_out, const uint8_t *blobs, const uint8_t *commitments,
+                                            size_t m, kzgb_ctx *ctx);
+/* Context from a c-kzg-4844 `trusted_setup.txt` (n_g1, n_g2, n_g1 G1 Lagrange points, n_g2 G2 monomials, optionally n_g1
+ * G1 monomials; hex, one point per line).  KZGB_BADARGS: unreadable or malformed file, point not in its group. */
+kzgb_ret kzgb_load_trusted_setup_file(kzgb_ctx **out, const char *path, const int *devices, int n_devices, size_t n_max);
+
 /* Batches (shards) of at least n_min proofs establish subgroup membership of all 2n points through 128 slice
  * sums per MSM of the bucket tables that sum r_i C_i and sum r_i pi_i fill anyway (soundness 2^-128 per point,
  * DESIGN.md "Batched subgroup check"); smaller ones, and any batch in which a slice sum fails, run the

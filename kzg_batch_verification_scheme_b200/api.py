@@ -100,6 +100,10 @@ class KzgLib:
             "verify_blob_kzg_proof_batch": [C.POINTER(C.c_bool), vp, vp, vp, sz, vp],
             "kzgb_blob_challenges_evals": [vp, vp, vp, vp, sz, vp],
             "kzgb_blob_eval": [vp, vp, vp, sz, vp],
+            "verify_kzg_proof_batch_eip4844": [C.POINTER(C.c_bool), vp, vp, vp, vp, sz, vp],
+            "verify_blob_kzg_proof_batch_eip4844": [C.POINTER(C.c_bool), vp, vp, vp, sz, vp],
+            "kzgb_blob_challenges_evals_eip4844": [vp, vp, vp, vp, sz, vp],
+            "kzgb_load_trusted_setup_file": [C.POINTER(vp), C.c_char_p, vp, i32, sz],
         }
         for name, args in sig.items():
             f = getattr(lib, name)
@@ -117,7 +121,9 @@ class KzgLib:
                "kzgb_combine_verify", "kzgb_shard_phase2_terms", "kzgb_shard_finish", "kzgb_combine_verify_terms", "kzgb_g1_decompress_batch", "kzgb_fs_challenges", "kzgb_g1_msm",
                "kzgb_g1_msm_times", "kzgb_pairing_check", "kzgb_last_artifacts", "kzgb_synth_instance",
                "kzgb_debug_op", "kzgb_imad_peak", "kzgb_imad32_peak", "kzgb_last_stage_ms", "kzgb_launch_count", "kzgb_set_threads",
-               "kzgb_set_subgroup_batch_min", "verify_blob_kzg_proof_batch", "kzgb_blob_challenges_evals", "kzgb_blob_eval", "kzgb_version"]
+               "kzgb_set_subgroup_batch_min", "verify_blob_kzg_proof_batch", "kzgb_blob_challenges_evals", "kzgb_blob_eval", "kzgb_version",
+               "verify_kzg_proof_batch_eip4844", "verify_blob_kzg_proof_batch_eip4844", "kzgb_blob_challenges_evals_eip4844",
+               "kzgb_load_trusted_setup_file"]
 
     def version(self) -> str:
         return self.lib.kzgb_version().decode()
@@ -139,6 +145,20 @@ class KzgLib:
             raise KzgError("a trusted setup is required (g1_monomial, g2_monomial); for tests and benchmarks use "
                            "test_context(), whose tau is public")
         return Context(self, g1_monomial, g2_monomial, devices, n_max)
+
+    def context_from_file(self, path, devices=None, n_max=1 << 16):
+        """Verifier over a c-kzg-4844 `trusted_setup.txt` (kzgb_load_trusted_setup_file)."""
+        ctx = Context.__new__(Context)
+        ctx.klib, ctx.lib = self, self.lib
+        nd = len(devices) if devices is not None else 0
+        devs = (C.c_int * nd)(*devices) if nd else None
+        ctx.n_devices = max(nd, 1)
+        h = C.c_void_p()
+        rc = self.lib.kzgb_load_trusted_setup_file(C.byref(h), str(path).encode(), C.cast(devs, C.c_void_p) if devs else None, nd, n_max)
+        if rc:
+            raise KzgError(f"kzgb_load_trusted_setup_file -> {rc}")
+        ctx.h = h
+        return ctx
 
     def test_context(self, devices=None, n_max=1 << 16, cells=False):
         """INSECURE: context over the repository's test setup, whose tau is derivable by anyone
@@ -364,6 +384,24 @@ class Context:
         y = C.create_string_buffer(32 * m)
         rc = self.lib.kzgb_blob_eval(y, _ptr(blobs), _ptr(z), m, self.h)
         return rc, y.raw
+
+    # ---- EIP-4844 / c-kzg-4844 transcript mode
+    def verify_kzg_proof_batch_eip4844(self, Cb, z, y, pi, n):
+        ok = C.c_bool(False)
+        rc = self.lib.verify_kzg_proof_batch_eip4844(C.byref(ok), _ptr(Cb), _ptr(z), _ptr(y), _ptr(pi), n, self.h)
+        return rc, bool(ok.value)
+
+    def verify_blob_kzg_proof_batch_eip4844(self, blobs, commitments: bytes, proofs: bytes, m=None):
+        m = len(commitments) // 48 if m is None else m
+        ok = C.c_bool(False)
+        rc = self.lib.verify_blob_kzg_proof_batch_eip4844(C.byref(ok), _ptr(blobs), _ptr(commitments), _ptr(proofs), m, self.h)
+        return rc, bool(ok.value)
+
+    def blob_challenges_evals_eip4844(self, blobs: bytes, commitments: bytes):
+        m = len(commitments) // 48
+        z, y = C.create_string_buffer(32 * m), C.create_string_buffer(32 * m)
+        rc = self.lib.kzgb_blob_challenges_evals_eip4844(z, y, _ptr(blobs), _ptr(commitments), m, self.h)
+        return rc, z.raw, y.raw
 
     def set_subgroup_batch_min(self, n_min: int) -> int:
         """Batches of >= n_min proofs use the batched subgroup check (0: always the per-point check)."""

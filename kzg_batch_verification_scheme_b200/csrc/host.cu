@@ -16,6 +16,7 @@
 
 #include "../../include/kzgb200.h"
 #include "kernels.h"
+#include "eip4844.cuh"
 
 #define CK(x)                                                                                         \
     do {                                                                                              \
@@ -239,7 +240,7 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
     }
     for (auto& e : s.ev) CK(cudaEventCreate(&e));
     CK(dmalloc(s.dC, 48 * (n_max + 1))); CK(dmalloc(s.dz, 32 * (n_max + 1))); CK(dmalloc(s.dy, 32 * (n_max + 1))); CK(dmalloc(s.dpi, 48 * (n_max + 1)));
-    CK(dmalloc(s.pts, 2 * (3 * n_max + 4)));
+    CK(dmalloc(s.pts, 2 * (4 * n_max + 8)));            // EIP-4844 mode lays out C | phi(C) | pi | G | phi(pi) | phi(G) for n <= n_max / 2
     CK(dmalloc(s.k1_tmp, 3 * (2 * n_max + 2)));
     CK(dmalloc(s.status, 2 * n_max + 2));
     CK(dmalloc(s.counters, 8));
@@ -790,6 +791,115 @@ kzgb_ret verify_on_slot(DeviceSlot& s, bool* ok, const uint8_t* C, const uint8_t
     return KZGB_OK;
 }
 
+// EIP-4844 / c-kzg-4844 transcript: ONE challenge r = SHA-256 over the whole batch (host, serial by
+// construction), coefficients r^i (255-bit).  All three sums are GLV-split 128-bit sums over 2n resp. 2(n+1) points:
+//   S1  over  C | phi(C)                    scalars  k1(r^i) | k2(r^i)
+//   S2' over  pi | G | phi(pi) | phi(G)     scalars  r^i z_i, -(sum r^i y_i)  split likewise
+//   S3  over  the same 2(n+1) points        scalars  r^i, 0 (the setup point does not take part)
+// Every point gets the deterministic per-point subgroup check: the coefficients r^i are functions of one value and
+// not independent between points, so the argument of the batched check (128 independent coins per point) is not
+// available here.  Needs 2(n+1) <= n_max.  `resident`: C, z, y, pi are already in s.dC .. s.dpi (blob path).
+kzgb_ret eip_verify_on_slot(kzgb_ctx* ctx, DeviceSlot& s, bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi,
+                            size_t n, bool resident) {
+    *ok = false;
+    if (!C || !z || !y || !pi || n == 0 || 2 * (n + 1) > s.n_max || n >> KZ_EIP_POW_BITS) return KZGB_BADARGS;
+    const MsmPlan pA = msm_make_plan(2 * n, 128), pZ = msm_make_plan(2 * (n + 1), 128);
+    const size_t eZ = (size_t)pZ.W * 2 * (n + 1), eA = (size_t)pA.W * 2 * n;
+    if (eA > s.sortR.capacity || eZ > s.sortR.capacity || eZ > s.sortZ.capacity || pA.total_buckets > s.max_bucketsR + 512 ||
+        pZ.total_buckets > s.max_bucketsR + 512 || pZ.total_buckets > s.max_bucketsZ + 512 || sg_work_entries(pA) + 256 > s.sg_cap ||
+        sg_work_entries(pZ) + 256 > s.sg_cap) {
+        fprintf(stderr, "[kzgb200] workspace too small for an EIP-4844-mode batch of %zu proofs (n_max %zu)\n", n, s.n_max);
+        return KZGB_ERROR;
+    }
+    CK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream, sA = s.stream5, sZ = s.stream4;
+    s.have_sums = false; s.sums_pending = false; s.have_ab = false; s.cur_n = 0; s.sg_batch = false;
+    ctx->terms_combined = false;
+    kzgb_artifacts& art = ctx->art;
+    memset(&art, 0, sizeof art);
+    art.n = n;
+    CK(cudaEventRecord(s.ev[0], st));
+    CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), st));
+    if (!resident) {
+        CK(cudaMemcpyAsync(s.dC, C, 48 * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.dpi, pi, 48 * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.dz, z, 32 * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.dy, y, 32 * n, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaEventRecord(s.ev[1], st));
+    // point layout (2 Fp each): C [0,n) | phi(C) [n,2n) | pi [2n,3n) | G 3n | phi(pi) [3n+1,4n+1) | phi(G) 4n+1
+    Fp* pC = s.pts;
+    Fp* pPi = s.pts + 2 * (2 * n);
+    launch_decompress_points(st, s.dC, n, pC, s.k1_tmp, s.status, s.counters);
+    launch_decompress_points(st, s.dpi, n, pPi, s.k1_tmp + 3 * n, s.status + n, s.counters);
+    CK(cudaMemcpyAsync(pPi + 2 * n, s.g1_pt, 2 * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    launch_endo_points(st, pC, n, pC + 2 * n);
+    launch_endo_points(st, pPi, n + 1, pPi + 2 * (n + 1));
+    CK(cudaEventRecord(s.ev[3], st));
+    // the transcript hash on the host while K1 runs, then powers and scalar products on the side stream
+    uint8_t hash[32];
+    host_eip4844_batch_hash(hash, C, z, y, pi, n);
+    memcpy(art.root, hash, 32);
+    memcpy(s.h_small + 8, hash, 32);
+    cudaStream_t s2 = s.stream2;
+    CK(cudaStreamWaitEvent(s2, s.ev[1], 0));
+    uint8_t* hash_dev = s.scratch + 2048;
+    Fr* table = (Fr*)(s.scratch + 4096);
+    CK(cudaMemcpyAsync(hash_dev, s.h_small + 8, 32, cudaMemcpyHostToDevice, s2));
+    uint32_t* rpow = s.rz;                          // 8 (n+1) limbs
+    uint32_t* rz = s.rz + 8 * (n + 1);              // 8 (n+1) limbs: needs 16 (n+1) <= 8 (n_max+1)
+    launch_eip_scalars(s2, hash_dev, table, s.dz, s.dy, n, s.root_words, rpow, rz, s.partials, s.sum_ry, s.counters);
+    uint32_t* zsA = s.r;                            // 4 * 2n limbs <= 4 n_max
+    uint32_t* zs3 = s.zs;                           // 4 * 2(n+1)
+    uint32_t* zsZ = s.zs + 4 * 2 * (n + 1);         // 4 * 2(n+1): needs 16 (n+1) <= 8 (n_max+1)
+    launch_glv_split(s2, rpow, n, zsA);
+    launch_glv_split(s2, rpow, n + 1, zs3);
+    launch_glv_split(s2, rz, n + 1, zsZ);
+    CK(cudaEventRecord(s.ev[4], s2));
+    CK(cudaStreamWaitEvent(st, s.ev[4], 0));
+    CK(cudaEventRecord(s.ev[11], st));              // points and scalars ready
+    CK(cudaStreamWaitEvent(sA, s.ev[11], 0));
+    CK(cudaStreamWaitEvent(sZ, s.ev[11], 0));
+    MsmWorkspace w1 = make_ws(s, s.sortR, s.bucketsA), w3 = make_ws(s, s.sortR, s.bucketsB), w2 = make_ws(s, s.sortZ, s.bucketsC);
+    w1.recs = s.recsA; w3.recs = s.recsB;
+    w3.sg_work = s.sg_partial + s.sg_cap; w3.slices = w3.sg_work + s.sg_cap - 256;
+    w2.sg_work = s.sg_partial + 2 * s.sg_cap; w2.slices = w2.sg_work + s.sg_cap - 256;
+    // S2' on its own stream; S1 and then S3 share the second sort buffer, one after the other on one stream
+    msm_sort_stage(sZ, pZ, zsZ, 4, 2 * (n + 1), w2);
+    save_ws(s.sortZ, w2);
+    msm_accumulate_stage(sZ, pZ, pPi, 2 * (n + 1), w2);
+    msm_slices_stage(sZ, pZ, w2, false);
+    CK(cudaEventRecord(s.ev[13], sZ));
+    msm_sort_stage(sA, pA, zsA, 4, 2 * n, w1);
+    msm_accumulate_stage(sA, pA, pC, 2 * n, w1);
+    msm_slices_stage(sA, pA, w1, false);
+    w3.keys = w1.keys; w3.vals = w1.vals; w3.keys_alt = w1.keys_alt; w3.vals_alt = w1.vals_alt;
+    msm_sort_stage(sA, pZ, zs3, 4, 2 * (n + 1), w3);
+    save_ws(s.sortR, w3);
+    msm_accumulate_stage(sA, pZ, pPi, 2 * (n + 1), w3);
+    msm_slices_stage(sA, pZ, w3, false);
+    CK(cudaEventRecord(s.ev[12], sA));
+    CK(cudaStreamWaitEvent(st, s.ev[12], 0));
+    CK(cudaStreamWaitEvent(st, s.ev[13], 0));
+    CK(cudaEventRecord(s.ev[6], st));
+    const MpSumDesc d1 = {w1.slices, w1.buckets, pA.c, pA.W, pA.nbits};
+    const MpSumDesc d2 = {w2.slices, w2.buckets, pZ.c, pZ.W, pZ.nbits};
+    const MpSumDesc d3 = {w3.slices, w3.buckets, pZ.c, pZ.W, pZ.nbits};
+    launch_mp_terms(st, d1, d2, d3, s.mp_terms);
+    CK(cudaEventRecord(s.ev[7], st));
+    CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    kzgb_ret rc = mp_finish(s, s.mp_terms, 1, s.mp_tab, ok);
+    art.n_bad_points = s.h_small[0];
+    art.n_bad_scalars = s.h_small[1];
+    if (rc || s.h_small[0] || s.h_small[1]) { *ok = false; return rc ? rc : KZGB_BADARGS; }
+    ctx->terms_combined = true;
+    ctx->ab_terms = s.mp_terms; ctx->ab_shards = 1; ctx->ab_gather_sum_ry = false;
+    fill_stage_ms(art, s, 0.0f);
+    art.stage_ms[8] = ev_ms(s.ev[7], s.ev[8]);
+    art.stage_ms[9] = ev_ms(s.ev[0], s.ev[8]);
+    return KZGB_OK;
+}
+
 void lane_main(Lane* L) {
     std::unique_lock<std::mutex> lk(L->mu);
     for (;;) {
@@ -1136,6 +1246,119 @@ kzgb_ret verify_blob_kzg_proof_batch(bool* ok, const uint8_t* blobs, const uint8
     CK(cudaMemcpyAsync(s.dpi, proofs, 48 * m, cudaMemcpyHostToDevice, s.stream));
     // the plain batch on device-resident (C, z, y, pi); one proof is still a batch of one (challenge r_0 from the root)
     return verify_common(ok, s.dC, s.dz, s.dy, s.dpi, m, ctx, true, false);
+}
+
+// ---- EIP-4844 / c-kzg-4844 transcript mode
+kzgb_ret verify_kzg_proof_batch_eip4844(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
+                                        kzgb_ctx* ctx) {
+    KZ_API_GUARD;
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!ctx) return KZGB_BADARGS;
+    return eip_verify_on_slot(ctx, ctx->slots[0], ok, C, z, y, pi, n, false);
+}
+kzgb_ret verify_blob_kzg_proof_batch_eip4844(bool* ok, const uint8_t* blobs, const uint8_t* comms, const uint8_t* proofs, size_t m,
+                                             kzgb_ctx* ctx) {
+    KZ_API_GUARD;
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!ctx || !blobs || !comms || !proofs || m == 0) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    if (2 * (m + 1) > s.n_max) return KZGB_BADARGS;
+    CK(cudaSetDevice(s.device));
+    // compute_challenge of every blob: a flat SHA-256 over 128 KiB + 80 bytes -- host threads, SHA extensions
+    std::vector<uint8_t> zs(32 * m), ys(32 * m);
+    {
+        unsigned nt = std::thread::hardware_concurrency();
+        nt = nt < 1 ? 1 : (nt > 16 ? 16 : nt);
+        if (nt > m) nt = (unsigned)m;
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t] {
+                for (size_t j = t; j < m; j += nt) host_eip4844_blob_hash(zs.data() + 32 * j, blobs + (size_t)KZGB_BLOB_BYTES * j, comms + 48 * j);
+            });
+        for (auto& t : th) t.join();
+    }
+    CK(cudaMemcpyAsync(s.dz, zs.data(), 32 * m, cudaMemcpyHostToDevice, s.stream));
+    launch_eip_reduce_be(s.stream, s.dz, m);                       // z = hash mod r
+    CK(cudaMemcpyAsync(zs.data(), s.dz, 32 * m, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    uint32_t bad = 0;
+    kzgb_ret rc = blob_zy(s, blobs, comms, zs.data(), m, &bad);   // y = p(z) on the device (barycentric); C, z, y stay resident
+    if (rc) return rc;
+    if (bad) {
+        memset(&ctx->art, 0, sizeof ctx->art);
+        ctx->art.n = m;
+        ctx->art.n_bad_scalars = bad;
+        return KZGB_BADARGS;
+    }
+    CK(cudaMemcpyAsync(ys.data(), s.dy, 32 * m, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(s.dpi, proofs, 48 * m, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    return eip_verify_on_slot(ctx, s, ok, comms, zs.data(), ys.data(), proofs, m, true);
+}
+// stage export: z_out, y_out of the EIP-4844 blob path (compute_challenge, evaluate_polynomial_in_evaluation_form)
+kzgb_ret kzgb_blob_challenges_evals_eip4844(uint8_t* z_out, uint8_t* y_out, const uint8_t* blobs, const uint8_t* comms, size_t m,
+                                            kzgb_ctx* ctx) {
+    KZ_API_GUARD;
+    if (!z_out || !y_out || !blobs || !comms || !ctx || m == 0) return KZGB_BADARGS;
+    DeviceSlot& s = ctx->slots[0];
+    if (m > s.n_max) return KZGB_BADARGS;
+    CK(cudaSetDevice(s.device));
+    for (size_t j = 0; j < m; ++j) host_eip4844_blob_hash(z_out + 32 * j, blobs + (size_t)KZGB_BLOB_BYTES * j, comms + 48 * j);
+    CK(cudaMemcpyAsync(s.dz, z_out, 32 * m, cudaMemcpyHostToDevice, s.stream));
+    launch_eip_reduce_be(s.stream, s.dz, m);
+    CK(cudaMemcpyAsync(z_out, s.dz, 32 * m, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    uint32_t bad = 0;
+    kzgb_ret rc = blob_zy(s, blobs, nullptr, z_out, m, &bad);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(y_out, s.dy, 32 * m, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    return bad ? KZGB_BADARGS : KZGB_OK;
+}
+
+// c-kzg-4844 trusted_setup.txt: "<n_g1>\n<n_g2>\n", n_g1 lines of G1 points in Lagrange form (96 hex digits; used only by
+// provers -- skipped), n_g2 lines of G2 monomials (192 hex digits) and, in files written for EIP-7594, n_g1 more lines
+// of G1 monomials.  The verifier needs [tau^0]G1 (the generator: taken from the monomial section when present), and
+// [tau^j]G2; with the monomial section it also gets the 64 G1 monomials of the cell batch.
+static int hex_nibble(int c) { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; }
+static bool read_hex_token(FILE* f, std::vector<uint8_t>& out, size_t nbytes) {
+    int c;
+    do { c = fgetc(f); } while (c == ' ' || c == '\n' || c == '\r' || c == '\t');
+    if (c == EOF) return false;
+    out.clear();
+    for (size_t i = 0; i < nbytes; ++i) {
+        int hi = hex_nibble(c), lo = hex_nibble(fgetc(f));
+        if (hi < 0 || lo < 0) return false;
+        out.push_back((uint8_t)(hi << 4 | lo));
+        c = fgetc(f);
+    }
+    if (c != EOF && c != '\n' && c != '\r' && c != ' ' && c != '\t') return false;       // token longer than expected
+    return true;
+}
+kzgb_ret kzgb_load_trusted_setup_file(kzgb_ctx** out, const char* path, const int* devices, int n_devices, size_t n_max) {
+    if (!out || !path) return KZGB_BADARGS;
+    FILE* f = fopen(path, "r");
+    if (!f) return KZGB_BADARGS;
+    unsigned long n1 = 0, n2 = 0;
+    std::vector<uint8_t> g1, g2, tok;
+    bool okf = fscanf(f, "%lu %lu", &n1, &n2) == 2 && n1 >= 1 && n1 <= (1ul << 20) && n2 >= 2 && n2 <= 4096;
+    for (unsigned long i = 0; okf && i < n1; ++i) okf = read_hex_token(f, tok, 48);                 // Lagrange section: not used
+    for (unsigned long i = 0; okf && i < n2; ++i) { okf = read_hex_token(f, tok, 96); if (okf) g2.insert(g2.end(), tok.begin(), tok.end()); }
+    if (okf) {
+        unsigned long got = 0;
+        while (got < n1 && read_hex_token(f, tok, 48)) { g1.insert(g1.end(), tok.begin(), tok.end()); ++got; }
+        if (got != 0 && got != n1) okf = false;                    // a truncated monomial section
+        if (got == 0) {
+            // no monomial section: [tau^0]G1 is the group generator
+            static const char* gen = "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb";
+            for (int i = 0; i < 48; ++i) g1.push_back((uint8_t)(hex_nibble(gen[2 * i]) << 4 | hex_nibble(gen[2 * i + 1])));
+        }
+    }
+    fclose(f);
+    if (!okf) return KZGB_BADARGS;
+    return kzgb_ctx_create(out, g1.data(), g1.size() / 48, g2.data(), g2.size() / 96, devices, n_devices, n_max);
 }
 
 kzgb_ret kzgb_g1_decompress_batch(uint8_t* affine_out, uint8_t* status_out, const uint8_t* in, size_t m, kzgb_ctx* ctx) {

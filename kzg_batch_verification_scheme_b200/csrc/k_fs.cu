@@ -2,6 +2,7 @@
 // derivation r_i, the scalar products r_i z_i and sum r_i y_i -- plus the device-side synthetic instance
 // generator and the host root hash.
 #include "kernels.h"
+#include "eip4844.cuh"
 #include "sha256.cuh"
 
 __device__ __forceinline__ u32 ld_be32(u32 x) { return __byte_perm(x, 0, 0x0123); }
@@ -142,6 +143,70 @@ void launch_challenges(cudaStream_t s, const uint32_t* root_words, uint64_t glob
     k_sum_ry<<<1, KZ_CH_THREADS, 0, s>>>(partials, nb, n, rz_out, sum_ry_out);
     KZ_COUNT_LAUNCH();
 }
+// ---- EIP-4844 transcript mode (eip4844.cuh): powers of one challenge
+__global__ void k_eip_table(const u8* __restrict__ hash_be, Fr* __restrict__ table, u32* __restrict__ r_out) {
+    if (threadIdx.x || blockIdx.x) return;
+    Fr r;
+    eip_power_table(table, r, hash_be);
+    for (int k = 0; k < 8; ++k) r_out[k] = r.v[k];
+}
+// rpow[i] = r^i (8 limbs; slot n = 0), rz[i] = r^i z_i, block partials of sum r^i y_i; counters[1] += scalars >= r
+__global__ void __launch_bounds__(KZ_CH_THREADS) k_eip_scalars(const Fr* __restrict__ table, const u8* __restrict__ z, const u8* __restrict__ y,
+                                                               size_t n, u32* __restrict__ rpow_out, u32* __restrict__ rz_out,
+                                                               u32* __restrict__ partials, u32* __restrict__ counters) {
+    __shared__ Fr red[KZ_CH_THREADS];
+    __shared__ Fr tab[KZ_EIP_POW_BITS];
+    if (threadIdx.x < KZ_EIP_POW_BITS) tab[threadIdx.x] = table[threadIdx.x];
+    __syncthreads();
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Fr ry = fr_zero();
+    if (i < n) {
+        Fr r = eip_power(tab, (u64)i), zr, yr;
+        fr_raw_from_be(zr, z + 32 * i);
+        fr_raw_from_be(yr, y + 32 * i);
+        u32 bad = (fr_raw_is_canonical(zr) ? 0u : 1u) + (fr_raw_is_canonical(yr) ? 0u : 1u);
+        if (bad) { atomicAdd(counters + 1, bad); zr = fr_zero(); yr = fr_zero(); }
+        Fr rz = fr_mul(r, fr_to_mont(zr));
+        ry = fr_mul(r, fr_to_mont(yr));
+        for (int k = 0; k < 8; ++k) { rpow_out[8 * i + k] = r.v[k]; rz_out[8 * i + k] = rz.v[k]; }
+    } else if (i == n) {
+        for (int k = 0; k < 8; ++k) rpow_out[8 * i + k] = 0;          // scalar of the setup point in the sum over the proofs
+    }
+    red[threadIdx.x] = ry;
+    __syncthreads();
+    for (int s = KZ_CH_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] = fr_add(red[threadIdx.x], red[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 8; ++k) partials[8 * blockIdx.x + k] = red[0].v[k];
+}
+void launch_eip_scalars(cudaStream_t s, const uint8_t* hash_be_dev, Fr* table, const uint8_t* z, const uint8_t* y, size_t n,
+                        uint32_t* r_out, uint32_t* rpow_out, uint32_t* rz_out, uint32_t* partials, uint32_t* sum_ry_out, uint32_t* counters) {
+    if (!n) return;
+    k_eip_table<<<1, 32, 0, s>>>(hash_be_dev, table, r_out);
+    KZ_COUNT_LAUNCH();
+    size_t nb = (n + 1 + KZ_CH_THREADS - 1) / KZ_CH_THREADS;
+    k_eip_scalars<<<(unsigned)nb, KZ_CH_THREADS, 0, s>>>(table, z, y, n, rpow_out, rz_out, partials, counters);
+    KZ_COUNT_LAUNCH();
+    k_sum_ry<<<1, KZ_CH_THREADS, 0, s>>>(partials, nb, n, rz_out, sum_ry_out);
+    KZ_COUNT_LAUNCH();
+}
+// m 32-byte big-endian hashes -> the same values mod r (blob challenges)
+__global__ void k_eip_reduce_be(u8* __restrict__ io, size_t m) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    Fr v;
+    fr_raw_from_be(v, io + 32 * i);
+    v = fr_reduce_raw(v);
+    fr_raw_to_be(io + 32 * i, v);
+}
+void launch_eip_reduce_be(cudaStream_t s, uint8_t* io, size_t m) {
+    if (!m) return;
+    k_eip_reduce_be<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(io, m);
+    KZ_COUNT_LAUNCH();
+}
+
 // r_i only, as 16 big-endian bytes (stage export kzgb_fs_challenges)
 __global__ void k_r_only(const u32* __restrict__ root_words, size_t n, u8* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,6 +433,33 @@ void host_sha256_root(uint8_t out[32], const uint8_t* digests, size_t n_chunks, 
     for (int i = 0; i < 8; ++i) { be[i] = (uint8_t)(deg >> (56 - 8 * i)); be[8 + i] = (uint8_t)(n_total >> (56 - 8 * i)); }
     s.update(be, 16);
     s.update(digests, 32 * n_chunks);
+    s.final(out);
+}
+
+// EIP-4844: SHA256("RCKZGBATCH___V1_" | u64be(4096) | u64be(n) | C_0 | z_0 | y_0 | pi_0 | C_1 | ...) over SoA inputs
+void host_eip4844_batch_hash(uint8_t out[32], const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n) {
+    HostSha s;
+    s.update((const uint8_t*)"RCKZGBATCH___V1_", 16);
+    uint8_t be[16];
+    const uint64_t deg = 4096, nn = n;
+    for (int i = 0; i < 8; ++i) { be[i] = (uint8_t)(deg >> (56 - 8 * i)); be[8 + i] = (uint8_t)(nn >> (56 - 8 * i)); }
+    s.update(be, 16);
+    uint8_t rec[160];
+    for (size_t i = 0; i < n; ++i) {
+        memcpy(rec, C + 48 * i, 48); memcpy(rec + 48, z + 32 * i, 32); memcpy(rec + 80, y + 32 * i, 32); memcpy(rec + 112, pi + 48 * i, 48);
+        s.update(rec, 160);
+    }
+    s.final(out);
+}
+// EIP-4844 compute_challenge: SHA256("FSBLOBVERIFY_V1_" | u128be(4096) | blob | commitment)
+void host_eip4844_blob_hash(uint8_t out[32], const uint8_t* blob, const uint8_t* commitment) {
+    HostSha s;
+    s.update((const uint8_t*)"FSBLOBVERIFY_V1_", 16);
+    uint8_t be[16] = {0};
+    be[14] = 0x10;                                      // 4096 as a 16-byte big-endian integer
+    s.update(be, 16);
+    s.update(blob, 131072);
+    s.update(commitment, 48);
     s.final(out);
 }
 

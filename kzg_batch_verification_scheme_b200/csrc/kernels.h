@@ -47,6 +47,12 @@ void launch_synth(cudaStream_t s, uint64_t seed, uint64_t offset, size_t n, cons
 void launch_build_comb(cudaStream_t s, Fp* comb_table /* 32*255 affine points */);
 void launch_scalars_from_be(cudaStream_t s, const uint8_t* be32, size_t m, uint32_t* limbs8, uint32_t* counters);
 void host_sha256_root(uint8_t out[32], const uint8_t* digests, size_t n_chunks, uint64_t n_total);
+// EIP-4844 transcript mode (eip4844.cuh): table = 32 Fr of scratch; r_out / sum_ry_out 8 limbs; rpow_out 8(n+1), rz_out 8(n+1) limbs
+void launch_eip_scalars(cudaStream_t s, const uint8_t* hash_be_dev, Fr* table, const uint8_t* z, const uint8_t* y, size_t n,
+                        uint32_t* r_out, uint32_t* rpow_out, uint32_t* rz_out, uint32_t* partials, uint32_t* sum_ry_out, uint32_t* counters);
+void launch_eip_reduce_be(cudaStream_t s, uint8_t* io, size_t m);
+void host_eip4844_batch_hash(uint8_t out[32], const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n);
+void host_eip4844_blob_hash(uint8_t out[32], const uint8_t* blob, const uint8_t* commitment);
 
 // ---- k_msm.cu
 struct MsmWorkspace {

@@ -10,6 +10,7 @@
 #include <mutex>
 
 #include "blobs.hpp"
+#include "eip4844.hpp"
 #include "../include/kzgb200_testing.h"
 
 using namespace orc;
@@ -126,6 +127,65 @@ kzgb_ret verify_kzg_proof_batch(bool* ok, const uint8_t* C, const uint8_t* z, co
 kzgb_ret verify_kzg_proof_batch_device(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi,
                                        size_t n, kzgb_ctx* c, void*) {
     return verify_impl(ok, C, z, y, pi, n, c, false);
+}
+
+kzgb_ret verify_kzg_proof_batch_eip4844(bool* ok, const uint8_t* C, const uint8_t* z, const uint8_t* y, const uint8_t* pi, size_t n,
+                                        kzgb_ctx* c) {
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!c || !C || !z || !y || !pi || n == 0) return KZGB_BADARGS;
+    bool v = false;
+    int rc = verify_batch_eip4844(v, c->art, c->setup, C, z, y, pi, n, c->threads);
+    *ok = v;
+    return rc ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret kzgb_blob_challenges_evals_eip4844(uint8_t* z_out, uint8_t* y_out, const uint8_t* blobs, const uint8_t* comms, size_t m,
+                                            kzgb_ctx* c) {
+    if (!z_out || !y_out || !blobs || !comms || !c || m == 0) return KZGB_BADARGS;
+    return blob_challenges_evals_eip4844(z_out, y_out, blobs, comms, m, c->threads) ? KZGB_BADARGS : KZGB_OK;
+}
+kzgb_ret verify_blob_kzg_proof_batch_eip4844(bool* ok, const uint8_t* blobs, const uint8_t* comms, const uint8_t* proofs, size_t m,
+                                             kzgb_ctx* c) {
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!c || !blobs || !comms || !proofs || m == 0) return KZGB_BADARGS;
+    std::vector<u8> zs(32 * m), ys(32 * m);
+    unsigned bad = blob_challenges_evals_eip4844(zs.data(), ys.data(), blobs, comms, m, c->threads);
+    if (bad) { c->art = Artifacts(); c->art.n = m; c->art.n_bad_scalars = bad; return KZGB_BADARGS; }
+    return verify_kzg_proof_batch_eip4844(ok, comms, zs.data(), ys.data(), proofs, m, c);
+}
+// c-kzg-4844 trusted_setup.txt (see kzgb200.h); the Lagrange section is skipped
+kzgb_ret kzgb_load_trusted_setup_file(kzgb_ctx** out, const char* path, const int* devices, int n_devices, size_t n_max) {
+    if (!out || !path) return KZGB_BADARGS;
+    FILE* f = fopen(path, "r");
+    if (!f) return KZGB_BADARGS;
+    auto token = [&](std::vector<u8>& dst, size_t nbytes) {
+        char buf[512];
+        if (fscanf(f, "%400s", buf) != 1 || strlen(buf) != 2 * nbytes) return false;
+        for (size_t i = 0; i < nbytes; ++i) {
+            unsigned v;
+            if (sscanf(buf + 2 * i, "%2x", &v) != 1) return false;
+            dst.push_back((u8)v);
+        }
+        return true;
+    };
+    unsigned long n1 = 0, n2 = 0;
+    bool okf = fscanf(f, "%lu %lu", &n1, &n2) == 2 && n1 >= 1 && n1 <= (1ul << 20) && n2 >= 2 && n2 <= 4096;
+    std::vector<u8> skip, g1, g2;
+    for (unsigned long i = 0; okf && i < n1; ++i) { skip.clear(); okf = token(skip, 48); }
+    for (unsigned long i = 0; okf && i < n2; ++i) okf = token(g2, 96);
+    if (okf) {
+        unsigned long got = 0;
+        while (got < n1 && token(g1, 48)) ++got;
+        if (got == 0) {
+            g1.clear();
+            g1.resize(48);
+            g1_compress(g1.data(), g1_generator());
+        } else if (got != n1) okf = false;
+    }
+    fclose(f);
+    if (!okf) return KZGB_BADARGS;
+    return kzgb_ctx_create(out, g1.data(), g1.size() / 48, g2.data(), g2.size() / 96, devices, n_devices, n_max);
 }
 
 kzgb_ret kzgb_pipeline_init(kzgb_ctx* c, int depth) {

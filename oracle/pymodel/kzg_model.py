@@ -261,3 +261,64 @@ def cell_batch_artifacts(comms, ci, xi, cells, proofs):
 
 def cell_verdict_tau_shortcut(art) -> bool:
     return bls.g1_add(art["A"], bls.g1_mul(pow(TAU, CELL_LEN, R), art["B"])) is None
+
+
+# ============================================================================= EIP-4844 transcript mode
+# Restated from the consensus-spec functions (deneb/polynomial-commitments.md): verify_kzg_proof_batch,
+# compute_challenge, evaluate_polynomial_in_evaluation_form, hash_to_bls_field.  No c-kzg vector exists offline.
+DOM_BATCH = b"RCKZGBATCH___V1_"
+DOM_BLOB = b"FSBLOBVERIFY_V1_"
+OMEGA_BLOB = pow(7, (R - 1) // FIELD_ELEMENTS_PER_BLOB, R)
+
+
+def eip_batch_digest(C, Z, Y, PI, n) -> bytes:
+    data = DOM_BATCH + FIELD_ELEMENTS_PER_BLOB.to_bytes(8, "big") + n.to_bytes(8, "big")
+    for i in range(n):
+        data += C[48 * i:48 * i + 48] + Z[32 * i:32 * i + 32] + Y[32 * i:32 * i + 32] + PI[48 * i:48 * i + 48]
+    return sha(data)
+
+
+def eip_batch_artifacts(C, Z, Y, PI, n):
+    out = {"ret": KZGB_OK}
+    cs = [bls.g1_decompress(C[48 * i:48 * i + 48]) for i in range(n)]
+    ps = [bls.g1_decompress(PI[48 * i:48 * i + 48]) for i in range(n)]
+    zs = [int.from_bytes(Z[32 * i:32 * i + 32], "big") for i in range(n)]
+    ys = [int.from_bytes(Y[32 * i:32 * i + 32], "big") for i in range(n)]
+    if any(s for s, _ in cs) or any(s for s, _ in ps) or any(v >= R for v in zs) or any(v >= R for v in ys):
+        out["ret"] = KZGB_BADARGS
+        return out
+    digest = eip_batch_digest(C, Z, Y, PI, n)
+    r = int.from_bytes(digest, "big") % R
+    rp = [pow(r, i, R) for i in range(n)]
+    proof_lincomb = proof_z_lincomb = c_minus_y_lincomb = None
+    for i in range(n):
+        proof_lincomb = bls.g1_add(proof_lincomb, bls.g1_mul(rp[i], ps[i][1]))
+        proof_z_lincomb = bls.g1_add(proof_z_lincomb, bls.g1_mul(rp[i] * zs[i] % R, ps[i][1]))
+        c_minus_y = bls.g1_add(cs[i][1], bls.g1_neg(bls.g1_mul(ys[i], bls.G1)))
+        c_minus_y_lincomb = bls.g1_add(c_minus_y_lincomb, bls.g1_mul(rp[i], c_minus_y))
+    a = bls.g1_add(c_minus_y_lincomb, proof_z_lincomb)          # paired with G2
+    b = bls.g1_neg(proof_lincomb)                                # paired with [tau]G2
+    out.update(root=digest, r=r, A=a, B=b, sum_ry=sum(x * y for x, y in zip(rp, ys)) % R)
+    return out
+
+
+def eip_blob_challenge(blob: bytes, commitment: bytes) -> int:
+    data = DOM_BLOB + FIELD_ELEMENTS_PER_BLOB.to_bytes(16, "big") + blob + commitment
+    return int.from_bytes(sha(data), "big") % R
+
+
+def _brp(i, bits):
+    return int(format(i, "0%db" % bits)[::-1], 2)
+
+
+def eip_blob_eval(blob: bytes, z: int) -> int:
+    """evaluate_polynomial_in_evaluation_form over the bit-reversed 4096-th roots of unity"""
+    n = FIELD_ELEMENTS_PER_BLOB
+    f = [int.from_bytes(blob[32 * i:32 * i + 32], "big") for i in range(n)]
+    dom = [pow(OMEGA_BLOB, _brp(i, 12), R) for i in range(n)]
+    if z in dom:
+        return f[dom.index(z)]
+    acc = 0
+    for fi, wi in zip(f, dom):
+        acc = (acc + fi * wi % R * pow((z - wi) % R, -1, R)) % R
+    return acc * (pow(z, n, R) - 1) % R * pow(n, -1, R) % R

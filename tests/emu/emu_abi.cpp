@@ -551,6 +551,10 @@ kzgb_ret kzgb_combine_verify(kzgb_ctx*, const uint8_t*, int, bool*) { return KZG
 kzgb_ret kzgb_shard_phase2_terms(kzgb_ctx*, int, const uint8_t*, uint64_t, void*, uint8_t*) { return KZGB_ERROR; }
 kzgb_ret kzgb_shard_finish(kzgb_ctx*, int, uint32_t*, uint32_t*) { return KZGB_ERROR; }
 kzgb_ret kzgb_pipeline_init(kzgb_ctx*, int) { return KZGB_ERROR; }
+kzgb_ret verify_kzg_proof_batch_eip4844(bool*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, kzgb_ctx*) { return KZGB_ERROR; }
+kzgb_ret verify_blob_kzg_proof_batch_eip4844(bool*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, kzgb_ctx*) { return KZGB_ERROR; }
+kzgb_ret kzgb_blob_challenges_evals_eip4844(uint8_t*, uint8_t*, const uint8_t*, const uint8_t*, size_t, kzgb_ctx*) { return KZGB_ERROR; }
+kzgb_ret kzgb_load_trusted_setup_file(kzgb_ctx**, const char*, const int*, int, size_t) { return KZGB_ERROR; }
 kzgb_ret verify_kzg_proof_batch_submit(uint64_t*, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, size_t, int, kzgb_ctx*) { return KZGB_ERROR; }
 kzgb_ret verify_kzg_proof_batch_wait(bool*, uint64_t, kzgb_ctx*) { return KZGB_ERROR; }
 kzgb_ret kzgb_combine_verify_terms(kzgb_ctx*, const uint8_t*, int, bool*) { return KZGB_ERROR; }

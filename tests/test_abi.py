@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def _declared_symbols():
     txt = (ROOT / "include" / "kzgb200.h").read_text()
-    names = set(re.findall(r"\b(kzgb_[a-z0-9_]+|verify_[a-z_]*kzg_proof[a-z_]*)\s*\(", txt))
+    names = set(re.findall(r"\b(kzgb_[a-z0-9_]+|verify_[a-z_]*kzg_proof[a-z0-9_]*)\s*\(", txt))
     return sorted(n for n in names if n not in ("kzgb_ret",))
 
 
