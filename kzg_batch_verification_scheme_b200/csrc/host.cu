@@ -1478,23 +1478,20 @@ kzgb_ret kzgb_g1_msm_times(float ms_out[4], kzgb_ctx* ctx) {
     return KZGB_OK;
 }
 
-// Cell batch (BASELINE.json config[4]).  Single device (slot 0): 2^14 openings are ~2 ms of work.
-kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, const uint32_t* ci, const uint32_t* xi,
-                                     const uint8_t* cells, const uint8_t* proofs, size_t m, kzgb_ctx* ctx) {
-    KZ_API_GUARD;
-    if (!ok) return KZGB_BADARGS;
-    *ok = false;
-    if (!ctx || !comms || !ci || !xi || !cells || !proofs || m == 0 || nc == 0) return KZGB_BADARGS;
-    DeviceSlot& s = ctx->slots[0];
-    const size_t M = m + nc + 64;                      // points of the A-side sum: proofs | commitments | [tau^j]G1
-    if (!s.cell_ready || M > s.n_max || nc > 0xFFFFFFFFull) return KZGB_BADARGS;
-    // both sums' plans against the workspaces, before anything is launched
-    const MsmPlan planB = msm_make_plan(m, 128), planA = msm_make_plan(2 * M, 128);
-    if ((size_t)planB.W * m > s.sortR.capacity || planB.total_buckets > s.max_bucketsR + 512 || sg_work_entries(planB) + 256 > s.sg_cap ||
-        (size_t)planA.W * 2 * M > s.sortZ.capacity || planA.total_buckets > s.max_bucketsZ + 512 || sg_work_entries(planA) + 256 > s.sg_cap) {
-        fprintf(stderr, "[kzgb200] workspace too small for a cell batch of %zu openings (n_max %zu)\n", m, s.n_max);
-        return KZGB_ERROR;
-    }
+// Cell batch (BASELINE.json config[4]: "on 8xB200").  The openings shard like the plain batch: contiguous ranges, multiples
+// of the 128-leaf hash chunk, one per device of the context.  Everything is linear in the openings, so a shard needs no
+// exchange beyond the chunk digests and the root: it runs K1 on its proofs and on ALL nc commitments, its openings' iNTTs,
+// its PARTIAL column sums S_j and commitment weights w_i, and one A-side sum over [its proofs | all commitments | [tau^j]G1]
+// with those partial scalars plus the B-side sum over its proofs -- the shards' 66 pairing terms add up to the batch's.
+struct CellShard {
+    size_t lo = 0, m = 0, nc = 0;
+    bool sg = false;
+    MsmPlan planA, planB;
+};
+// phase 1 of one shard: copies, leaf + chunk hashes (digests on the host when it returns), K1 left running
+static kzgb_ret cell_phase1(DeviceSlot& s, CellShard& sh, const uint8_t* comms, const uint32_t* ci, const uint32_t* xi,
+                            const uint8_t* cells, const uint8_t* proofs, uint8_t* digests_out) {
+    const size_t m = sh.m, nc = sh.nc, lo = sh.lo;
     CK(cudaSetDevice(s.device));
     cudaStream_t st = s.stream;
     if (m > s.cell_cap) {
@@ -1504,51 +1501,53 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
         s.cell_cap = m;
     }
     s.have_sums = false; s.have_ab = false; s.sums_pending = false; s.cur_n = 0;
-    kzgb_artifacts& art = ctx->art;
-    memset(&art, 0, sizeof art);
-    art.n = m;
     CK(cudaEventRecord(s.ev[0], st));
     CK(cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), st));
     CK(cudaMemcpyAsync(s.dC, comms, 48 * nc, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.dpi, proofs, 48 * m, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.d_ci, ci, 4 * m, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.d_xi, xi, 4 * m, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.d_cells, cells, 2048 * m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.dpi, proofs + 48 * lo, 48 * m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_ci, ci + lo, 4 * m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_xi, xi + lo, 4 * m, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_cells, cells + 2048 * lo, 2048 * m, cudaMemcpyHostToDevice, st));
     // Fiat-Shamir on the side stream: cell leaves -> chunk digests -> host root (binds the commitments as well)
     CK(cudaEventRecord(s.ev[1], st));
     CK(cudaStreamWaitEvent(s.stream2, s.ev[1], 0));
     launch_cell_leaf_hash(s.stream2, s.d_ci, s.d_xi, s.d_cells, s.dpi, m, s.leaves);
     launch_chunk_hash(s.stream2, s.leaves, m, s.digests);
-    size_t nch = (m + KZGB_CHUNK - 1) / KZGB_CHUNK;
+    const size_t nch = (m + KZGB_CHUNK - 1) / KZGB_CHUNK;
     CK(cudaMemcpyAsync(s.h_digests, s.digests, 32 * nch, cudaMemcpyDeviceToHost, s.stream2));
     CK(cudaEventRecord(s.ev[2], s.stream2));
-    // K1 on proofs and commitments; the 64 setup monomials follow them in the point array.  Large batches prove
-    // subgroup membership of the proofs on the bucket slices of the B-side sum (sum r_k pi_k), like the plain batch;
-    // the few commitments get the per-point check on their own stream (three serial chains of pure latency)
-    const bool sg = s.sg_min && m >= s.sg_min && m >= 2;
-    s.sg_batch = sg;
-    s.cur_n = 0;
+    // K1 on proofs and commitments; the 64 setup monomials follow them in the point array.  Large shards prove subgroup
+    // membership of the proofs on the bucket slices of the B-side sum (sum r_k pi_k), like the plain batch; the few
+    // commitments get the per-point check on their own stream (three serial chains of pure latency)
+    sh.sg = s.sg_min && m >= s.sg_min && m >= 2;
+    s.sg_batch = sh.sg;
     CK(cudaStreamWaitEvent(s.stream4, s.ev[1], 0));
     launch_decompress_points(s.stream4, s.dC, nc, s.pts + 2 * m, s.k1_tmp + 3 * m, s.status + m, s.counters);
     CK(cudaEventRecord(s.ev[13], s.stream4));
-    if (sg) launch_decompress_sqrt_points(st, s.dpi, m, s.pts, s.status, s.counters);
+    if (sh.sg) launch_decompress_sqrt_points(st, s.dpi, m, s.pts, s.status, s.counters);
     else launch_decompress_points(st, s.dpi, m, s.pts, s.k1_tmp, s.status, s.counters);
     CK(cudaStreamWaitEvent(st, s.ev[13], 0));
     CK(cudaMemcpyAsync(s.pts + 2 * (m + nc), s.cell_g1, 2 * 64 * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     CK(cudaEventSynchronize(s.ev[2]));
-    std::vector<uint8_t> dig(32 * nch);
-    words_to_be(dig.data(), (const uint32_t*)s.h_digests, 8 * nch);
-    uint8_t root[32];
-    host_sha256_cell_root(root, comms, nc, dig.data(), nch, m);
-    memcpy(art.root, root, 32);
+    words_to_be(digests_out, (const uint32_t*)s.h_digests, 8 * nch);
+    return KZGB_OK;
+}
+// phase 2 of one shard: scalars, both sums, the shard's 66 pairing terms in s.mp_terms (classic: A, B in s.sums[3..4])
+static kzgb_ret cell_phase2(DeviceSlot& s, const CellShard& sh, const uint8_t root[32]) {
+    const size_t m = sh.m, nc = sh.nc, M = m + nc + 64;
+    CK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
     be_to_words(s.h_small + 8, root, 8);
     CK(cudaMemcpyAsync(s.root_words, s.h_small + 8, 32, cudaMemcpyHostToDevice, st));
     // per opening: r_k, r_k h^64, r_k * interpolation coefficients; then column sums and commitment weights
-    launch_cell_scalars(st, s.cell_W, s.root_words, s.d_ci, s.d_xi, (uint32_t)nc, s.d_cells, m, s.cell_coefs, s.r, s.rz, s.counters);
+    launch_cell_scalars(st, s.cell_W, s.root_words, s.d_ci, s.d_xi, (uint32_t)nc, s.d_cells, m, (uint64_t)sh.lo, s.cell_coefs, s.r, s.rz,
+                        s.counters);
     launch_cell_reductions(st, s.cell_coefs, s.d_ci, s.r, m, (uint32_t)nc, s.rz + 8 * m, s.rz + 8 * (m + nc));
     CK(cudaMemsetAsync(s.sum_ry, 0, 8 * sizeof(uint32_t), st));
     CK(cudaEventRecord(s.ev[11], st));
     // B-side: sum r_k pi_k, 128-bit scalars, on a side stream beside the A-side sum
+    const MsmPlan& planB = sh.planB;
+    const MsmPlan& planA = sh.planA;
     MsmWorkspace wsB = make_ws(s, s.sortR, s.bucketsA);
     {
         cudaStream_t sb = s.stream3;
@@ -1559,9 +1558,9 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
         msm_sort_stage(sb, planB, s.r, 4, m, wsB);
         save_ws(s.sortR, wsB);
         msm_accumulate_stage(sb, planB, s.pts, m, wsB);
-        if (s.classic) msm_window_sums_stage(sb, planB, wsB, sg); else msm_slices_stage(sb, planB, wsB, sg);
+        if (s.classic) msm_window_sums_stage(sb, planB, wsB, sh.sg); else msm_slices_stage(sb, planB, wsB, sh.sg);
         CK(cudaEventRecord(s.ev[12], sb));
-        if (sg) {
+        if (sh.sg) {
             launch_sg_check(sb, planB, wsB, wsB, s.counters, 1);
             CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, sb));
             CK(cudaEventRecord(s.ev[9], sb));
@@ -1577,46 +1576,139 @@ kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, 
     msm_accumulate_stage(st, planA, s.pts, mm, wsA);
     if (s.classic) msm_window_sums_stage(st, planA, wsA, false); else msm_slices_stage(st, planA, wsA, false);
     CK(cudaStreamWaitEvent(st, s.ev[12], 0));
-    ctx->terms_combined = false;
     if (s.classic) {
         const MsmPlan* plans[2] = {&planA, &planB};
         MsmWorkspace* wss[2] = {&wsA, &wsB};
         G1Jac* outs[2] = {s.sums + 0, s.sums + 2};
         msm_combine_stage(st, plans, wss, outs, 2);
         launch_set_ab(st, s.sums + 0, s.sums + 2, s.sums + 3);
-        launch_pairing(st, s.lines_cell, s.sums + 3, s.result_dev);
     } else {
         // A-side sum and -(B-side sum) as 2 x 33 pairing terms against the multiples of (G2, [tau^64]G2)
         const MpSumDesc dA = {wsA.slices, wsA.buckets, planA.c, planA.W, planA.nbits};
         const MpSumDesc dNone = {nullptr, nullptr, 0, 0, -1};
         const MpSumDesc dB = {wsB.slices, wsB.buckets, planB.c, planB.W, planB.nbits};
         launch_mp_terms(st, dA, dNone, dB, s.mp_terms);
-        launch_mp_coefs(st, s.mp_terms, 1, s.mp_coef);
-        launch_mp_check(st, s.mp_tab_cell, s.mp_coef, s.mp_part, s.mp_F, s.result_dev);
     }
-    CK(cudaMemcpyAsync(s.h_small + 16, s.result_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (!sg) CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(s.ev[8], st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    if (sg) {
-        // verdict of the batched check (it ran beside the pairing); on failure the per-point chains name the proofs
-        CK(cudaEventSynchronize(s.ev[9]));
-        if (s.h_small[2]) {
-            launch_subgroup_points(st, s.pts, m, s.k1_tmp, s.status, s.counters);
-            CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            CK(cudaGetLastError());
+    CK(cudaEventRecord(s.ev[7], st));
+    if (!sh.sg) CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    return KZGB_OK;
+}
+// input-validation verdict of one shard (after its main stream has been synchronised); on a failed slice check the
+// per-point chains name the proofs
+static kzgb_ret cell_finish(DeviceSlot& s, const CellShard& sh) {
+    if (!sh.sg) return KZGB_OK;
+    CK(cudaSetDevice(s.device));
+    CK(cudaEventSynchronize(s.ev[9]));
+    if (s.h_small[2]) {
+        launch_subgroup_points(s.stream, s.pts, sh.m, s.k1_tmp, s.status, s.counters);
+        CK(cudaMemcpyAsync(s.h_small, s.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        CK(cudaGetLastError());
+    }
+    s.sg_batch = false;
+    return KZGB_OK;
+}
+kzgb_ret verify_cell_kzg_proof_batch(bool* ok, const uint8_t* comms, size_t nc, const uint32_t* ci, const uint32_t* xi,
+                                     const uint8_t* cells, const uint8_t* proofs, size_t m, kzgb_ctx* ctx) {
+    KZ_API_GUARD;
+    if (!ok) return KZGB_BADARGS;
+    *ok = false;
+    if (!ctx || !comms || !ci || !xi || !cells || !proofs || m == 0 || nc == 0 || nc > 0xFFFFFFFFull) return KZGB_BADARGS;
+    // shards: contiguous, multiples of the hash chunk; a shard below 1024 openings is all fixed latency, so small batches
+    // use fewer devices
+    const size_t nch = (m + KZGB_CHUNK - 1) / KZGB_CHUNK;
+    size_t G = ctx->slots.size();
+    const bool classic = ctx->slots[0].classic;
+    if (classic) G = 1;
+    while (G > 1 && (m / G < 1024 || G > nch)) --G;
+    std::vector<CellShard> sh(G);
+    for (size_t g = 0; g < G; ++g) {
+        size_t a = nch * g / G * KZGB_CHUNK, b = g + 1 == G ? m : nch * (g + 1) / G * KZGB_CHUNK;
+        sh[g].lo = a; sh[g].m = b - a; sh[g].nc = nc;
+        DeviceSlot& s = ctx->slots[g];
+        const size_t M = sh[g].m + nc + 64;                   // points of the A-side sum: proofs | commitments | [tau^j]G1
+        if (!s.cell_ready || M > s.n_max) return KZGB_BADARGS;
+        // both sums' plans against the workspaces, before anything is launched
+        sh[g].planB = msm_make_plan(sh[g].m, 128);
+        sh[g].planA = msm_make_plan(2 * M, 128);
+        const MsmPlan &pB = sh[g].planB, &pA = sh[g].planA;
+        if ((size_t)pB.W * sh[g].m > s.sortR.capacity || pB.total_buckets > s.max_bucketsR + 512 || sg_work_entries(pB) + 256 > s.sg_cap ||
+            (size_t)pA.W * 2 * M > s.sortZ.capacity || pA.total_buckets > s.max_bucketsZ + 512 || sg_work_entries(pA) + 256 > s.sg_cap) {
+            fprintf(stderr, "[kzgb200] workspace too small for a cell batch shard of %zu openings (n_max %zu)\n", sh[g].m, s.n_max);
+            return KZGB_ERROR;
         }
-        s.sg_batch = false;
     }
-    art.n_bad_points = s.h_small[0];
-    art.n_bad_scalars = s.h_small[1];
-    art.stage_ms[9] = ev_ms(s.ev[0], s.ev[8]);
-    if (s.h_small[0] || s.h_small[1]) return KZGB_BADARGS;
-    if (s.classic) s.have_ab = true;
-    else { ctx->terms_combined = true; ctx->ab_terms = s.mp_terms; ctx->ab_shards = 1; ctx->ab_gather_sum_ry = false; }
-    *ok = s.h_small[16] == 1;
+    kzgb_artifacts& art = ctx->art;
+    memset(&art, 0, sizeof art);
+    art.n = m;
+    ctx->terms_combined = false;
+    ctx->n_shards_last = (int)G;
+    std::vector<uint8_t> dig(32 * nch);
+    std::vector<kzgb_ret> rcs(G, KZGB_OK);
+    auto first_error = [&]() { for (kzgb_ret r : rcs) if (r) return r; return KZGB_OK; };
+    ctx->pool.run(G, [&](size_t g) {
+        rcs[g] = cell_phase1(ctx->slots[g], sh[g], comms, ci, xi, cells, proofs, dig.data() + 32 * (sh[g].lo / KZGB_CHUNK));
+    });
+    if (kzgb_ret rc = first_error()) return rc;
+    uint8_t root[32];
+    host_sha256_cell_root(root, comms, nc, dig.data(), nch, m);
+    memcpy(art.root, root, 32);
+    DeviceSlot& s0 = ctx->slots[0];
+    std::vector<uint32_t> badp(G, 0), bads(G, 0);
+    ctx->pool.run(G, [&](size_t g) {
+        DeviceSlot& s = ctx->slots[g];
+        rcs[g] = cell_phase2(s, sh[g], root);
+        if (rcs[g] || G == 1) return;
+        auto body = [&]() -> kzgb_ret {
+            CK(cudaMemcpyAsync(s.h_terms, s.mp_terms, sizeof(G1Xyzz) * KZ_MP_PAIRS, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaStreamSynchronize(s.stream));
+            CK(cudaGetLastError());
+            if (kzgb_ret frc = cell_finish(s, sh[g])) return frc;
+            badp[g] = s.h_small[0]; bads[g] = s.h_small[1];
+            return KZGB_OK;
+        };
+        rcs[g] = body();
+    });
+    if (kzgb_ret rc = first_error()) return rc;
+    CK(cudaSetDevice(s0.device));
+    cudaStream_t st = s0.stream;
+    kzgb_ret rc = KZGB_OK;
+    if (G == 1) {
+        if (classic) launch_pairing(st, s0.lines_cell, s0.sums + 3, s0.result_dev);
+        else {
+            launch_mp_coefs(st, s0.mp_terms, 1, s0.mp_coef);
+            launch_mp_check(st, s0.mp_tab_cell, s0.mp_coef, s0.mp_part, s0.mp_F, s0.result_dev);
+        }
+        CK(cudaMemcpyAsync(s0.h_small + 16, s0.result_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(s0.ev[8], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        rc = cell_finish(s0, sh[0]);                      // the batched check ran beside the pairing
+        badp[0] = s0.h_small[0]; bads[0] = s0.h_small[1];
+        *ok = s0.h_small[16] == 1;
+    } else {
+        uint32_t anyb = 0;
+        for (size_t g = 0; g < G; ++g) anyb |= badp[g] | bads[g];
+        if (!anyb) {
+            for (size_t g = 0; g < G; ++g)
+                CK(cudaMemcpyAsync(s0.mp_terms_in + g * KZ_MP_PAIRS, ctx->slots[g].h_terms, sizeof(G1Xyzz) * KZ_MP_PAIRS,
+                                   cudaMemcpyHostToDevice, st));
+            rc = mp_finish(s0, s0.mp_terms_in, (int)G, s0.mp_tab_cell, ok);
+        }
+    }
+    uint32_t tp = 0, ts = 0;
+    for (size_t g = 0; g < G; ++g) { tp += badp[g]; ts += bads[g]; }
+    art.n_bad_points = tp;
+    art.n_bad_scalars = ts;
+    art.stage_ms[9] = ev_ms(s0.ev[0], s0.ev[8]);
+    if (rc || tp || ts) { *ok = false; return rc ? rc : KZGB_BADARGS; }
+    if (classic) s0.have_ab = true;
+    else {
+        ctx->terms_combined = true;
+        ctx->ab_terms = G == 1 ? s0.mp_terms : s0.mp_terms_in;
+        ctx->ab_shards = (int)G;
+        ctx->ab_gather_sum_ry = false;
+    }
     return KZGB_OK;
 }
 

@@ -36,19 +36,20 @@ void launch_cell_leaf_hash(cudaStream_t s, const uint32_t* ci, const uint32_t* x
 
 __global__ void __launch_bounds__(KZ_CELL_LEN) k_cell_scalars(const Fr* __restrict__ W, const u32* __restrict__ root_words,
                                                               const u32* __restrict__ ci, const u32* __restrict__ xi, u32 nc,
-                                                              const u8* __restrict__ cells, size_t m, Fr* __restrict__ coefs,
+                                                              const u8* __restrict__ cells, size_t m, u64 k0, Fr* __restrict__ coefs,
                                                               u32* __restrict__ r_out, u32* __restrict__ rh_out,
                                                               u32* __restrict__ counters) {
     __shared__ CellScratch S;
     size_t k = blockIdx.x;
     if (k >= m) return;
-    coop_cell_body(S, W, root_words, (u64)k, ci[k], xi[k], nc, cells + 2048 * k, coefs + KZ_CELL_LEN * k, r_out + 4 * k, rh_out + 8 * k);
+    // k0: index of this shard's first opening in the whole batch (the challenge r_k hashes the global index)
+    coop_cell_body(S, W, root_words, k0 + (u64)k, ci[k], xi[k], nc, cells + 2048 * k, coefs + KZ_CELL_LEN * k, r_out + 4 * k, rh_out + 8 * k);
     if (threadIdx.x == 0 && S.bad) atomicAdd(counters + 1, S.bad);
 }
 void launch_cell_scalars(cudaStream_t s, const Fr* W, const uint32_t* root_words, const uint32_t* ci, const uint32_t* xi, uint32_t nc,
-                         const uint8_t* cells, size_t m, Fr* coefs, uint32_t* r_out, uint32_t* rh_out, uint32_t* counters) {
+                         const uint8_t* cells, size_t m, uint64_t k0, Fr* coefs, uint32_t* r_out, uint32_t* rh_out, uint32_t* counters) {
     if (!m) return;
-    k_cell_scalars<<<(unsigned)m, KZ_CELL_LEN, 0, s>>>(W, root_words, ci, xi, nc, cells, m, coefs, r_out, rh_out, counters);
+    k_cell_scalars<<<(unsigned)m, KZ_CELL_LEN, 0, s>>>(W, root_words, ci, xi, nc, cells, m, k0, coefs, r_out, rh_out, counters);
     KZ_COUNT_LAUNCH();
 }
 

@@ -131,7 +131,7 @@ void launch_blob_eval(cudaStream_t s, const Fr* W, const uint8_t* blobs, const u
 void launch_cell_leaf_hash(cudaStream_t s, const uint32_t* ci, const uint32_t* xi, const uint8_t* cells, const uint8_t* proofs, size_t m,
                            uint32_t* leaves);
 void launch_cell_scalars(cudaStream_t s, const Fr* W, const uint32_t* root_words, const uint32_t* ci, const uint32_t* xi, uint32_t nc,
-                         const uint8_t* cells, size_t m, Fr* coefs, uint32_t* r_out, uint32_t* rh_out, uint32_t* counters);
+                         const uint8_t* cells, size_t m, uint64_t k0, Fr* coefs, uint32_t* r_out, uint32_t* rh_out, uint32_t* counters);
 void launch_cell_reductions(cudaStream_t s, const Fr* coefs, const uint32_t* ci, const uint32_t* r, size_t m, uint32_t nc,
                             uint32_t* w_out, uint32_t* negS_out);
 void host_sha256_cell_root(uint8_t out[32], const uint8_t* comms, size_t nc, const uint8_t* digests, size_t n_chunks, uint64_t m);

@@ -442,3 +442,36 @@ def test_gpu_in_process_multi_device_equals_single(gpu_lib, oracle_lib):
         assert ctx.verify_kzg_proof_batch(C, Z, Y, PI, n) == (0, True)
         ctx.close()
     one.close(); octx.close()
+
+
+def test_gpu_cell_batch_multi_device(gpu_lib, oracle_lib):
+    """BASELINE.json config[4] "on 8xB200": the 2^14 openings sharded over every physical device of the box (in-process
+    context over devices 0..G-1): verdict, pairing inputs A, B and the root equal the oracle's and the one-device run; a
+    tampered evaluation in the LAST shard is rejected; a proof outside G1 in a middle shard is BADARGS with count 1."""
+    import torch
+    from tests.test_cells_oracle import synth_cells
+    G = torch.cuda.device_count()
+    if G < 2:
+        pytest.skip("needs at least 2 physical GPUs (run with gpurun --gpus 2)")
+    g1, g2 = oracle_lib.synth_setup(64, 65)
+    octx = oracle_lib.context(g1, g2)
+    comms, ci, xi, cells, proofs = synth_cells(oracle_lib, 0x4B5A4704, 128, 128, 4096)
+    m = len(ci)
+    assert octx.verify_cell_kzg_proof_batch(comms, ci, xi, cells, proofs) == (0, True)
+    ao = octx.last_artifacts()
+    bad = bytearray(cells); bad[2048 * (m - 3) + 32 * 13 + 30] ^= 4
+    off = bytearray(proofs); off[48 * (m // 2):48 * (m // 2 + 1)] = b.g1_compress((0, 2))
+    for g in sorted({1, 2, G}):
+        ctx = gpu_lib.context(g1, g2, devices=list(range(g)), n_max=1 << 15)
+        for _ in range(2):
+            assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, cells, proofs) == (0, True)
+            a = ctx.last_artifacts()
+            assert a["A"] == ao["A"] and a["B"] == ao["B"] and a["root"] == ao["root"], g
+        assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, bytes(bad), proofs) == (0, False)
+        assert ctx.verify_cell_kzg_proof_batch(comms, ci, xi, cells, bytes(off)) == (1, False)
+        assert ctx.last_artifacts()["n_bad_points"] == 1
+        # a small batch on the same context uses fewer devices
+        small = synth_cells(oracle_lib, 0x4B5A4727, 3, 40, 256)
+        assert ctx.verify_cell_kzg_proof_batch(*small) == octx.verify_cell_kzg_proof_batch(*small) == (0, True)
+        ctx.close()
+    octx.close()
