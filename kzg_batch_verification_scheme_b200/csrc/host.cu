@@ -42,7 +42,7 @@ namespace {
 
 struct SortBuf {
     uint32_t *keys = nullptr, *vals = nullptr, *keys_alt = nullptr, *vals_alt = nullptr, *bucket_start = nullptr;
-    uint32_t *count = nullptr, *cursor = nullptr;
+    uint32_t *count = nullptr, *cursor = nullptr, *tile_sum = nullptr;
     size_t capacity = 0;
 };
 
@@ -222,6 +222,7 @@ kzgb_ret slot_alloc_sort(SortBuf& b, size_t cap, size_t buckets) {
     b.capacity = cap;
     CK(dmalloc(b.keys, cap)); CK(dmalloc(b.vals, cap)); CK(dmalloc(b.keys_alt, cap)); CK(dmalloc(b.vals_alt, cap));
     CK(dmalloc(b.bucket_start, buckets + 2)); CK(dmalloc(b.count, buckets + 2)); CK(dmalloc(b.cursor, buckets + 2));
+    CK(dmalloc(b.tile_sum, 1024));
     return KZGB_OK;
 }
 
@@ -358,7 +359,7 @@ void slot_free(DeviceSlot& s) {
     if (s.stream2) cudaStreamSynchronize(s.stream2);
     void* dev[] = {s.dC, s.dz, s.dy, s.dpi, s.pts, s.k1_tmp, s.status, s.counters, s.leaves, s.digests, s.root_words, s.r, s.rz,
                    s.partials, s.sum_ry, s.zs, s.sortR.keys, s.sortR.vals, s.sortR.keys_alt, s.sortR.vals_alt, s.sortR.bucket_start, s.sortR.count, s.sortR.cursor,
-                   s.sortZ.count, s.sortZ.cursor,
+                   s.sortZ.count, s.sortZ.cursor, s.sortR.tile_sum, s.sortZ.tile_sum,
                    s.sortZ.keys, s.sortZ.vals, s.sortZ.keys_alt, s.sortZ.vals_alt, s.sortZ.bucket_start, s.bucketsA,
                    s.bucketsB, s.bucketsC, s.winsums, s.sums, s.partial_dev, s.partials_in,
                    s.scratch, s.result_dev, s.lines, s.g1_pt, s.setup_status, s.comb, s.recs.head, s.recs.tail,
@@ -381,7 +382,7 @@ void slot_free(DeviceSlot& s) {
 MsmWorkspace make_ws(DeviceSlot& s, SortBuf& b, G1Xyzz* buckets) {
     MsmWorkspace ws;
     ws.keys = b.keys; ws.vals = b.vals; ws.keys_alt = b.keys_alt; ws.vals_alt = b.vals_alt;
-    ws.capacity = b.capacity; ws.bucket_start = b.bucket_start; ws.count = b.count; ws.cursor = b.cursor;
+    ws.capacity = b.capacity; ws.bucket_start = b.bucket_start; ws.count = b.count; ws.cursor = b.cursor; ws.tile_sum = b.tile_sum;
     ws.buckets = buckets;
     ws.winsums = s.winsums; ws.recs = s.recs;
     ws.sg_work = s.sg_partial; ws.slices = s.sg_partial + s.sg_cap - 256;

@@ -24,31 +24,84 @@ __global__ void __launch_bounds__(128) k_msm_digits(const u32* __restrict__ scal
     for (int w = 0; w < plan.W; ++w) atomicAdd(&count[keys[(size_t)w * m + i]], 1u);
 }
 
-// exclusive scan of count[0 .. nkeys) into start[0 .. nkeys] (start[nkeys] = N) and a working copy `cursor`.
-// One block: each thread owns a contiguous slice, block-level scan of the slice totals in shared memory.
-#define KZ_SCAN_THREADS 1024
-__global__ void __launch_bounds__(KZ_SCAN_THREADS) k_bucket_scan(const u32* __restrict__ count, u32 nkeys, u32* __restrict__ start,
-                                                                 u32* __restrict__ cursor) {
-    __shared__ u32 part[KZ_SCAN_THREADS];
-    u32 per = (nkeys + KZ_SCAN_THREADS - 1) / KZ_SCAN_THREADS;
-    u32 lo = threadIdx.x * per, hi = lo + per < nkeys ? lo + per : nkeys;
-    u32 sum = 0;
-    for (u32 k = lo; k < hi; ++k) sum += count[k];
-    part[threadIdx.x] = sum;
+// Exclusive scan of count[0 .. nkeys) into start[0 .. nkeys] (start[nkeys] = N) and a working copy `cursor`: the bucket
+// boundary table.  Three small launches of 256-thread blocks (tile sums, scan of the <= 1024 tile sums, tile scans):
+// blocks this small fit beside the resident K1 blocks, so the side stream does not wait for a K1 wave to retire -- the
+// single 1024-thread block of round 1 did (and took 0.44 ms per sum at n = 2^20 on one SM).
+#define KZ_SCAN_THREADS 256
+#define KZ_SCAN_ITEMS 8
+#define KZ_SCAN_TILE (KZ_SCAN_THREADS * KZ_SCAN_ITEMS)
+#define KZ_SCAN_MAX_TILES 1024
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* sh, u32& total) {
+    // Hillis-Steele over KZ_SCAN_THREADS values in shared memory; returns the exclusive prefix of this thread
+    sh[threadIdx.x] = v;
     __syncthreads();
-    for (int off = 1; off < KZ_SCAN_THREADS; off <<= 1) {          // Hillis-Steele inclusive scan
-        u32 v = (int)threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+    for (int off = 1; off < KZ_SCAN_THREADS; off <<= 1) {
+        u32 t = (int)threadIdx.x >= off ? sh[threadIdx.x - off] : 0u;
         __syncthreads();
-        part[threadIdx.x] += v;
+        sh[threadIdx.x] += t;
         __syncthreads();
     }
-    u32 run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
-    for (u32 k = lo; k < hi; ++k) {
-        start[k] = run;
-        cursor[k] = run;
-        run += count[k];
+    total = sh[KZ_SCAN_THREADS - 1];
+    u32 incl = sh[threadIdx.x];
+    __syncthreads();
+    return incl - v;
+}
+__global__ void __launch_bounds__(KZ_SCAN_THREADS) k_scan_tiles(const u32* __restrict__ count, u32 nkeys, u32 tiles_per_block,
+                                                                u32* __restrict__ tile_sum) {
+    __shared__ u32 sh[KZ_SCAN_THREADS];
+    // block b sums tiles_per_block consecutive tiles (so that at most KZ_SCAN_MAX_TILES sums remain)
+    const u32 lo = blockIdx.x * tiles_per_block * KZ_SCAN_TILE;
+    u32 hi = lo + tiles_per_block * KZ_SCAN_TILE;
+    if (hi > nkeys) hi = nkeys;
+    u32 sum = 0;
+    for (u32 k = lo + threadIdx.x; k < hi; k += KZ_SCAN_THREADS) sum += count[k];
+    u32 total;
+    block_exclusive_scan(sum, sh, total);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(KZ_SCAN_THREADS) k_scan_tile_sums(u32* __restrict__ tile_sum, u32 nblocks, u32 nkeys, u32* __restrict__ start) {
+    __shared__ u32 sh[KZ_SCAN_THREADS];
+    // <= KZ_SCAN_MAX_TILES values: each thread owns a contiguous slice of 4
+    const u32 per = (nblocks + KZ_SCAN_THREADS - 1) / KZ_SCAN_THREADS;
+    const u32 lo = threadIdx.x * per, hi = lo + per < nblocks ? lo + per : nblocks;
+    u32 sum = 0;
+    for (u32 k = lo; k < hi; ++k) sum += tile_sum[k];
+    u32 total;
+    u32 run = block_exclusive_scan(sum, sh, total);
+    for (u32 k = lo; k < hi; ++k) { u32 v = tile_sum[k]; tile_sum[k] = run; run += v; }
+    if (threadIdx.x == 0) start[nkeys] = total;
+}
+__global__ void __launch_bounds__(KZ_SCAN_THREADS) k_scan_final(const u32* __restrict__ count, u32 nkeys, u32 tiles_per_block,
+                                                                const u32* __restrict__ tile_off, u32* __restrict__ start,
+                                                                u32* __restrict__ cursor) {
+    __shared__ u32 sh[KZ_SCAN_THREADS];
+    u32 base = tile_off[blockIdx.x];
+    for (u32 t = 0; t < tiles_per_block; ++t) {
+        const u32 lo = (blockIdx.x * tiles_per_block + t) * KZ_SCAN_TILE + threadIdx.x * KZ_SCAN_ITEMS;
+        u32 v[KZ_SCAN_ITEMS], sum = 0;
+#pragma unroll
+        for (int i = 0; i < KZ_SCAN_ITEMS; ++i) { v[i] = lo + i < nkeys ? count[lo + i] : 0u; sum += v[i]; }
+        u32 total;
+        u32 run = base + block_exclusive_scan(sum, sh, total);
+#pragma unroll
+        for (int i = 0; i < KZ_SCAN_ITEMS; ++i) {
+            if (lo + i < nkeys) { start[lo + i] = run; cursor[lo + i] = run; }
+            run += v[i];
+        }
+        base += total;
     }
-    if (threadIdx.x == KZ_SCAN_THREADS - 1) start[nkeys] = part[KZ_SCAN_THREADS - 1];
+}
+static void launch_bucket_scan(cudaStream_t s, const u32* count, u32 nkeys, u32* start, u32* cursor, u32* tile_sum) {
+    const u32 tiles = (nkeys + KZ_SCAN_TILE - 1) / KZ_SCAN_TILE;
+    const u32 tpb = (tiles + KZ_SCAN_MAX_TILES - 1) / KZ_SCAN_MAX_TILES;          // tiles per block: 1 up to 2 M keys
+    const u32 nblocks = (tiles + tpb - 1) / tpb;
+    k_scan_tiles<<<nblocks, KZ_SCAN_THREADS, 0, s>>>(count, nkeys, tpb, tile_sum);
+    KZ_COUNT_LAUNCH();
+    k_scan_tile_sums<<<1, KZ_SCAN_THREADS, 0, s>>>(tile_sum, nblocks, nkeys, start);
+    KZ_COUNT_LAUNCH();
+    k_scan_final<<<nblocks, KZ_SCAN_THREADS, 0, s>>>(count, nkeys, tpb, tile_sum, start, cursor);
+    KZ_COUNT_LAUNCH();
 }
 __global__ void __launch_bounds__(256) k_bucket_scatter(const u32* __restrict__ keys, const u32* __restrict__ vals, size_t N,
                                                         u32* __restrict__ cursor, u32* __restrict__ skeys, u32* __restrict__ svals) {
@@ -324,8 +377,7 @@ void msm_sort_stage(cudaStream_t s, const MsmPlan& plan, const uint32_t* scalars
     cudaMemsetAsync(ws.count, 0, sizeof(u32) * (nkeys + 1), s);
     k_msm_digits<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(scalars, nl, m, ws.keys_alt, ws.vals_alt, ws.count, plan);
     KZ_COUNT_LAUNCH();
-    k_bucket_scan<<<1, KZ_SCAN_THREADS, 0, s>>>(ws.count, nkeys, ws.bucket_start, ws.cursor);
-    KZ_COUNT_LAUNCH();
+    launch_bucket_scan(s, ws.count, nkeys, ws.bucket_start, ws.cursor, ws.tile_sum);
     k_bucket_scatter<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(ws.keys_alt, ws.vals_alt, N, ws.cursor, ws.keys, ws.vals);
     KZ_COUNT_LAUNCH();
 }

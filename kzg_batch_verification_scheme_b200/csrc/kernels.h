@@ -60,6 +60,7 @@ struct MsmWorkspace {
     size_t capacity;
     uint32_t* bucket_start;                        // total_buckets + 2: exclusive scan of the key histogram
     uint32_t *count, *cursor;                      // total_buckets + 2 each: histogram, scatter cursors
+    uint32_t* tile_sum;                            // 1024: tile sums of the bucket scan
     G1Xyzz* buckets;                               // max total buckets
     G1Xyzz* sg_work;                               // sg_work_entries(plan): run sums and row / column totals
     G1Xyzz* slices;                                // 256: slice sums of the last reduction
