@@ -64,11 +64,7 @@ __global__ void __launch_bounds__(32) k_mp_coefs(const G1Xyzz* __restrict__ term
     Quad q = quad_make(qsm, qi);
     G1Xyzz acc = terms_in[p];
     for (int g = 1; g < n_shards; ++g) acc = quad_xyzz_add(q, acc, terms_in[(size_t)g * KZ_MP_PAIRS + p]);
-    MpCoef c;
-    Fp d0;
-    quad_mul4(q, acc.ZZ, acc.ZZZ, acc.X, acc.ZZZ, acc.Y, acc.ZZ, acc.Y, acc.ZZ, c.alpha, c.beta, c.gamma, d0);
-    c.inf = xyzz_is_inf(acc) ? 1u : 0u;
-    c.pad[0] = c.pad[1] = c.pad[2] = 0;
+    const MpCoef c = mp_coef_of(q, acc);
     if (q.ql == 0) coef[p] = c;
 }
 void launch_mp_coefs(cudaStream_t s, const G1Xyzz* terms_in, int n_shards, MpCoef* coef) {
@@ -92,15 +88,7 @@ __global__ void __launch_bounds__(128 * MP_UNITS) k_mp_lines(const G2Lines* __re
     // line values as dense Fp12: l = a alpha + (b beta) w^2 + gamma w^3; a pair at infinity contributes 1
     for (int idx = threadIdx.x; idx < nl * 12; idx += blockDim.x) {
         const int l = idx / 12, ci = idx - 12 * l, p = grp + l * MP_NG;
-        const MpCoef& cf = coef[p];
-        const G2Lines& T = tab[p];
-        const bool inf = cf.inf != 0;
-        Fp v = fp_zero();
-        if (!inf && (ci < 2 || ci == 4 || ci == 5)) {
-            const Fp2& src = ci < 2 ? T.a[s] : T.b[s];
-            v = fp_mul((ci & 1) ? src.c1 : src.c0, ci < 2 ? cf.alpha : cf.beta);
-        } else if (!inf && ci == 6) v = cf.gamma;
-        else if (inf && ci == 0) v = fp_one();
+        const Fp v = mp_line_coeff(tab[p], s, coef[p], ci);
         if (ci & 1) pool[l].c[ci >> 1].c1 = v; else pool[l].c[ci >> 1].c0 = v;
     }
     __syncthreads();

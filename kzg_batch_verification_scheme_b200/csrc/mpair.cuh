@@ -61,6 +61,28 @@ KZ_HD G1Xyzz mp_term(Quad& q, const MpSumDesc& d, int t) {
     }
     return acc;
 }
+// (ZZ ZZZ, X ZZZ, Y ZZ) of a term: the three products every line of its pair needs.  With x = X/ZZ, y = Y/ZZZ the line
+// a + (b x) w^2 + y w^3 scaled by ZZ ZZZ (a factor in Fp, killed by the final exponentiation) is a alpha + (b beta) w^2 + gamma w^3.
+KZ_HD MpCoef mp_coef_of(Quad& q, const G1Xyzz& acc) {
+    MpCoef c;
+    Fp d0;
+    quad_mul4(q, acc.ZZ, acc.ZZZ, acc.X, acc.ZZZ, acc.Y, acc.ZZ, acc.Y, acc.ZZ, c.alpha, c.beta, c.gamma, d0);
+    c.inf = xyzz_is_inf(acc) ? 1u : 0u;
+    c.pad[0] = c.pad[1] = c.pad[2] = 0;
+    return c;
+}
+// Fp coefficient ci (0..11: c[ci/2].c0 / .c1) of the line value of Miller step s at a pair, as a dense Fp12;
+// a pair at infinity contributes the constant 1
+KZ_HD Fp mp_line_coeff(const G2Lines& T, int s, const MpCoef& cf, int ci) {
+    const bool inf = cf.inf != 0;
+    if (!inf && (ci < 2 || ci == 4 || ci == 5)) {
+        const Fp2& src = ci < 2 ? T.a[s] : T.b[s];
+        return fp_mul((ci & 1) ? src.c1 : src.c0, ci < 2 ? cf.alpha : cf.beta);
+    }
+    if (!inf && ci == 6) return cf.gamma;
+    if (inf && ci == 0) return fp_one();
+    return fp_zero();
+}
 // Miller step index of iteration it (bit 62 - it): doubling step, and whether an addition step follows it
 KZ_HD int mp_step_of_iter(int it, bool& has_add) {
     const u64 k = ((u64)X_ABS_HI << 32) | X_ABS_LO;

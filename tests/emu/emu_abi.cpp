@@ -16,6 +16,8 @@
 #include "../../kzg_batch_verification_scheme_b200/csrc/cells.cuh"
 #include "../../tools/microbench/fpd.cuh"     // recorded negative result (FP64-limb multiplier): emulation test only, not in the product
 #include "../../kzg_batch_verification_scheme_b200/csrc/blob.cuh"
+#include "../../kzg_batch_verification_scheme_b200/csrc/mpair.cuh"
+#include "../../kzg_batch_verification_scheme_b200/csrc/eip4844.cuh"
 
 struct kzgb_ctx {
     G2Lines lines[2];
@@ -31,6 +33,14 @@ struct kzgb_ctx {
     Fr sum_ry;
     bool have_sums = false;
     size_t sg_min = 0;             // batched subgroup check for batches of at least this many proofs (0 = never)
+    std::vector<G2Lines> mp_tab;   // Horner-free pairing check: lines of [2^(4t)]G2, [2^(4t)][tau]G2, t < 33
+};
+
+// what the device keeps of one sum for the Horner-free pairing check: plan, bucket table, slice sums
+struct EmuSum {
+    MsmPlan plan;
+    std::vector<G1Xyzz> buckets, slices;
+    MpSumDesc desc() const { return {slices.data(), buckets.data(), plan.c, plan.W, plan.nbits}; }
 };
 
 static void words_from_be(u32* w, const u8* in, int nw) {
@@ -42,7 +52,7 @@ static void words_to_be(u8* out, const u32* w, int nw) {
 
 // emulated MSM pipeline: digits -> sort -> bounds -> accumulate -> segments -> window sums -> combine
 // sg_fail != null: also run the batched subgroup check on this sum's buckets (count of slice sums outside G1)
-static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nbits, u32* sg_fail = nullptr) {
+static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nbits, u32* sg_fail = nullptr, EmuSum* keep = nullptr) {
     if (nbits == 255) {      // GLV split exactly as the device pipeline does it
         std::vector<u32> zs(4 * 2 * m);
         std::vector<Fp> p2(2 * 2 * m);
@@ -54,7 +64,7 @@ static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nb
             p2[2 * i] = p.x; p2[2 * i + 1] = p.y;
             p2[2 * (m + i)] = q.x; p2[2 * (m + i) + 1] = q.y;
         }
-        return emu_msm(p2.data(), zs.data(), 4, 2 * m, 128);
+        return emu_msm(p2.data(), zs.data(), 4, 2 * m, 128, nullptr, keep);
     }
     MsmPlan plan = msm_make_plan(m, nbits);
     size_t N = m * (size_t)plan.W;
@@ -104,7 +114,13 @@ static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nb
         for (u32 lane = 0; lane < 5; ++lane)          // any lane count gives the same sum
             acc = xyzz_add(acc, sg_slice_part(tot.data() + (size_t)sl.w * L.tstride, buckets.data() + plan.bucket_off[sl.w], g, sl, lane, 5));
         slices[sid] = acc;
-        if (sg_fail && !sg_sum_in_g1(acc)) *sg_fail += 1;
+        if (sg_fail) {
+            // the device runs the |x|^2 chains on quads (quad.cuh): both forms of the test must agree
+            Quad q = quad_make(nullptr, 0);
+            const bool in1 = sg_sum_in_g1(acc), in2 = quad_sum_in_g1(q, acc);
+            if (in1 != in2) { fprintf(stderr, "emu: quad and one-thread subgroup tests differ on slice %d\n", sid); abort(); }
+            if (!in1) *sg_fail += 1;
+        }
     }
     for (int w = 0; w < plan.W; ++w) {
         const SgWin g = sg_win(plan, w);
@@ -116,7 +132,62 @@ static G1Jac emu_msm(const Fp* pts, const u32* scalars, int nl, size_t m, int nb
         bool same = jac_is_inf(a) ? jac_is_inf(c2) : (!jac_is_inf(c2) && aff_is_inf(jac_to_aff(jac_add(a, jac_neg(c2)))));
         if (!same) { fprintf(stderr, "emu: window %d total differs\n", w); abort(); }
     }
+    if (keep) { keep->plan = plan; keep->buckets = buckets; keep->slices = slices; }
     return msm_combine_body(wins.data(), plan.W, plan.c);
+}
+
+// ---- Horner-free pairing check (mpair.cuh) restated sequentially: the same terms, coefficients, line values and final
+// check as k_mp_terms / k_mp_coefs / k_mp_lines / k_mp_check, without the chunked merging of Miller iterations (which
+// only regroups the same product).  tab = 66 line tables, sums d1 + d2 on the A side, d3 (negated) on the B side.
+static bool emu_mp_setup(std::vector<G2Lines>& tab, const u8* g2_two_points) {
+    tab.resize(KZ_MP_PAIRS);
+    for (int b = 0; b < 2; ++b) {
+        G2Aff q;
+        if (!g2_decompress(q, g2_two_points + 96 * b)) return false;
+        Fp2 la, lb;
+        for (int t = 0; t < KZ_MP_TERMS; ++t) {
+            G2Aff out;
+            if (!g2_mul_xabs(out, q, &tab[b * KZ_MP_TERMS + t])) return false;
+            for (int u = 0; u < KZ_MP_G && t + 1 < KZ_MP_TERMS; ++u)
+                if (!g2_dbl_step(q, la, lb)) return false;
+        }
+    }
+    return true;
+}
+static bool emu_mp_check(const std::vector<G2Lines>& tab, const MpSumDesc& d1, const MpSumDesc& d2, const MpSumDesc& d3) {
+    Quad q = quad_make(nullptr, 0);
+    std::vector<MpCoef> coef(KZ_MP_PAIRS);
+    for (int t = 0; t < KZ_MP_TERMS; ++t) {
+        G1Xyzz a = quad_xyzz_add(q, mp_term(q, d1, t), mp_term(q, d2, t));
+        coef[t] = mp_coef_of(q, a);
+        coef[KZ_MP_TERMS + t] = mp_coef_of(q, xyzz_neg(mp_term(q, d3, t)));
+    }
+    static MpScratch S;
+    mp_unit_init(S.U);
+    auto line_product = [&](int s) {
+        Fp12 acc;
+        for (int p = 0; p < KZ_MP_PAIRS; ++p) {
+            Fp12 l;
+            for (int ci = 0; ci < 12; ++ci) {
+                Fp v = mp_line_coeff(tab[p], s, coef[p], ci);
+                if (ci & 1) l.c[ci >> 1].c1 = v; else l.c[ci >> 1].c0 = v;
+            }
+            if (p == 0) acc = l; else mp_mul(S.U, acc, acc, l);
+        }
+        return acc;
+    };
+    Fp12 f;
+    for (int it = 0; it < KZ_MP_ITERS; ++it) {
+        bool has_add;
+        const int s0 = mp_step_of_iter(it, has_add);
+        Fp12 F = line_product(s0);
+        if (has_add) { Fp12 G = line_product(s0 + 1); mp_mul(S.U, F, F, G); }
+        if (it == 0) f = F;
+        else { mp_mul(S.U, f, f, f); mp_mul(S.U, f, f, F); }
+    }
+    coop_conj(S.f, f);
+    mp_final_check(S);
+    return S.result == 1;
 }
 
 extern "C" {
@@ -130,6 +201,7 @@ kzgb_ret kzgb_ctx_create(kzgb_ctx** out, const uint8_t* g1m, size_t n1, const ui
     words_from_be(w, g1m, 12);
     bool ok = g1_decompress_validate(c->g1, w) == ST_OK && !aff_is_inf(c->g1);
     ok = ok && g2_setup_point(c->lines[0], g2m) && g2_setup_point(c->lines[1], g2m + 96);
+    ok = ok && emu_mp_setup(c->mp_tab, g2m);
     if (!ok) { delete c; return KZGB_BADARGS; }
     if (n1 >= 64 && n2 >= 65) {
         c->cell_g1.resize(64);
@@ -264,8 +336,9 @@ static kzgb_ret emu_verify(bool* ok, const u8* C, const u8* z, const u8* y, cons
     Fr neg = fr_neg(sum);
     for (int k = 0; k < 8; ++k) rz[8 * n + k] = neg.v[k];
     pts[2 * 2 * n] = c->g1.x; pts[2 * 2 * n + 1] = c->g1.y;
-    c->sums[0] = emu_msm(pts.data(), r.data(), 4, n, 128, sg_batch ? &sg_fail : nullptr);
-    c->sums[2] = emu_msm(pts.data() + 2 * n, r.data(), 4, n, 128, sg_batch ? &sg_fail : nullptr);
+    EmuSum k1, k2, k3;
+    c->sums[0] = emu_msm(pts.data(), r.data(), 4, n, 128, sg_batch ? &sg_fail : nullptr, &k1);
+    c->sums[2] = emu_msm(pts.data() + 2 * n, r.data(), 4, n, 128, sg_batch ? &sg_fail : nullptr, &k3);
     if (sg_fail) {           // a slice sum left G1: the per-point check names the offenders
         for (size_t i = 0; i < 2 * n; ++i) {
             G1Aff p = load_point(pts.data(), i);
@@ -274,13 +347,16 @@ static kzgb_ret emu_verify(bool* ok, const u8* C, const u8* z, const u8* y, cons
         c->art.n_bad_points = badp;
         return KZGB_BADARGS;
     }
-    c->sums[1] = emu_msm(pts.data() + 2 * n, rz.data(), 8, n + 1, 255);
+    c->sums[1] = emu_msm(pts.data() + 2 * n, rz.data(), 8, n + 1, 255, nullptr, &k2);
     c->sum_ry = sum;
     c->have_sums = true;
     G1Jac AB[2] = {jac_add(c->sums[0], c->sums[1]), jac_neg(c->sums[2])};
     PairScratch S;
     coop_pairing_check(S, c->lines, AB);
     *ok = S.result == 1;
+    // the product's default path: multi-pairing over the slice-sum terms, inversion-free final check -- same verdict
+    const bool ok2 = emu_mp_check(c->mp_tab, k1.desc(), k2.desc(), k3.desc());
+    if (ok2 != *ok) { fprintf(stderr, "emu: Horner-free pairing check (%d) and two-pairing kernel (%d) disagree\n", (int)ok2, (int)*ok); abort(); }
     return KZGB_OK;
 }
 kzgb_ret verify_kzg_proof(bool* ok, const uint8_t C[48], const uint8_t z[32], const uint8_t y[32], const uint8_t pi[48], kzgb_ctx* c) {
