@@ -487,11 +487,13 @@ def main():
                 # several batches in flight through the LIBRARY's submit / wait API (one context, one caller thread): the
                 # latency-bound tail (bucket reduction, pairing) of batch k runs under K1 of batch k+1
                 pipe = {}
-                for lg, nb in ((12, 48), (16, 36), (args.n, 8)):
+                for lg, nb in ((12, 96), (16, 36), (args.n, 8)):
                     if lg > args.n:
                         continue
                     npl = 1 << lg
-                    depth = 3 if lg <= 16 else 2
+                    # small batches are bound by the one-SM serial pairing kernel (0.7 ms): more of them in flight run those
+                    # kernels side by side on different SMs
+                    depth = 8 if lg <= 12 else 3 if lg <= 16 else 2
                     assert ctx.pipeline_init(depth) == 0
 
                     def run(count):
