@@ -350,7 +350,8 @@ def main():
     nch = (n_local + CHUNK - 1) // CHUNK
 
     extras, configs = {}, {}
-    roofline = roofline_hbm = cpu_baseline = None
+    roofline = roofline_hbm = roofline_hbm_k6 = cpu_baseline = None
+    msm_top = {}
     if rank == 0:
         peaks_path = ROOT / "MEASURED_PEAKS.json"
         peaks = json.loads(peaks_path.read_text()) if peaks_path.exists() else {}
@@ -410,6 +411,19 @@ def main():
                             "unit": "GB/s", "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                             "note": "K1 is integer-pipe bound by construction (hundreds of Fp products per ~150-625 bytes moved); HBM fraction reported for completeness"}
+            # K6 point stream (BJ:5 "achieved HBM GB/s for the point stream"): every sorted entry reads its key, value and one 96-byte
+            # affine point; 4 n W entries over the three sums (S2' has 2(n+1) points).  Measured DRAM traffic of pass 1 is 1.5x
+            # this (points on 16-byte alignment straddle 32-byte sectors: profiles/r2_k6_accumulate_pass1_ncu_full_n1048576.txt)
+            acc_ms = stages.get("msm_accumulate", 0.0)
+            if acc_ms > 0:
+                from math import ceil, log2
+                c_w = max(3, min(16, int(log2(max(n_local, 2))) - 3))
+                entries = (2 * n_local + 2 * (n_local + 1)) * ceil(128 / c_w)
+                k6_bytes = entries * (96 + 8)
+                roofline_hbm_k6 = {"bound": "hbm", "kernel": "K6 accumulate (pass 1 + pass 2 + slice sums of the three sums)", "achieved": k6_bytes / (acc_ms * 1e-3) / 1e9,
+                                   "peak": hbm_peak, "unit": "GB/s", "frac": k6_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak,
+                                   "algorithmic_bytes": k6_bytes, "stage_ms": acc_ms,
+                                   "note": "integer-pipe bound (2868 multiply-adds per 104 bytes); reported because BASELINE.json:5 asks for it"}
         if not args.no_extras:
             # CPU baseline: oracle port on the box's host cores, bounded sample (~10-20 s)
             try:
@@ -540,6 +554,17 @@ def main():
                     extras[f"msm_{nbits}bit_ms"] = {"sort": best[0], "accumulate": best[1], "reduce": best[2], "total": best[3]}
                     ipp = 52.2e3 if nbits == 255 else 29.4e3          # SURVEY 8(d) multiply-adds per point at c=16
                     extras[f"msm_{nbits}bit_imad_frac"] = m * ipp / (best[3] * 1e-3) / imad_peak
+                    msm_top[f"{nbits}bit_2^20"] = {"mpts_per_s": m / (best[3] * 1e-3) / 1e6, "ms": best[3],
+                                                   "imad_frac_survey_model": m * ipp / (best[3] * 1e-3) / imad_peak}
+                    # the same at m = 2^16
+                    m16 = 1 << 16
+                    b16 = None
+                    for _ in range(3):
+                        rc, out = ctx.g1_msm(aff[:96 * m16], sc[:m16].tobytes(), nbits)
+                        assert rc == 0
+                        t = ctx.g1_msm_times()
+                        b16 = t if b16 is None or t[3] < b16[3] else b16
+                    msm_top[f"{nbits}bit_2^16"] = {"mpts_per_s": m16 / (b16[3] * 1e-3) / 1e6, "ms": b16[3]}
                 # blob-level caller: 1024 blobs of 128 KiB from pinned host memory.  Random
                 # evaluations with unrelated (valid) commitments and proofs: same work, verdict "false"
                 mb = 1024
@@ -579,7 +604,8 @@ def main():
             "e2e_pinned": {"value": n_total / (ms_pin * 1e-3), "unit": "proofs/s", "ms_per_step": ms_pin, "host_memory": "pinned"},
             "gpu_launches": launches,
             "stage_ms": stages,
-            "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_hbm_k6": roofline_hbm_k6, "cpu_baseline": cpu_baseline,
+            "msm": msm_top,
             "planted_invalid_rejected": reject_ok,
             "configs": configs,
             "extras": extras,
