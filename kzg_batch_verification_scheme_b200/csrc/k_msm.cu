@@ -406,6 +406,10 @@ static u32 msm_chunk_len_plan(const MsmPlan& plan, size_t m) {
     }();
     static const int tune = [] { const char* e = getenv("KZGB_ACC_WAVE_TUNE"); return e ? atoi(e) : 1; }();
     const size_t N = m * (size_t)plan.W;
+    // Very large sums (the window width is capped at 16, so buckets hold hundreds of entries from m = 2^22 on): with L = 32 a
+    // bucket straddles dozens of chunks and pass 2 adds their records one after the other on ONE lane (m = 2^24, 255-bit:
+    // 238 ms instead of ~110).  Grow the chunk until a bucket spans ~4 chunks, keeping at least 8 waves of pass-1 threads.
+    while (L < 1024 && (double)L < heavy / 4.0 && N / (2 * (size_t)L) >= 8 * (size_t)per_wave * 32 * KZ_ACC_WARPS) L <<= 1;
     if (tune && N / L / 128 < 12 * (size_t)per_wave) {
         u32 bestL = L;
         double best = 1e300;
