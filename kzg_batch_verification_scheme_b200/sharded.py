@@ -45,7 +45,9 @@ class HostMailbox:
         size = self.region * self.KINDS * 2
         names = [None]
         if rank == 0:
-            names[0] = f"/dev/shm/kzgb200_{tag or os.environ.get('MASTER_PORT', '0')}_{os.getpid()}"
+            import tempfile
+            base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+            names[0] = os.path.join(base, f"kzgb200_{tag or os.environ.get('MASTER_PORT', '0')}_{os.getpid()}")
             with open(names[0], "wb") as f:
                 f.truncate(size)
         if world > 1:
