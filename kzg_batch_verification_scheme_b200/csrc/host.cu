@@ -109,7 +109,12 @@ struct DeviceSlot {
     uint8_t* h_digests = nullptr;      // 32 * ceil(n_max/KZGB_CHUNK)
     uint32_t* h_small = nullptr;       // 64 words: [0..2] counters, [8..15] root words, [16] result
     uint8_t* h_partial = nullptr;      // 320 * 64
-    cudaEvent_t ev[28] = {};
+    cudaEvent_t ev[32] = {};
+    cudaStream_t stream6 = nullptr;    // high priority: S1 when it starts under K1 of the proofs (s1_early)
+    bool s1_early = false;             // current shard: K1 ran commitments first and recorded ev[26] (+ ev[29]) when they were done
+    bool c_done_two = false;           // ... on two streams (host pieces alternate): ev[29] as well
+    bool s1_early_enabled = true;      // KZGB_S1_EARLY=0 switches the overlap off
+    bool s1_early_force = false;       // KZGB_S1_EARLY=3: for every shard of >= 16384 proofs (measurement)
     // current shard (between phase 1 and phase 2)
     const uint8_t *cur_C = nullptr, *cur_z = nullptr, *cur_y = nullptr, *cur_pi = nullptr;
     size_t cur_n = 0;
@@ -238,6 +243,8 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
         CK(cudaStreamCreateWithFlags(&s.stream3, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&s.stream4, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&s.stream5, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&s.stream6, cudaStreamNonBlocking, hi_pri));
+        { const char* e = getenv("KZGB_S1_EARLY"); s.s1_early_enabled = !(e && atoi(e) == 0); s.s1_early_force = e && atoi(e) == 3; }
     }
     for (auto& e : s.ev) CK(cudaEventCreate(&e));
     CK(dmalloc(s.dC, 48 * (n_max + 1))); CK(dmalloc(s.dz, 32 * (n_max + 1))); CK(dmalloc(s.dy, 32 * (n_max + 1))); CK(dmalloc(s.dpi, 48 * (n_max + 1)));
@@ -376,6 +383,7 @@ void slot_free(DeviceSlot& s) {
     if (s.stream3) cudaStreamDestroy(s.stream3);
     if (s.stream4) cudaStreamDestroy(s.stream4);
     if (s.stream5) cudaStreamDestroy(s.stream5);
+    if (s.stream6) cudaStreamDestroy(s.stream6);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -433,6 +441,15 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
     s.sums_pending = false;
     s.have_ab = false;
     s.head_mode = false;
+    // Mid-size shards decompress the commitments first and record when they are done: sum r_i C_i (S1) then accumulates
+    // and reduces UNDER K1 of the proofs on a high-priority stream, so its latency-bound tail and the idle partial waves
+    // of its kernels cost nothing.  Measured on B200 (device-resident, ms without / with): n = 24576 2.54 / 2.55,
+    // 49152 3.81 / 3.80, 65536 4.71 / 4.46, 81920 5.43 / 5.17, 98304 5.77 / 5.75, 131072 7.16 / 7.22, 2^18 12.57 / 12.88,
+    // 2^20 44.65 / 44.81 -- it pays where K1 is a few waves long and the reduction tails are a large share; for larger
+    // shards the mixed residency (232-register accumulation blocks displacing 142-register K1 blocks) costs more than the
+    // tails save.  KZGB_S1_EARLY=0 switches it off, =3 forces it for every shard of >= 16384 proofs.
+    s.s1_early = s.s1_early_enabled && s.sg_batch && ((n >= 57344 && n <= 90112) || (s.s1_early_force && n >= 16384));
+    s.c_done_two = false;
     if (on_device) {
         s.cur_C = C; s.cur_z = z; s.cur_y = y; s.cur_pi = pi;
         CK(cudaEventRecord(s.ev[1], st));                // inputs already resident
@@ -442,9 +459,18 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
         launch_leaf_hash(s2, C, z, y, pi, n, s.leaves, s.counters);
         launch_chunk_hash(s2, s.leaves, n, s.digests);
         if (s.sg_batch) {
-            // ONE launch over both arrays: every launch boundary costs the idle tail of a partial wave (2n points are
-            // 36.9 waves of 148 x 384 threads at n = 2^20, two launches of n points 2 x 18.5 -> 38)
-            launch_decompress_sqrt(st, C, pi, n, s.pts, s.status, s.counters);
+            if (s.s1_early) {
+                // commitments, then proofs on a second stream (its blocks fill the tail of the first launch)
+                launch_decompress_sqrt_points(st, C, n, s.pts, s.status, s.counters);
+                CK(cudaEventRecord(s.ev[26], st));
+                CK(cudaStreamWaitEvent(s.stream5, s.ev[1], 0));
+                launch_decompress_sqrt_points(s.stream5, pi, n, s.pts + 2 * n, s.status + n, s.counters);
+                CK(cudaEventRecord(s.ev[25], s.stream5));
+                CK(cudaStreamWaitEvent(st, s.ev[25], 0));
+            } else {
+                // ONE launch over both arrays: every launch boundary costs the idle tail of a partial wave
+                launch_decompress_sqrt(st, C, pi, n, s.pts, s.status, s.counters);
+            }
         } else {
             launch_decompress(st, C, pi, n, s.pts, s.k1_tmp, s.status, s.counters);
         }
@@ -479,6 +505,10 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
                 launch_decompress_sqrt_points(ks, s.dC + 48 * a, m, s.pts + 2 * a, s.status + a, s.counters);
             }
         }
+        if (s.head_mode && s.s1_early) {                 // commitments decompressed: on the main stream, and on stream5 if a piece ran there
+            CK(cudaEventRecord(s.ev[26], st));
+            if (ncut >= 2) { CK(cudaEventRecord(s.ev[29], s.stream5)); s.c_done_two = true; }
+        }
         CK(cudaMemcpyAsync(s.dpi, pi, 48 * n, cudaMemcpyHostToDevice, s2));
         CK(cudaEventRecord(s.ev[22], s2));               // pi resident
         CK(cudaStreamWaitEvent(st, s.ev[1], 0));
@@ -489,6 +519,10 @@ kzgb_ret phase1(DeviceSlot& s, const uint8_t* C, const uint8_t* z, const uint8_t
             launch_decompress_sqrt_points(ks, s.dpi, n, s.pts + 2 * n, s.status + n, s.counters);
             CK(cudaEventRecord(s.ev[25], s.stream5));
             CK(cudaStreamWaitEvent(st, s.ev[25], 0));   // every piece has finished before the main stream goes on
+        } else if (s.sg_batch && s.s1_early) {
+            launch_decompress_sqrt_points(st, s.dC, n, s.pts, s.status, s.counters);
+            CK(cudaEventRecord(s.ev[26], st));
+            launch_decompress_sqrt_points(st, s.dpi, n, s.pts + 2 * n, s.status + n, s.counters);
         } else if (s.sg_batch) {
             launch_decompress_sqrt(st, s.dC, s.dpi, n, s.pts, s.status, s.counters);
         } else {
@@ -532,6 +566,7 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     if (!shard_fits(s, n)) return KZGB_ERROR;            // checked in phase 1 already; never reached after a successful phase 1
     MsmWorkspace wr = make_ws(s, s.sortR, s.bucketsA), wz = make_ws(s, s.sortZ, s.bucketsC);
     msm_sort_stage(s2, s.planR, s.r, 4, n, wr);
+    CK(cudaEventRecord(s.ev[28], s2));                   // digits of the r_i sorted: S1 can start once the commitments are decompressed
     msm_sort_stage(s2, s.planZ, s.zs, 4, 2 * (n + 1), wz);
     save_ws(s.sortR, wr); save_ws(s.sortZ, wz);
     CK(cudaEventRecord(s.ev[5], s2));
@@ -545,11 +580,18 @@ kzgb_ret phase2(DeviceSlot& s, const uint8_t root[32], uint64_t global_offset, b
     wr2.sg_work = s.sg_partial + s.sg_cap; wr2.slices = wr2.sg_work + s.sg_cap - 256;
     wz.sg_work = s.sg_partial + 2 * s.sg_cap; wz.slices = wz.sg_work + s.sg_cap - 256;
     // Longest chain (S2', twice the points) first, all three sums at normal priority.
-    cudaStream_t sS3 = s.stream3, sS1 = s.stream5;
+    const bool early = s.s1_early && !classic;
+    cudaStream_t sS3 = s.stream3, sS1 = early ? s.stream6 : s.stream5;
     CK(cudaEventRecord(s.ev[11], st));
     CK(cudaStreamWaitEvent(sS3, s.ev[11], 0));
     CK(cudaStreamWaitEvent(s.stream4, s.ev[11], 0));
-    CK(cudaStreamWaitEvent(sS1, s.ev[11], 0));
+    if (early) {
+        CK(cudaStreamWaitEvent(sS1, s.ev[28], 0));
+        CK(cudaStreamWaitEvent(sS1, s.ev[26], 0));
+        if (s.c_done_two) CK(cudaStreamWaitEvent(sS1, s.ev[29], 0));
+    } else {
+        CK(cudaStreamWaitEvent(sS1, s.ev[11], 0));
+    }
     auto reduce = [&](cudaStream_t q, const MsmPlan& plan, MsmWorkspace& w, bool want_all) {
         if (classic) msm_window_sums_stage(q, plan, w, want_all); else msm_slices_stage(q, plan, w, want_all);
     };
