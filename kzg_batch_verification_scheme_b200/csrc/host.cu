@@ -111,6 +111,11 @@ struct DeviceSlot {
     uint8_t* h_partial = nullptr;      // 320 * 64
     cudaEvent_t ev[32] = {};
     cudaStream_t stream6 = nullptr;    // high priority: S1 when it starts under K1 of the proofs (s1_early)
+    // the fixed tail of every batch -- coefficients, line products, merge, serial check, verdict D2H -- as ONE CUDA graph
+    // per (terms buffer, shard count, line table); KZGB_NO_GRAPH=1 launches the four kernels one by one
+    struct TailGraph { const void* terms; int n_shards; const void* tab; cudaGraphExec_t exec; };
+    std::vector<TailGraph> tail_graphs;
+    bool use_graph = true;
     bool s1_early = false;             // current shard: K1 ran commitments first and recorded ev[26] (+ ev[29]) when they were done
     bool c_done_two = false;           // ... on two streams (host pieces alternate): ev[29] as well
     bool s1_early_enabled = true;      // KZGB_S1_EARLY=0 switches the overlap off
@@ -244,6 +249,7 @@ kzgb_ret slot_init(DeviceSlot& s, int device, size_t n_max, const uint8_t* g1m, 
         CK(cudaStreamCreateWithFlags(&s.stream4, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&s.stream5, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithPriority(&s.stream6, cudaStreamNonBlocking, hi_pri));
+        { const char* e = getenv("KZGB_NO_GRAPH"); s.use_graph = !(e && atoi(e) != 0); }
         { const char* e = getenv("KZGB_S1_EARLY"); s.s1_early_enabled = !(e && atoi(e) == 0); s.s1_early_force = e && atoi(e) == 3; }
     }
     for (auto& e : s.ev) CK(cudaEventCreate(&e));
@@ -378,6 +384,8 @@ void slot_free(DeviceSlot& s) {
     if (s.h_small) cudaFreeHost(s.h_small);
     if (s.h_partial) cudaFreeHost(s.h_partial);
     if (s.h_terms) cudaFreeHost(s.h_terms);
+    for (auto& g : s.tail_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    s.tail_graphs.clear();
     for (auto& e : s.ev) if (e) cudaEventDestroy(e);
     if (s.stream2) cudaStreamDestroy(s.stream2);
     if (s.stream3) cudaStreamDestroy(s.stream3);
@@ -689,9 +697,31 @@ kzgb_ret combine(DeviceSlot& s, const uint8_t* partials, int np, bool* ok) {
 // Pairing check on the terms of n_shards shards resident in terms_dev (device memory of s)
 kzgb_ret mp_finish(DeviceSlot& s, const G1Xyzz* terms_dev, int n_shards, const G2Lines* tab, bool* ok) {
     cudaStream_t st = s.stream;
-    launch_mp_coefs(st, terms_dev, n_shards, s.mp_coef);
-    launch_mp_check(st, tab, s.mp_coef, s.mp_part, s.mp_F, s.result_dev);
-    CK(cudaMemcpyAsync(s.h_small + 16, s.result_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    cudaGraphExec_t exec = nullptr;
+    if (s.use_graph) {
+        for (auto& g : s.tail_graphs)
+            if (g.terms == terms_dev && g.n_shards == n_shards && g.tab == tab) exec = g.exec;
+        if (!exec) {
+            // first use with these arguments: capture the sequence (nothing else is queued on a capturing stream meanwhile:
+            // one in-flight call per slot), instantiate, keep
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            launch_mp_coefs(st, terms_dev, n_shards, s.mp_coef);
+            launch_mp_check(st, tab, s.mp_coef, s.mp_part, s.mp_F, s.result_dev);
+            cudaMemcpyAsync(s.h_small + 16, s.result_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
+            CK(cudaStreamEndCapture(st, &graph));
+            g_kzgb_launches.fetch_sub(4, std::memory_order_relaxed);   // the four kernels were captured, not launched
+            CK(cudaGraphInstantiate(&exec, graph, 0));
+            CK(cudaGraphDestroy(graph));
+            s.tail_graphs.push_back({terms_dev, n_shards, tab, exec});
+        }
+        CK(cudaGraphLaunch(exec, st));
+        g_kzgb_launches.fetch_add(4, std::memory_order_relaxed);   // k_mp_coefs, k_mp_lines, k_mp_merge, k_mp_check
+    } else {
+        launch_mp_coefs(st, terms_dev, n_shards, s.mp_coef);
+        launch_mp_check(st, tab, s.mp_coef, s.mp_part, s.mp_F, s.result_dev);
+        CK(cudaMemcpyAsync(s.h_small + 16, s.result_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaEventRecord(s.ev[8], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
