@@ -211,6 +211,7 @@ def main():
         torch.cuda.synchronize()
         if multi:
             dist.barrier()
+            box.barrier()            # shared-memory rendezvous right after: the ranks leave within microseconds of each other
         torch.cuda.synchronize()
 
     def step(w, ptrs, on_device):

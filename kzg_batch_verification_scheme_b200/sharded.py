@@ -35,7 +35,7 @@ class HostMailbox:
     followed by `world` payload slots.  A rank publishes by copying its payload into its slot and then storing the
     sequence number into its flag (x86 keeps the store order); readers poll the flags.  Every verification ends with
     an all-gather, so a slot is never rewritten before all ranks have read it."""
-    KINDS = 3
+    KINDS = 4            # digests, terms / partials, verdicts, barrier
 
     def __init__(self, dist, rank: int, world: int, max_n_local: int, tag: str | None = None):
         self.rank, self.world = rank, world
@@ -87,6 +87,10 @@ class HostMailbox:
         self.mm[off:off + n] = payload
         self.flags[kind][p][self.rank] = seq
         return seq
+
+    def barrier(self):
+        """All ranks have arrived (microseconds of skew; the gloo barrier releases ranks tens of microseconds apart)."""
+        self.collect(3, self.post(3, b""), 0)
 
     def collect(self, kind: int, seq: int, nbytes: int, timeout_s: float = 120.0):
         """Wait until every rank has published exchange `seq` of `kind`; returns one memoryview per rank."""

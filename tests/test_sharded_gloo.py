@@ -24,6 +24,8 @@ from kzg_batch_verification_scheme_b200.sharded import HostMailbox
 n_local, seed = 1024, 0x4B5A4705
 mailbox = HostMailbox(dist, rank, world, 2 * n_local, tag="test%d" % world)
 full = lib.test_context()
+for _ in range(3):
+    mailbox.barrier()
 for box, mode in ((None, "terms"), (None, "partials"), (mailbox, "terms"), (mailbox, "partials")):
     C, Z, Y, PI = ctx.synth_instance(seed, rank * n_local, n_local)
     rc, ok = sharded_verify(ctx, dist, rank, world, C, Z, Y, PI, n_local, box=box, mode=mode)
