@@ -69,7 +69,9 @@ kzgb_ret verify_kzg_proof_batch(bool *ok, const uint8_t *C /*48n*/, const uint8_
 /* ---- cell batch (BASELINE.json config[4]): m multi-point openings on cosets of 64 points
  * (PeerDAS-shaped; conventions in DESIGN.md "Cell batch").  commitments: nc unique 48-byte G1; opening k refers to
  * commitments[commitment_indices[k]] and cell cell_indices[k] (< 128), carries 64 evaluations (32 B big-endian each,
- * < r) and one proof.  Needs a context created with n1 >= 64 ([tau^j]G1) and n2 >= 65 ([tau^64]G2). */
+ * < r) and one proof.  Needs a context created with n1 >= 64 ([tau^j]G1) and n2 >= 65 ([tau^64]G2).  A context over several
+ * devices shards the openings over them (contiguous ranges of at least 1024 openings, multiples of KZGB_CHUNK); the result
+ * does not depend on the device count. */
 kzgb_ret verify_cell_kzg_proof_batch(bool *ok, const uint8_t *commitments /*48 nc*/, size_t nc,
                                      const uint32_t *commitment_indices /*m*/, const uint32_t *cell_indices /*m*/,
                                      const uint8_t *cells /*2048 m*/, const uint8_t *proofs /*48 m*/, size_t m, kzgb_ctx *ctx);
